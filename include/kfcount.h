@@ -1,0 +1,123 @@
+/*
+ * kfcount.h -- C ABI of libkfcount.so, the B200-native k-mer frequency engine.
+ *
+ * This is the drop-in boundary for kf2vec's k-mer frequency step.  The reference has no FFI of its
+ * own: its boundary is the Python callable get_frequencies(args) (kf2vec/main.py:250-373), which
+ * shells out to `jellyfish count -m k -s 100M -t p -C` (main.py:308-311) and `jellyfish dump -c`
+ * (main.py:317-319) per input file and post-processes with pandas (main.py:323-357).  Every entry
+ * point below names the reference lines it replaces.  INTEGRATION.md shows the ctypes stub a
+ * kf2vec maintainer would add.
+ *
+ * Conventions: plain C types only; caller allocates every output; return 0 (KF_OK) or a negative
+ * KF_ERR_* code; no exceptions cross the boundary; "d_" parameters are device pointers on the
+ * device selected by kf_init, everything else is host memory.  There is no CPU fallback: without a
+ * usable CUDA device every compute entry point returns KF_ERR_NO_DEVICE.
+ */
+#ifndef KFCOUNT_H
+#define KFCOUNT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KF_ABI_VERSION 1
+
+/* error codes */
+#define KF_OK 0
+#define KF_ERR_ARG (-1)          /* bad argument (k out of range, null pointer, ...) */
+#define KF_ERR_NO_DEVICE (-2)    /* no CUDA device / kf_init not called / wrong architecture */
+#define KF_ERR_CUDA (-3)         /* a CUDA runtime call failed; kf_last_cuda_error() has the text */
+#define KF_ERR_IO (-4)           /* file could not be read / written */
+#define KF_ERR_FORMAT (-5)       /* first byte is neither '>' nor '@' (jellyfish: "unsupported format") */
+#define KF_ERR_FASTQ (-6)        /* FASTQ is not in 4-line layout (multi-line FASTQ is not supported on GPU) */
+#define KF_ERR_NOMEM (-7)        /* host or device allocation failed */
+#define KF_ERR_LAYOUT (-8)       /* device arena violates the layout contract of kf_count_device */
+#define KF_ERR_EMPTY (-9)        /* zero-length input (jellyfish fails on it; the reference then crashes) */
+
+/* flags (bit set) */
+#define KF_FLAG_PSEUDOCOUNT 1u   /* main.py:332-334  counts += 0.5 before normalising           */
+#define KF_FLAG_RAW_CNT 2u       /* main.py:340-342  skip the normalisation                      */
+#define KF_FLAG_FORCE_WALKER 4u  /* debug: disable the vectorised fast path (byte walker only)   */
+
+/* limits */
+#define KF_MIN_K 1
+#define KF_MAX_K 12              /* dense canonical output up to k=12 (8,390,656 columns)        */
+#define KF_MAX_K_SMEM 7          /* 4^k u32 bins privatised in shared memory up to here          */
+#define KF_CHUNK 512             /* arena alignment unit: one warp-load of 32 x 16 bytes         */
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+/* Selects the CUDA device, checks it is sm_100, creates the library's stream and workspace.
+ * Replaces nothing in the reference (Jellyfish needs no init); one call per process/rank. */
+int kf_init(int device);
+int kf_shutdown(void);
+int kf_device(void);                       /* device chosen by kf_init, or KF_ERR_NO_DEVICE       */
+const char *kf_strerror(int code);
+const char *kf_last_cuda_error(void);
+int kf_abi_version(void);
+
+/* ---- vocabulary: kf2vec/data/<vocab file> + main.py:278-296 ----------------------------------- */
+/* Number of canonical k-mers = number of columns of a .kf row: (4^k + [k even] 4^(k/2)) / 2. */
+int64_t kf_vocab_size(int k);
+/* Writes the sorted canonical k-mers, one per line ("AAAAAAA\n..."), V*(k+1) bytes, to out. */
+int kf_vocab(int k, char *out, size_t out_len);
+/* canonical 2-bit codes (A0 C1 G2 T3, first base most significant) in column order */
+int kf_vocab_codes(int k, uint32_t *out, size_t n_out);
+
+/* ---- counting, host buffers in / host rows out (the end-to-end call) -------------------------- */
+/* Replaces, per input i, `jellyfish count -C` + `jellyfish dump -c` + vocabulary merge + pseudocount
+ * + normalise (main.py:308-342).  bufs[i] holds the raw bytes of one .fa/.fna/.fasta/.fq/.fastq file.
+ *   counts_out [n][V] uint64  canonical counts in vocabulary order              (may be NULL)
+ *   freq_out   [n][V] double  c/sum(c), or c (+0.5) with KF_FLAG_RAW_CNT         (may be NULL)
+ *   totals_out [n]    uint64  number of valid k-mers                             (may be NULL)
+ *   status_out [n]    int     KF_OK or the per-file error                        (required)
+ * Host->device copies, all kernels and device->host copies happen inside the call. */
+int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens, int n, int k, uint32_t flags,
+                     uint64_t *counts_out, double *freq_out, uint64_t *totals_out, int *status_out);
+
+/* Same, reading the files itself (the loop body of main.py:301-357 without the text formatting). */
+int kf_count_files(const char *const *paths, int n, int k, uint32_t flags,
+                   uint64_t *counts_out, double *freq_out, uint64_t *totals_out, int *status_out);
+
+/* ---- counting, device-resident arena (kernel-only path; trainer hand-off) --------------------- */
+/* Arena layout contract: file i occupies d_arena[offsets[i] .. offsets[i]+lens[i]); offsets[i] is a
+ * multiple of KF_CHUNK; files are in increasing offset order and do not overlap; every byte of the
+ * arena that belongs to no file is 0; at least 2*KF_CHUNK zero bytes follow the last file
+ * (arena_bytes says how much is allocated).  formats[i] is '>' or '@' (first byte of file i).
+ * Outputs are device pointers (any may be NULL): d_counts [n][V] uint64, d_freq [n][V] double,
+ * d_feat [n][V] float = fp32(freq * 1e4) (train_classifier_model.py:149,323), d_totals [n] uint64.
+ * Work is enqueued on `stream` (a cudaStream_t; NULL = the library's stream) and NOT synchronised. */
+int kf_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *offsets,
+                    const uint64_t *lens, const uint8_t *formats, int n, int k, uint32_t flags,
+                    uint64_t *d_counts, double *d_freq, float *d_feat, uint64_t *d_totals,
+                    void *stream);
+/* Number of kernels kf_count_device launched in its last call (for bench.py's gpu_launches). */
+int kf_last_launch_count(void);
+
+/* ---- .kf writer: main.py:344-357 --------------------------------------------------------------- */
+/* Formats one row exactly as pandas `astype(str)` + ",".join does (Python repr of float64: shortest
+ * round-trip digits, exponent form when exp10 < -4 or >= 16, "nan" for 0/0).  int_mode != 0 prints
+ * integers ("5" not "5.0"): the reference's dtype quirk for -raw_cnt rows with no missing k-mer.
+ * Returns the number of bytes written (excluding the NUL) or a negative error. */
+int64_t kf_format_row(const char *sample, const double *row, int64_t V, int int_mode, char *out,
+                      size_t out_len);
+int kf_write_kf(const char *out_path, const char *sample, const double *row, int64_t V, int int_mode,
+                int append);
+
+/* ---- synthetic inputs (bench / tests) ---------------------- */
+/* Deterministic bacterial-size FASTA: GC ~ U(0.30,0.70) from seed, n_bases split into 1..50 contigs,
+ * 10 N-runs of 1..100, upper case, line_width-column lines, LF, header ">g<id>_c<j> synthetic".
+ * Call with out == NULL to get the exact size.  Returns bytes written or a negative error. */
+int64_t kf_synth_fasta(uint64_t seed, int64_t genome_id, int64_t n_bases, int line_width, uint8_t *out,
+                       size_t out_len);
+/* 4-line FASTQ: n_reads x read_len sampled from a seed-derived genome of genome_len bases, random
+ * strand, per-base N 0.2 %, 1 % of reads with an N-run, qualities '!'..'J' (may start with '@'/'+'). */
+int64_t kf_synth_fastq(uint64_t seed, int64_t sample_id, int64_t genome_len, int64_t n_reads,
+                       int read_len, uint8_t *out, size_t out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFCOUNT_H */

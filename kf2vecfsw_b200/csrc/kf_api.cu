@@ -1,0 +1,374 @@
+// kf_api.cu -- C ABI of libkfcount.so: device context, tile planning, kernel launches, host<->device
+// staging.  See include/kfcount.h for the contract and the reference lines each entry point replaces.
+#include "kfcount.h"
+#include "kf_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace kf {
+void canonical_codes(int k, std::vector<uint32_t> &out);  // kf_host.cpp
+
+namespace {
+
+constexpr int THREADS_SMEM = 512;   // 16 warps; 2 CTAs/SM -> 32 warps/SM, 64 regs/thread
+constexpr int CTAS_PER_SM = 2;
+constexpr int THREADS_GMEM = 512;
+constexpr uint32_t TILE_CHUNKS = 1024;                 // 512 KiB per tile: 64 chunks per warp
+constexpr size_t GMEM_WS_LIMIT = (size_t)12 << 30;     // forward-count workspace cap for k >= 8
+
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    // workspaces (grow-only)
+    void *d_fwd = nullptr; size_t fwd_cap = 0;
+    Tile *d_tiles = nullptr; size_t tiles_cap = 0;
+    int *d_cta_begin = nullptr; size_t cta_cap = 0;
+    uint32_t *d_canon[KF_MAX_K + 1] = {nullptr};
+    // end-to-end staging
+    uint8_t *d_arena = nullptr; size_t arena_cap = 0;
+    unsigned long long *d_counts = nullptr; size_t counts_cap = 0;
+    double *d_freq = nullptr; size_t freq_cap = 0;
+    unsigned long long *d_totals = nullptr; size_t totals_cap = 0;
+    // plan cache
+    std::vector<uint64_t> pc_offsets, pc_lens;
+    std::vector<uint8_t> pc_formats;
+    int pc_k = -1, pc_grid = 0, pc_ntiles = 0;
+    uint32_t pc_f0 = 0, pc_f1 = 0;
+    std::string last_err;
+    int last_launches = 0;
+};
+
+Ctx g;
+std::mutex g_mu;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            g.last_err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return KF_ERR_CUDA;                                                                   \
+        }                                                                                         \
+    } while (0)
+
+template <typename T>
+int ensure(T *&ptr, size_t &cap, size_t need_bytes) {
+    if (need_bytes <= cap) return KF_OK;
+    if (ptr) { CK(cudaDeviceSynchronize()); CK(cudaFree(ptr)); ptr = nullptr; cap = 0; }
+    size_t want = need_bytes + need_bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc((void **)&ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc((void **)&ptr, need_bytes);
+        want = need_bytes;
+        if (e != cudaSuccess) { cudaGetLastError(); g.last_err = "cudaMalloc failed"; return KF_ERR_NOMEM; }
+    }
+    cap = want;
+    return KF_OK;
+}
+
+int ensure_canon(int k) {
+    if (g.d_canon[k]) return KF_OK;
+    std::vector<uint32_t> c;
+    canonical_codes(k, c);
+    CK(cudaMalloc((void **)&g.d_canon[k], c.size() * sizeof(uint32_t)));
+    CK(cudaMemcpy(g.d_canon[k], c.data(), c.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return KF_OK;
+}
+
+// Cut the FASTA files [f0,f1) into per-CTA contiguous, chunk-balanced tile lists.
+void build_plan(const uint64_t *offsets, const uint64_t *lens, const uint8_t *formats, uint32_t f0, uint32_t f1,
+                int grid, std::vector<Tile> &tiles, std::vector<int> &cta_begin) {
+    uint64_t total = 0;
+    for (uint32_t f = f0; f < f1; f++)
+        if (formats[f] == '>' && lens[f] > 0) total += (lens[f] + CHUNK - 1) / CHUNK;
+    tiles.clear();
+    cta_begin.assign((size_t)grid + 1, 0);
+    uint64_t done = 0;   // chunks assigned so far
+    int cta = 0;
+    auto cta_hi = [&](int b) { return (total * (uint64_t)(b + 1)) / (uint64_t)grid; };
+    for (uint32_t f = f0; f < f1; f++) {
+        if (formats[f] != '>' || lens[f] == 0) continue;
+        const uint64_t fc0 = offsets[f] / CHUNK;
+        const uint64_t nch = (lens[f] + CHUNK - 1) / CHUNK;
+        uint64_t pos = 0;
+        while (pos < nch) {
+            while (cta < grid - 1 && done >= cta_hi(cta)) { cta++; cta_begin[(size_t)cta] = (int)tiles.size(); }
+            uint64_t room = cta_hi(cta) - done;
+            if (cta == grid - 1) room = total - done;
+            uint64_t take = std::min<uint64_t>(std::min<uint64_t>(nch - pos, room), TILE_CHUNKS);
+            if (take == 0) take = 1;
+            Tile t;
+            t.first_chunk = (uint32_t)(fc0 + pos);
+            t.n_chunks = (uint32_t)take;
+            t.file = f;
+            t.file_chunk0 = (uint32_t)fc0;
+            tiles.push_back(t);
+            pos += take;
+            done += take;
+        }
+    }
+    while (cta < grid) { cta++; cta_begin[(size_t)cta] = (int)tiles.size(); }
+}
+
+template <int K>
+int launch_smem(const uint8_t *d_arena, int grid, bool force_walker, cudaStream_t s) {
+    constexpr size_t smem = sizeof(uint32_t) << (2 * K);
+    unsigned long long *fwd = (unsigned long long *)g.d_fwd;
+    if (force_walker) {
+        auto kern = count_fasta_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM, true>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd);
+    } else {
+        auto kern = count_fasta_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM, false>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd);
+    }
+    CK(cudaGetLastError());
+    return KF_OK;
+}
+
+template <int K>
+int launch_gmem(const uint8_t *d_arena, int grid, bool force_walker, uint32_t file_base, cudaStream_t s) {
+    uint32_t *fwd = (uint32_t *)g.d_fwd;
+    if (force_walker)
+        count_fasta_gmem_kernel<K, THREADS_GMEM, true><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, file_base);
+    else
+        count_fasta_gmem_kernel<K, THREADS_GMEM, false><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, file_base);
+    CK(cudaGetLastError());
+    return KF_OK;
+}
+
+int launch_count(int k, const uint8_t *d_arena, int grid, bool fw, uint32_t file_base, cudaStream_t s) {
+    switch (k) {
+        case 1: return launch_smem<1>(d_arena, grid, fw, s);
+        case 2: return launch_smem<2>(d_arena, grid, fw, s);
+        case 3: return launch_smem<3>(d_arena, grid, fw, s);
+        case 4: return launch_smem<4>(d_arena, grid, fw, s);
+        case 5: return launch_smem<5>(d_arena, grid, fw, s);
+        case 6: return launch_smem<6>(d_arena, grid, fw, s);
+        case 7: return launch_smem<7>(d_arena, grid, fw, s);
+        case 8: return launch_gmem<8>(d_arena, grid, fw, file_base, s);
+        case 9: return launch_gmem<9>(d_arena, grid, fw, file_base, s);
+        case 10: return launch_gmem<10>(d_arena, grid, fw, file_base, s);
+        case 11: return launch_gmem<11>(d_arena, grid, fw, file_base, s);
+        case 12: return launch_gmem<12>(d_arena, grid, fw, file_base, s);
+        default: return KF_ERR_ARG;
+    }
+}
+
+// Count + fold for the files [f0,f1) of a batch whose arena is already on the device.
+int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *lens, const uint8_t *formats,
+              uint32_t f0, uint32_t f1, int k, uint32_t flags, unsigned long long *d_counts, double *d_freq,
+              float *d_feat, unsigned long long *d_totals, cudaStream_t s) {
+    const bool smem_path = k <= KF_MAX_K_SMEM;
+    const size_t NB = (size_t)1 << (2 * k);
+    const int64_t V = kf_vocab_size(k);
+    const uint32_t nf = f1 - f0;
+    const int grid = smem_path ? g.sm_count * CTAS_PER_SM : g.sm_count * 4;
+    int rc;
+    if ((rc = ensure_canon(k)) != KF_OK) return rc;
+    const size_t fwd_bytes = (size_t)nf * NB * (smem_path ? sizeof(unsigned long long) : sizeof(uint32_t));
+    if ((rc = ensure(g.d_fwd, g.fwd_cap, fwd_bytes)) != KF_OK) return rc;
+
+    // plan (cached on layout)
+    bool hit = g.pc_k == k && g.pc_grid == grid && g.pc_f0 == f0 && g.pc_f1 == f1 &&
+               g.pc_offsets.size() == (size_t)nf && std::equal(g.pc_offsets.begin(), g.pc_offsets.end(), offsets + f0) &&
+               std::equal(g.pc_lens.begin(), g.pc_lens.end(), lens + f0) &&
+               std::equal(g.pc_formats.begin(), g.pc_formats.end(), formats + f0);
+    if (!hit) {
+        std::vector<Tile> tiles;
+        std::vector<int> cta_begin;
+        build_plan(offsets, lens, formats, f0, f1, grid, tiles, cta_begin);
+        if ((rc = ensure(g.d_tiles, g.tiles_cap, (tiles.size() + 1) * sizeof(Tile))) != KF_OK) return rc;
+        if ((rc = ensure(g.d_cta_begin, g.cta_cap, cta_begin.size() * sizeof(int))) != KF_OK) return rc;
+        // the tables may still be read by kernels of a previous call on another stream
+        CK(cudaDeviceSynchronize());
+        if (!tiles.empty()) CK(cudaMemcpy(g.d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(g.d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+        g.pc_k = k; g.pc_grid = grid; g.pc_f0 = f0; g.pc_f1 = f1; g.pc_ntiles = (int)tiles.size();
+        g.pc_offsets.assign(offsets + f0, offsets + f1);
+        g.pc_lens.assign(lens + f0, lens + f1);
+        g.pc_formats.assign(formats + f0, formats + f1);
+    }
+    CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));
+    if (g.pc_ntiles > 0) {
+        // file indices inside tiles are batch-global; forward rows are relative to f0
+        if (smem_path) {
+            // smem kernels index g_fwd by absolute file id: shift the base pointer
+            void *saved = g.d_fwd;
+            g.d_fwd = (void *)((unsigned long long *)saved - (size_t)f0 * NB);
+            rc = launch_count(k, d_arena, grid, (flags & KF_FLAG_FORCE_WALKER) != 0, f0, s);
+            g.d_fwd = saved;
+        } else {
+            rc = launch_count(k, d_arena, grid, (flags & KF_FLAG_FORCE_WALKER) != 0, f0, s);
+        }
+        if (rc != KF_OK) return rc;
+        g.last_launches++;
+    }
+    if (smem_path)
+        fold_normalize_kernel<unsigned long long><<<nf, 1024, 0, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
+                                                                       f0, d_counts, d_freq, d_feat, d_totals);
+    else
+        fold_normalize_kernel<uint32_t><<<nf, 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, d_counts,
+                                                             d_freq, d_feat, d_totals);
+    CK(cudaGetLastError());
+    g.last_launches++;
+    return KF_OK;
+}
+
+int count_device_locked(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *offsets, const uint64_t *lens,
+                        const uint8_t *formats, int n, int k, uint32_t flags, unsigned long long *d_counts,
+                        double *d_freq, float *d_feat, unsigned long long *d_totals, cudaStream_t s) {
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (!d_arena || !offsets || !lens || !formats || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
+    uint64_t prev_end = 0;
+    for (int i = 0; i < n; i++) {
+        if (offsets[i] % CHUNK != 0 || offsets[i] < prev_end) return KF_ERR_LAYOUT;
+        prev_end = offsets[i] + lens[i];
+    }
+    if (prev_end + 2 * CHUNK > arena_bytes) return KF_ERR_LAYOUT;
+    if ((prev_end + CHUNK - 1) / CHUNK + 2 >= 0xFFFFFFFFull) return KF_ERR_ARG;
+    g.last_launches = 0;
+    if (n == 0) return KF_OK;
+    const size_t NB = (size_t)1 << (2 * k);
+    if (k <= KF_MAX_K_SMEM) return run_files(d_arena, offsets, lens, formats, 0, (uint32_t)n, k, flags, d_counts, d_freq, d_feat, d_totals, s);
+    // large k: bound the dense forward-count workspace
+    size_t per = std::max<size_t>(1, GMEM_WS_LIMIT / (NB * sizeof(uint32_t)));
+    for (uint32_t f0 = 0; f0 < (uint32_t)n; f0 += (uint32_t)per) {
+        uint32_t f1 = (uint32_t)std::min<size_t>((size_t)n, (size_t)f0 + per);
+        int rc = run_files(d_arena, offsets, lens, formats, f0, f1, k, flags, d_counts, d_freq, d_feat, d_totals, s);
+        if (rc != KF_OK) return rc;
+    }
+    return KF_OK;
+}
+
+}  // namespace
+}  // namespace kf
+
+using namespace kf;
+
+extern "C" {
+
+int kf_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); g.last_err = "no CUDA device"; return KF_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return KF_ERR_ARG;
+    if (g.device == device) return KF_OK;
+    if (g.device >= 0) return KF_ERR_ARG;   // one device per process (one process per GPU)
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { g.last_err = "device is not sm_100 (Blackwell B200)"; return KF_ERR_NO_DEVICE; }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
+    g.sm_count = prop.multiProcessorCount;
+    g.device = device;
+    return KF_OK;
+}
+
+int kf_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_OK;
+    cudaDeviceSynchronize();
+    cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
+    cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals);
+    for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
+    cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
+    g = Ctx();
+    return KF_OK;
+}
+
+int kf_device(void) { return g.device >= 0 ? g.device : KF_ERR_NO_DEVICE; }
+const char *kf_last_cuda_error(void) { return g.last_err.c_str(); }
+int kf_last_launch_count(void) { return g.last_launches; }
+
+int kf_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *offsets, const uint64_t *lens,
+                    const uint8_t *formats, int n, int k, uint32_t flags, uint64_t *d_counts, double *d_freq,
+                    float *d_feat, uint64_t *d_totals, void *stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    return count_device_locked(d_arena, arena_bytes, offsets, lens, formats, n, k, flags,
+                               (unsigned long long *)d_counts, d_freq, d_feat, (unsigned long long *)d_totals, s);
+}
+
+int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens_in, int n, int k, uint32_t flags,
+                     uint64_t *counts_out, double *freq_out, uint64_t *totals_out, int *status_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (!bufs || !lens_in || !status_out || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
+    if (n == 0) return KF_OK;
+    const int64_t V = kf_vocab_size(k);
+    std::vector<uint64_t> offsets((size_t)n), lens((size_t)n);
+    std::vector<uint8_t> formats((size_t)n);
+    uint64_t off = 0;
+    for (int i = 0; i < n; i++) {
+        offsets[(size_t)i] = off;
+        status_out[i] = KF_OK;
+        uint64_t L = lens_in[i];
+        if (L == 0 || !bufs[i]) { status_out[i] = KF_ERR_EMPTY; L = 0; formats[(size_t)i] = 0; }
+        else {
+            formats[(size_t)i] = bufs[i][0];
+            if (bufs[i][0] == '@') { status_out[i] = KF_ERR_FASTQ; L = 0; }          // FASTQ kernel: not in this build yet
+            else if (bufs[i][0] != '>') { status_out[i] = KF_ERR_FORMAT; L = 0; }
+        }
+        lens[(size_t)i] = L;
+        off += (L + CHUNK - 1) / CHUNK * CHUNK;
+    }
+    const size_t arena_bytes = off + 2 * CHUNK;
+    int rc;
+    if ((rc = ensure(g.d_arena, g.arena_cap, arena_bytes)) != KF_OK) return rc;
+    if ((rc = ensure(g.d_counts, g.counts_cap, (size_t)n * V * sizeof(unsigned long long))) != KF_OK) return rc;
+    if ((rc = ensure(g.d_freq, g.freq_cap, (size_t)n * V * sizeof(double))) != KF_OK) return rc;
+    if ((rc = ensure(g.d_totals, g.totals_cap, (size_t)n * sizeof(unsigned long long))) != KF_OK) return rc;
+    // stage: zero the arena (gaps must be NUL), then one copy per file
+    CK(cudaMemsetAsync(g.d_arena, 0, arena_bytes, g.copy_stream));
+    for (int i = 0; i < n; i++)
+        if (lens[(size_t)i]) CK(cudaMemcpyAsync(g.d_arena + offsets[(size_t)i], bufs[i], lens[(size_t)i], cudaMemcpyHostToDevice, g.copy_stream));
+    CK(cudaEventRecord(g.ev_copy, g.copy_stream));
+    CK(cudaStreamWaitEvent(g.stream, g.ev_copy, 0));
+    rc = count_device_locked(g.d_arena, arena_bytes, offsets.data(), lens.data(), formats.data(), n, k, flags, g.d_counts,
+                             g.d_freq, nullptr, g.d_totals, g.stream);
+    if (rc != KF_OK) return rc;
+    if (counts_out) CK(cudaMemcpyAsync(counts_out, g.d_counts, (size_t)n * V * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    if (freq_out) CK(cudaMemcpyAsync(freq_out, g.d_freq, (size_t)n * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    if (totals_out) CK(cudaMemcpyAsync(totals_out, g.d_totals, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return KF_OK;
+}
+
+int kf_count_files(const char *const *paths, int n, int k, uint32_t flags, uint64_t *counts_out, double *freq_out,
+                   uint64_t *totals_out, int *status_out) {
+    if (!paths || !status_out || n < 0) return KF_ERR_ARG;
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    std::vector<std::vector<uint8_t>> data((size_t)n);
+    std::vector<const uint8_t *> bufs((size_t)n);
+    std::vector<size_t> lens((size_t)n);
+    std::vector<int> io_fail((size_t)n, 0);
+    for (int i = 0; i < n; i++) {
+        FILE *f = fopen(paths[i], "rb");
+        if (!f) { io_fail[(size_t)i] = 1; continue; }
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        data[(size_t)i].resize(sz > 0 ? (size_t)sz : 0);
+        if (sz > 0 && fread(data[(size_t)i].data(), 1, (size_t)sz, f) != (size_t)sz) io_fail[(size_t)i] = 1;
+        fclose(f);
+        bufs[(size_t)i] = data[(size_t)i].data();
+        lens[(size_t)i] = io_fail[(size_t)i] ? 0 : data[(size_t)i].size();
+    }
+    int rc = kf_count_buffers(bufs.data(), lens.data(), n, k, flags, counts_out, freq_out, totals_out, status_out);
+    for (int i = 0; i < n; i++)
+        if (io_fail[(size_t)i]) status_out[i] = KF_ERR_IO;
+    return rc;
+}
+
+}  // extern "C"

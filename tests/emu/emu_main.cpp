@@ -1,0 +1,101 @@
+// emu_main.cpp -- TEST INFRASTRUCTURE.  Runs the real kernel code of kf_kernels.cuh under the host
+// emulation (cuda_emu.h) with the real tile planner's layout rules, on one or more FASTA files, and
+// prints the canonical counts (one line per file) so tests/ can compare them with the oracle.
+//   usage: emu_main <k> <threads_per_cta> <grid> <force_walker 0|1> <tile_chunks> file...
+#include "cuda_emu.h"
+#include "../../kf2vecfsw_b200/csrc/kf_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+namespace emu {
+thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+thread_local BlockShared *t_block = nullptr;
+void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()> &fn) {
+    for (unsigned b = 0; b < grid; b++) {
+        BlockShared bs;
+        pthread_barrier_init(&bs.bar, nullptr, block);
+        bs.smem.assign(smem_bytes + 16, 0);
+        bs.warps = std::vector<WarpShared>(block / 32);
+        for (auto &w : bs.warps) pthread_barrier_init(&w.bar, nullptr, 32);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < block; t++)
+            th.emplace_back([&, t]() {
+                t_threadIdx.x = t; t_blockIdx.x = b; t_blockDim.x = block; t_gridDim.x = grid;
+                t_block = &bs;
+                fn();
+            });
+        for (auto &x : th) x.join();
+    }
+}
+}  // namespace emu
+
+namespace kf { void canonical_codes(int k, std::vector<uint32_t> &out); }
+
+using namespace kf;
+
+template <int K, int THREADS>
+static void run(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
+                bool fw, unsigned long long *fwd) {
+    size_t smem = sizeof(uint32_t) << (2 * K);
+    if (fw) emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, true>(arena, tiles.data(), cta_begin.data(), fwd); });
+    else    emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, false>(arena, tiles.data(), cta_begin.data(), fwd); });
+}
+
+int main(int argc, char **argv) {
+    if (argc < 7) { fprintf(stderr, "usage\n"); return 2; }
+    int k = atoi(argv[1]), threads = atoi(argv[2]), grid = atoi(argv[3]);
+    bool fw = atoi(argv[4]) != 0;
+    uint32_t tile_chunks = (uint32_t)atoi(argv[5]);
+    int n = argc - 6;
+    std::vector<uint64_t> off(n), len(n);
+    std::vector<uint8_t> arena;
+    for (int i = 0; i < n; i++) {
+        FILE *f = fopen(argv[6 + i], "rb");
+        if (!f) { perror(argv[6 + i]); return 1; }
+        fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+        off[i] = arena.size();
+        arena.resize(arena.size() + (size_t)(sz + CHUNK - 1) / CHUNK * CHUNK, 0);
+        if (fread(arena.data() + off[i], 1, (size_t)sz, f) != (size_t)sz) return 1;
+        fclose(f);
+        len[i] = (uint64_t)sz;
+    }
+    arena.resize(arena.size() + 2 * CHUNK, 0);
+    // same cutting rule as kf_api.cu:build_plan (chunk-balanced contiguous CTA ranges, tiles <= tile_chunks)
+    uint64_t total = 0;
+    for (int i = 0; i < n; i++) total += (len[i] + CHUNK - 1) / CHUNK;
+    std::vector<Tile> tiles; std::vector<int> cta_begin(grid + 1, 0);
+    uint64_t done = 0; int cta = 0;
+    auto cta_hi = [&](int b) { return total * (uint64_t)(b + 1) / (uint64_t)grid; };
+    for (int f = 0; f < n; f++) {
+        uint64_t fc0 = off[f] / CHUNK, nch = (len[f] + CHUNK - 1) / CHUNK, pos = 0;
+        while (pos < nch) {
+            while (cta < grid - 1 && done >= cta_hi(cta)) { cta++; cta_begin[cta] = (int)tiles.size(); }
+            uint64_t room = (cta == grid - 1) ? total - done : cta_hi(cta) - done;
+            uint64_t take = std::min<uint64_t>(std::min<uint64_t>(nch - pos, room), tile_chunks);
+            if (!take) take = 1;
+            tiles.push_back(Tile{(uint32_t)(fc0 + pos), (uint32_t)take, (uint32_t)f, (uint32_t)fc0});
+            pos += take; done += take;
+        }
+    }
+    while (cta < grid) { cta++; cta_begin[cta] = (int)tiles.size(); }
+    size_t NB = (size_t)1 << (2 * k);
+    std::vector<unsigned long long> fwd((size_t)n * NB, 0);
+#define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data()); break;
+    switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }
+    std::vector<uint32_t> canon; canonical_codes(k, canon);
+    long long V = (long long)canon.size();
+    std::vector<unsigned long long> counts((size_t)n * V), totals(n);
+    std::vector<double> freq((size_t)n * V);
+    emu::launch(n, 64, 0, [&]() { fold_normalize_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, 0u, counts.data(), freq.data(), (float *)nullptr, totals.data()); });
+    for (int f = 0; f < n; f++) {
+        printf("%llu", totals[f]);
+        for (long long i = 0; i < V; i++) printf(" %llu", counts[(size_t)f * V + i]);
+        printf("\n");
+        printf("F");
+        for (long long i = 0; i < V; i++) printf(" %.17g", freq[(size_t)f * V + i]);
+        printf("\n");
+    }
+    return 0;
+}
