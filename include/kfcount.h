@@ -95,6 +95,9 @@ int kf_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *
                     void *stream);
 /* Number of kernels kf_count_device launched in its last call (for bench.py's gpu_launches). */
 int kf_last_launch_count(void);
+/* Device time of the counting kernel(s) of the last kf_count_device / kf_count_buffers call, from CUDA
+ * events recorded on the launching stream (waits for them).  Used for the roofline figure. */
+int kf_last_count_kernel_ms(float *ms);
 
 /* ---- .kf writer: main.py:344-357 --------------------------------------------------------------- */
 /* Formats one row exactly as pandas `astype(str)` + ",".join does (Python repr of float64: shortest

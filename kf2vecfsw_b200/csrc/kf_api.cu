@@ -25,7 +25,8 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    bool ev_valid = false;
     // workspaces (grow-only)
     void *d_fwd = nullptr; size_t fwd_cap = 0;
     Tile *d_tiles = nullptr; size_t tiles_cap = 0;
@@ -199,6 +200,7 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     }
     CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));
     if (g.pc_ntiles > 0) {
+        if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         // file indices inside tiles are batch-global; forward rows are relative to f0
         if (smem_path) {
             // smem kernels index g_fwd by absolute file id: shift the base pointer
@@ -210,6 +212,8 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             rc = launch_count(k, d_arena, grid, (flags & KF_FLAG_FORCE_WALKER) != 0, f0, s);
         }
         if (rc != KF_OK) return rc;
+        CK(cudaEventRecord(g.ev_k1, s));
+        g.ev_valid = true;
         g.last_launches++;
     }
     if (smem_path)
@@ -236,6 +240,7 @@ int count_device_locked(const uint8_t *d_arena, size_t arena_bytes, const uint64
     if (prev_end + 2 * CHUNK > arena_bytes) return KF_ERR_LAYOUT;
     if ((prev_end + CHUNK - 1) / CHUNK + 2 >= 0xFFFFFFFFull) return KF_ERR_ARG;
     g.last_launches = 0;
+    g.ev_valid = false;
     if (n == 0) return KF_OK;
     const size_t NB = (size_t)1 << (2 * k);
     if (k <= KF_MAX_K_SMEM) return run_files(d_arena, offsets, lens, formats, 0, (uint32_t)n, k, flags, d_counts, d_freq, d_feat, d_totals, s);
@@ -270,6 +275,8 @@ int kf_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
+    CK(cudaEventCreate(&g.ev_k0));
+    CK(cudaEventCreate(&g.ev_k1));
     g.sm_count = prop.multiProcessorCount;
     g.device = device;
     return KF_OK;
@@ -283,6 +290,7 @@ int kf_shutdown(void) {
     cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
+    cudaEventDestroy(g.ev_k0); cudaEventDestroy(g.ev_k1);
     g = Ctx();
     return KF_OK;
 }
@@ -290,6 +298,14 @@ int kf_shutdown(void) {
 int kf_device(void) { return g.device >= 0 ? g.device : KF_ERR_NO_DEVICE; }
 const char *kf_last_cuda_error(void) { return g.last_err.c_str(); }
 int kf_last_launch_count(void) { return g.last_launches; }
+int kf_last_count_kernel_ms(float *ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (!ms || !g.ev_valid) return KF_ERR_ARG;
+    CK(cudaEventSynchronize(g.ev_k1));
+    CK(cudaEventElapsedTime(ms, g.ev_k0, g.ev_k1));
+    return KF_OK;
+}
 
 int kf_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *offsets, const uint64_t *lens,
                     const uint8_t *formats, int n, int k, uint32_t flags, uint64_t *d_counts, double *d_freq,

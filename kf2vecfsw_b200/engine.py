@@ -1,0 +1,295 @@
+"""ctypes binding of libkfcount.so (include/kfcount.h) -- the host-side mirror of the C ABI.
+
+No CPU fallback lives here: if the shared library is missing or no sm_100 device is visible, compute
+calls raise ``KfError``.  Host-only helpers (vocabulary, .kf formatting, synthetic inputs) work without
+a GPU because they are plain C++ inside the same library.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+KF_FLAG_PSEUDOCOUNT = 1
+KF_FLAG_RAW_CNT = 2
+KF_FLAG_FORCE_WALKER = 4
+KF_CHUNK = 512
+KF_MAX_K = 12
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_INIT_DEVICE: Optional[int] = None
+
+
+class KfError(RuntimeError):
+    def __init__(self, code: int, what: str = ""):
+        self.code = code
+        msg = "libkfcount error %d" % code
+        try:
+            L = _load()
+            msg += " (%s)" % L.kf_strerror(code).decode()
+            if code == -3:
+                msg += ": " + L.kf_last_cuda_error().decode()
+        except Exception:  # pragma: no cover
+            pass
+        if what:
+            msg = what + ": " + msg
+        super().__init__(msg)
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libkfcount.so")
+
+
+def _load():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            "kf2vecfsw_b200: %s is not built. Run `python -m kf2vecfsw_b200.build` (needs nvcc). "
+            "There is no CPU fallback." % path)
+    L = ctypes.CDLL(path)
+    c_u8pp = ctypes.POINTER(ctypes.c_void_p)
+    L.kf_init.argtypes = [ctypes.c_int]
+    L.kf_shutdown.argtypes = []
+    L.kf_device.argtypes = []
+    L.kf_strerror.argtypes = [ctypes.c_int]
+    L.kf_strerror.restype = ctypes.c_char_p
+    L.kf_last_cuda_error.restype = ctypes.c_char_p
+    L.kf_abi_version.restype = ctypes.c_int
+    L.kf_vocab_size.argtypes = [ctypes.c_int]
+    L.kf_vocab_size.restype = ctypes.c_int64
+    L.kf_vocab.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]
+    L.kf_vocab_codes.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+    L.kf_count_buffers.argtypes = [c_u8pp, ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p]
+    L.kf_count_files.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_count_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_last_launch_count.restype = ctypes.c_int
+    L.kf_last_count_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float)]
+    L.kf_format_row.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char_p,
+                                ctypes.c_size_t]
+    L.kf_format_row.restype = ctypes.c_int64
+    L.kf_write_kf.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
+                              ctypes.c_int]
+    L.kf_synth_fasta.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_size_t]
+    L.kf_synth_fasta.restype = ctypes.c_int64
+    L.kf_synth_fastq.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                 ctypes.c_void_p, ctypes.c_size_t]
+    L.kf_synth_fastq.restype = ctypes.c_int64
+    _LIB = L
+    return L
+
+
+def _check(rc: int, what: str = ""):
+    if rc != 0:
+        raise KfError(rc, what)
+
+
+def _flags(pseudocount: bool, raw_cnt: bool, force_walker: bool = False) -> int:
+    return (KF_FLAG_PSEUDOCOUNT if pseudocount else 0) | (KF_FLAG_RAW_CNT if raw_cnt else 0) | \
+           (KF_FLAG_FORCE_WALKER if force_walker else 0)
+
+
+# ---- lifecycle -----------------------------------------------------------------------------------
+def init(device: Optional[int] = None) -> int:
+    """One process per GPU: picks LOCAL_RANK (torchrun) or 0 unless told otherwise."""
+    global _INIT_DEVICE
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _INIT_DEVICE == device:
+        return device
+    _check(_load().kf_init(device), "kf_init(%d)" % device)
+    _INIT_DEVICE = device
+    return device
+
+
+def _require_init():
+    if _INIT_DEVICE is None:
+        init()
+
+
+# ---- vocabulary ------------------------------------------------------------------------------------
+def vocab_size(k: int) -> int:
+    v = _load().kf_vocab_size(k)
+    if v < 0:
+        raise KfError(int(v), "kf_vocab_size")
+    return int(v)
+
+
+def vocab(k: int) -> List[str]:
+    V = vocab_size(k)
+    buf = ctypes.create_string_buffer(V * (k + 1))
+    _check(_load().kf_vocab(k, buf, len(buf)), "kf_vocab")
+    return buf.raw.decode().split("\n")[:V]
+
+
+def vocab_codes(k: int) -> np.ndarray:
+    V = vocab_size(k)
+    out = np.zeros(V, dtype=np.uint32)
+    _check(_load().kf_vocab_codes(k, out.ctypes.data, V), "kf_vocab_codes")
+    return out
+
+
+# ---- counting: host buffers -------------------------------------------------------------------------
+def _as_u8(b) -> np.ndarray:
+    if isinstance(b, np.ndarray):
+        if b.dtype != np.uint8 or not b.flags.c_contiguous:
+            raise TypeError("buffers must be contiguous uint8 arrays or bytes")
+        return b
+    if hasattr(b, "numpy") and hasattr(b, "data_ptr"):  # CPU torch tensor (possibly pinned)
+        return b.numpy()
+    return np.frombuffer(b, dtype=np.uint8)
+
+
+def count_buffers(bufs: Sequence, k: int = 7, pseudocount: bool = False, raw_cnt: bool = False,
+                  want_counts: bool = True, want_freq: bool = True, force_walker: bool = False,
+                  out_counts: Optional[np.ndarray] = None, out_freq: Optional[np.ndarray] = None
+                  ) -> Tuple[Optional[np.ndarray], Optional[np.ndarray], np.ndarray, np.ndarray]:
+    """End-to-end call on host buffers (one per input file).  Returns (counts u64 [n,V] | None,
+    freq f64 [n,V] | None, totals u64 [n], status i32 [n])."""
+    _require_init()
+    L = _load()
+    n = len(bufs)
+    V = vocab_size(k)
+    arrs = [_as_u8(b) for b in bufs]
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (ctypes.c_size_t * max(n, 1))(*[a.size for a in arrs])
+    counts = out_counts if out_counts is not None else (np.empty((n, V), dtype=np.uint64) if want_counts else None)
+    freq = out_freq if out_freq is not None else (np.empty((n, V), dtype=np.float64) if want_freq else None)
+    totals = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    rc = L.kf_count_buffers(ptrs, lens, n, k, _flags(pseudocount, raw_cnt, force_walker),
+                            counts.ctypes.data if counts is not None else None,
+                            freq.ctypes.data if freq is not None else None, totals.ctypes.data, status.ctypes.data)
+    _check(rc, "kf_count_buffers")
+    return counts, freq, totals, status
+
+
+def count_files(paths: Sequence[str], k: int = 7, pseudocount: bool = False, raw_cnt: bool = False):
+    _require_init()
+    L = _load()
+    n = len(paths)
+    V = vocab_size(k)
+    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(p) for p in paths])
+    counts = np.empty((n, V), dtype=np.uint64)
+    freq = np.empty((n, V), dtype=np.float64)
+    totals = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    _check(L.kf_count_files(arr, n, k, _flags(pseudocount, raw_cnt), counts.ctypes.data, freq.ctypes.data,
+                            totals.ctypes.data, status.ctypes.data), "kf_count_files")
+    return counts, freq, totals, status
+
+
+# ---- counting: device-resident arena ------------------------------------------------------------------
+class DeviceArena:
+    """A batch of input files laid out in HBM per the contract of ``kf_count_device``: every file starts
+    at a multiple of 512 bytes, gaps are NUL, 1 KiB of NUL follows the last file."""
+
+    def __init__(self, host_buffers: Sequence, device=None, pinned_host=None):
+        import torch
+        _require_init()
+        self.device = torch.device("cuda", _INIT_DEVICE) if device is None else device
+        arrs = [_as_u8(b) for b in host_buffers]
+        self.n = len(arrs)
+        self.lens = np.array([a.size for a in arrs], dtype=np.uint64)
+        padded = (self.lens + np.uint64(KF_CHUNK - 1)) // np.uint64(KF_CHUNK) * np.uint64(KF_CHUNK)
+        self.offsets = np.zeros(self.n, dtype=np.uint64)
+        if self.n > 1:
+            self.offsets[1:] = np.cumsum(padded)[:-1]
+        self.nbytes = int(padded.sum()) + 2 * KF_CHUNK
+        self.formats = np.array([a[0] if a.size else 0 for a in arrs], dtype=np.uint8)
+        self.tensor = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
+        for a, off in zip(arrs, self.offsets):
+            if a.size:
+                src = torch.from_numpy(a) if a.flags.writeable else torch.frombuffer(memoryview(a), dtype=torch.uint8)
+                self.tensor[int(off): int(off) + a.size].copy_(src, non_blocking=True)
+        torch.cuda.synchronize(self.device)
+
+    @property
+    def file_bytes(self) -> int:
+        return int(self.lens.sum())
+
+
+def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_cnt: bool = False,
+                 counts=None, freq=None, feat=None, totals=None, force_walker: bool = False, stream=None):
+    """Enqueues count + fold/normalise for the arena on ``stream`` (default: torch's current stream).
+    Output tensors (torch, on the arena's device) are optional: counts int64/uint64 [n,V], freq float64
+    [n,V], feat float32 [n,V] (= fp32(freq*1e4), the matrix the trainers consume), totals int64 [n]."""
+    import torch
+    _require_init()
+    L = _load()
+    if stream is None:
+        stream = torch.cuda.current_stream(arena.device)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    rc = L.kf_count_device(ctypes.c_void_p(arena.tensor.data_ptr()), arena.nbytes, arena.offsets.ctypes.data,
+                           arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, k,
+                           _flags(pseudocount, raw_cnt, force_walker), ptr(counts), ptr(freq), ptr(feat), ptr(totals),
+                           ctypes.c_void_p(stream.cuda_stream))
+    _check(rc, "kf_count_device")
+
+
+def last_launch_count() -> int:
+    return int(_load().kf_last_launch_count())
+
+
+def last_count_kernel_ms() -> float:
+    ms = ctypes.c_float(0)
+    _check(_load().kf_last_count_kernel_ms(ctypes.byref(ms)), "kf_last_count_kernel_ms")
+    return float(ms.value)
+
+
+# ---- .kf text -------------------------------------------------------------------------------------------
+def format_row(sample: str, row: np.ndarray, int_mode: bool = False) -> str:
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    s = sample.encode()
+    buf = ctypes.create_string_buffer(len(s) + 2 + row.size * 32 + 1)
+    n = _load().kf_format_row(s, row.ctypes.data, row.size, 1 if int_mode else 0, buf, len(buf))
+    if n < 0:
+        raise KfError(int(n), "kf_format_row")
+    return buf.raw[:n].decode()
+
+
+def write_kf(path: str, sample: str, row: np.ndarray, int_mode: bool = False, append: bool = False) -> None:
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    _check(_load().kf_write_kf(os.fsencode(path), sample.encode(), row.ctypes.data, row.size, 1 if int_mode else 0,
+                               1 if append else 0), "kf_write_kf(%s)" % path)
+
+
+# ---- synthetic inputs --------------------------------------------------------------------------------------
+def synth_fasta(seed: int, genome_id: int, n_bases: int, line_width: int = 80, out: Optional[np.ndarray] = None):
+    L = _load()
+    size = L.kf_synth_fasta(seed, genome_id, n_bases, line_width, None, 0)
+    if size < 0:
+        raise KfError(int(size), "kf_synth_fasta")
+    if out is None:
+        out = np.empty(size, dtype=np.uint8)
+    n = L.kf_synth_fasta(seed, genome_id, n_bases, line_width, out.ctypes.data, out.size)
+    if n < 0:
+        raise KfError(int(n), "kf_synth_fasta")
+    return out[:n]
+
+
+def synth_fasta_size(seed: int, genome_id: int, n_bases: int, line_width: int = 80) -> int:
+    return int(_load().kf_synth_fasta(seed, genome_id, n_bases, line_width, None, 0))
+
+
+def synth_fastq(seed: int, sample_id: int, genome_len: int, n_reads: int, read_len: int = 150):
+    L = _load()
+    size = L.kf_synth_fastq(seed, sample_id, genome_len, n_reads, read_len, None, 0)
+    if size < 0:
+        raise KfError(int(size), "kf_synth_fastq")
+    out = np.empty(size, dtype=np.uint8)
+    n = L.kf_synth_fastq(seed, sample_id, genome_len, n_reads, read_len, out.ctypes.data, out.size)
+    if n < 0:
+        raise KfError(int(n), "kf_synth_fastq")
+    return out[:n]

@@ -1,0 +1,107 @@
+"""Drop-in for kf2vec's ``get_frequencies(args)`` (reference ``kf2vec/main.py:250-373``).
+
+Same argparse ``Namespace`` in, same ``<output_dir>/<sample>.kf`` files out, same prints, same sample
+naming, same column order / pseudocount / normalisation / text format -- but the per-file
+``jellyfish count`` + ``jellyfish dump`` subprocesses and the pandas merge are replaced by one batched call
+into ``libkfcount.so`` (CUDA, sm_100a).  ``build_library`` (main.py:573), ``process_query_data`` (main.py:629)
+and ``get_chunks`` (main.py:869-881) call this function with their own ``args``; both wrapper parsers omit
+``raw_cnt`` (main.py:1253-1353), so optional attributes are read with ``getattr``.
+"""
+from __future__ import annotations
+
+import fnmatch
+import os
+import sys
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import engine
+
+FORMATS = ['.fq', '.fastq', '.fa', '.fna', '.fasta']  # main.py:272
+DEFAULT_K = 7                                          # main.py:80
+BATCH_BYTES = 4 << 30                                  # host bytes staged per library call
+
+
+def list_inputs(input_dir: str) -> Tuple[List[str], List[str]]:
+    """main.py:272-275 -- os.listdir order, fnmatch on the five suffixes, sample = name.rsplit('.f', 1)[0]."""
+    files_names = [f for f in os.listdir(input_dir)
+                   if True in (fnmatch.fnmatch(f, '*' + form) for form in FORMATS)]
+    samples_names = [f.rsplit('.f', 1)[0] for f in files_names]
+    return files_names, samples_names
+
+
+def _batches(paths: List[str]) -> List[List[int]]:
+    out, cur, cur_bytes = [], [], 0
+    for i, p in enumerate(paths):
+        sz = os.path.getsize(p)
+        if cur and cur_bytes + sz > BATCH_BYTES:
+            out.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(i)
+        cur_bytes += sz
+    if cur:
+        out.append(cur)
+    return out
+
+
+def get_frequencies(args) -> None:
+    """Reference: kf2vec/main.py:250-373."""
+    print('\n==> Starting k-mer counting for {}\n'.format(args.input_dir))
+
+    if not os.path.exists(args.input_dir):                       # main.py:255-259
+        print("No such directory '{}'".format(args.input_dir), file=sys.stderr)
+        exit(0)
+    if not os.path.exists(args.output_dir):                      # main.py:262-266
+        print("No such directory '{}'".format(args.output_dir), file=sys.stderr)
+        exit(0)
+
+    k = getattr(args, 'k', DEFAULT_K)
+    pseudocount = bool(getattr(args, 'pseudocount', False))
+    raw_cnt = bool(getattr(args, 'raw_cnt', False))
+    # args.p (jellyfish -t) has no meaning here: the GPU path is not thread-parallel on the host.
+
+    files_names, samples_names = list_inputs(args.input_dir)
+    paths = [os.path.join(args.input_dir, f) for f in files_names]
+    V = engine.vocab_size(k)
+
+    for batch in _batches(paths):
+        bufs = [np.fromfile(paths[i], dtype=np.uint8) for i in batch]
+        counts, freq, totals, status = engine.count_buffers(bufs, k=k, pseudocount=pseudocount, raw_cnt=raw_cnt)
+        for j, i in enumerate(batch):
+            if status[j] != 0:
+                # The reference ignores jellyfish's exit code and then dies with IndexError at main.py:315;
+                # fail with the real cause instead of writing a bogus row.
+                raise engine.KfError(int(status[j]), "k-mer counting failed for {}".format(files_names[i]))
+            if pseudocount:
+                print('>>> Adding pseudocounts. Sample: {}'.format(files_names[i]))       # main.py:333
+            if not raw_cnt:
+                print('>>> Normalizing. Sample: {}'.format(files_names[i]))               # main.py:341
+            # pandas keeps the merged column int64 only when no vocabulary k-mer is missing (main.py:327-328):
+            # then str() prints "5", otherwise "5.0".
+            int_mode = raw_cnt and not pseudocount and bool(np.all(counts[j] > 0))
+            f3 = os.path.join(args.output_dir, "{}.{}".format(samples_names[i], "kf"))
+            engine.write_kf(f3, str(samples_names[i]), freq[j], int_mode=int_mode)
+        del bufs
+
+    print('\n==> Done processing {}'.format(args.input_dir))
+
+
+def frequency_matrix(input_dir: str, k: int = DEFAULT_K, pseudocount: bool = False, device=None):
+    """Fast path for the trainers: the [N, V] float32 feature matrix fp32(freq * 1e4) straight from HBM,
+    skipping the .kf text round trip of train_classifier_model.py:144-150 / utils.py:436-437.
+    Returns (sample names, torch.float32 CUDA tensor)."""
+    import torch
+    files_names, samples_names = list_inputs(input_dir)
+    paths = [os.path.join(input_dir, f) for f in files_names]
+    V = engine.vocab_size(k)
+    engine.init()
+    rows = []
+    for batch in _batches(paths):
+        bufs = [np.fromfile(paths[i], dtype=np.uint8) for i in batch]
+        arena = engine.DeviceArena(bufs, device=device)
+        feat = torch.empty((arena.n, V), dtype=torch.float32, device=arena.device)
+        engine.count_device(arena, k=k, pseudocount=pseudocount, feat=feat)
+        rows.append(feat)
+    torch.cuda.synchronize()
+    return samples_names, (torch.cat(rows, 0) if rows else torch.empty((0, V), dtype=torch.float32))

@@ -1,0 +1,61 @@
+"""Adversarial FASTA / FASTQ generators shared by the CPU (emulation) and GPU parity tests."""
+import random
+
+
+def rand_fasta(rng: random.Random) -> bytes:
+    out = bytearray()
+    nrec = rng.randint(1, 6)
+    style = rng.choice(['wrap', 'wrap', 'short', 'unwrapped', 'mixed', 'crlf', 'blank'])
+    for _ in range(nrec):
+        hl = rng.choice([5, 20, 100, 600, 1500]) if rng.random() < 0.3 else rng.randint(1, 60)
+        hdr = ''.join(rng.choice('ACGTacgtN >|_.0123456789xyz') for _ in range(hl))
+        out += b'>' + hdr.encode() + b'\n'
+        L = rng.choice([0, 1, 3, 6, 7, 8, 15, 16, 17, 100, 511, 512, 513, 3000, 20000]) if rng.random() < 0.5 \
+            else rng.randint(0, 5000)
+        alphabet = 'ACGT' * 20 + 'acgt' * 5 + 'N' * (3 if rng.random() < 0.5 else 0) + \
+                   ('RYKM-*.>' if rng.random() < 0.3 else '')
+        seq = ''.join(rng.choice(alphabet) for _ in range(L))
+        if rng.random() < 0.3 and L > 50:
+            p = rng.randint(0, L - 10)
+            n = rng.randint(1, 40)
+            seq = seq[:p] + 'N' * n + seq[p + n:]
+        if style == 'unwrapped':
+            w = 10 ** 9
+        elif style == 'short':
+            w = rng.randint(1, 20)
+        elif style == 'mixed':
+            w = None
+        else:
+            w = rng.choice([60, 70, 80, 61, 15, 16, 17, 31, 32, 33])
+        i = 0
+        while i < len(seq):
+            ww = w if w else rng.randint(1, 100)
+            line = seq[i:i + ww]
+            i += ww
+            out += line.encode() + (b'\r\n' if style == 'crlf' else b'\n')
+            if style == 'blank' and rng.random() < 0.2:
+                out += b'\n' * rng.randint(1, 3)
+    if rng.random() < 0.3 and out.endswith(b'\n'):
+        out = out[:-1]
+    return bytes(out)
+
+
+def rand_fastq(rng: random.Random) -> bytes:
+    """Well-formed 4-line FASTQ with nasty content: N runs, lower case, qualities starting with '@'/'+',
+    empty reads, reads shorter than k, variable read lengths."""
+    out = bytearray()
+    nrec = rng.randint(1, 60)
+    for r in range(nrec):
+        L = rng.choice([0, 1, 6, 7, 8, 15, 16, 17, 31, 32, 33, 100, 150, 151, 500, 513]) if rng.random() < 0.5 \
+            else rng.randint(0, 300)
+        alphabet = 'ACGT' * 20 + 'acgt' * 3 + 'N' * (2 if rng.random() < 0.5 else 0)
+        seq = ''.join(rng.choice(alphabet) for _ in range(L))
+        qual = ''.join(chr(rng.randint(33, 74)) for _ in range(L))
+        if L and rng.random() < 0.3:
+            qual = rng.choice('@+>') + qual[1:]
+        hdr = '@r%d %s' % (r, ''.join(rng.choice('ACGT@+>: /') for _ in range(rng.randint(0, 40))))
+        plus = '+' + (hdr[1:] if rng.random() < 0.2 else '')
+        out += (hdr + '\n' + seq + '\n' + plus + '\n' + qual + '\n').encode()
+    if rng.random() < 0.3:
+        out = out[:-1]
+    return bytes(out)

@@ -1,0 +1,70 @@
+"""Kernel LOGIC on the CPU: the real device code of kf2vecfsw_b200/csrc/kf_kernels.cuh (decode, line-state
+resolution, byte walker, tiling, flush, fold/normalise) compiled for the host against tests/emu/cuda_emu.h
+(one OS thread per CUDA thread) and checked against the oracle.  This is not a product path -- the
+product is the nvcc build of the same header -- it exists so kernel bugs are caught before GPU time."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import kf_oracle as o
+from fuzzgen import rand_fasta
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+BIN = os.path.join(EMU, "emu_main")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_binary():
+    srcs = [os.path.join(EMU, "emu_main.cpp"), os.path.join(ROOT, "kf2vecfsw_b200", "csrc", "kf_host.cpp")]
+    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "kf2vecfsw_b200", "csrc", "kf_kernels.cuh")]
+    if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DKF_EMU", "-I", EMU, "-I", os.path.join(ROOT, "include"),
+                               "-pthread"] + srcs + ["-o", BIN])
+
+
+def run_emu(k, threads, grid, force_walker, tile_chunks, files):
+    out = subprocess.run([BIN, str(k), str(threads), str(grid), str(int(force_walker)), str(tile_chunks)] + files,
+                         capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    res = []
+    for i in range(len(files)):
+        row = np.array(out[2 * i].split(), dtype=np.uint64)
+        freq = np.array(out[2 * i + 1].split()[1:], dtype=np.float64)
+        res.append((int(row[0]), row[1:], freq))
+    return res
+
+
+def test_emulated_kernels_reproduce_toy_goldens(toy_inputs, tmp_path):
+    files = []
+    for s in ("G000830275sub", "G000402355sub", "G000830295"):   # 1 record / 43 records / 100 N
+        p = str(tmp_path / (s + ".fna"))
+        open(p, "wb").write(toy_inputs[s])
+        files.append((s, p))
+    res = run_emu(7, 64, 5, False, 64, [p for _, p in files])
+    for (s, _), (tot, counts, freq) in zip(files, res):
+        ref = o.canonical_counts_bytes(toy_inputs[s], 7)
+        vals, _ = o.row_values(ref, False, False)
+        assert np.array_equal(counts, ref), s
+        assert tot == int(ref.sum())
+        assert np.array_equal(freq, vals), s   # bit-exact fp64
+
+
+@pytest.mark.parametrize("seed0", [0, 1000])
+def test_emulated_kernels_fuzz(seed0, tmp_path):
+    for s in range(seed0, seed0 + 25):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 3)):
+            p = str(tmp_path / ("s%d_%d.fa" % (s, i)))
+            open(p, "wb").write(rand_fasta(rng))
+            files.append(p)
+        k = rng.choice([3, 4, 5, 7])
+        grid, thr, tile = rng.randint(1, 4), rng.choice([32, 64]), rng.choice([1, 2, 3, 5, 64])
+        for fw in (False, True):
+            res = run_emu(k, thr, grid, fw, tile, files)
+            for f, (tot, counts, _) in zip(files, res):
+                ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
+                assert np.array_equal(counts, ref), (s, fw, k, grid, thr, tile, f)

@@ -1,0 +1,191 @@
+// ubench.cu -- developer micro-benchmarks for the counting kernel's design choices (not product code).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I include -I kf2vecfsw_b200/csrc tools/ubench.cu -o tools/ubench
+// Run on a B200: tools/ubench [arena_MiB]
+//
+// Every variant streams the same synthetic 80-column FASTA arena (one record) and reports GB/s of file
+// bytes, bases per SM-clock (SM clock measured with clock64 inside the kernel) and ms.
+#include "kf_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+using namespace kf;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+__global__ void gen_fasta(uint8_t *arena, size_t n, int width) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint8_t c;
+        if (i < 16) c = (i == 0) ? '>' : (i == 15 ? '\n' : 'x');
+        else if ((i - 16) % (size_t)(width + 1) == (size_t)width) c = '\n';
+        else {
+            uint64_t z = i * 0x9E3779B97F4A7C15ull;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            c = "ACGT"[z & 3];
+        }
+        arena[i] = c;
+    }
+}
+
+enum Mode { FULL_PROD = 0, XOR_SINK = 1, DECODE_ONLY = 2, LOAD_ONLY = 3, ATOMS_ONLY = 4, PAIR16 = 5, SIMPLE_U32 = 6, ATOMS_ONLY_PAIR = 7 };
+
+// Fast-path-only range processor (clean input assumed) used to compare sinks.
+template <int MODE, int K>
+__device__ __forceinline__ void simple_range(const uint8_t *__restrict__ arena, uint32_t c0, uint32_t c1, uint32_t *hist,
+                                             uint32_t &sink) {
+    const int lane = threadIdx.x & 31;
+    const uint4 *base = reinterpret_cast<const uint4 *>(arena);
+    uint4 wnxt = __ldg(base + (size_t)(c0 + 1) * 32 + lane);
+    Lane cur = decode16(__ldg(base + (size_t)c0 * 32 + lane));
+    for (uint32_t c = c0; c < c1; ++c) {
+        const uint4 wnn = __ldg(base + (size_t)(c + 2) * 32 + lane);
+        if (MODE == LOAD_ONLY) { sink ^= wnxt.x ^ wnxt.y ^ wnxt.z ^ wnxt.w; wnxt = wnn; continue; }
+        const Lane nxt = decode16(wnxt);
+        if (MODE == DECODE_ONLY) { sink ^= cur.bits + cur.n; cur = nxt; wnxt = wnn; continue; }
+        const uint32_t xw = cur.bits & ~3u;
+        const uint32_t nx0 = nxt.bits & ~3u;
+        const uint32_t nb = __shfl_sync(FULL, lane == 0 ? nx0 : xw, (lane + 1) & 31);
+        uint32_t hi = cur.bits, lo = nb;
+        if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
+        if (MODE == PAIR16) {
+            // (K+1)-mers at even base offsets; u16 counters packed two per word: word = x >> 1... here
+            // word index = low 15 bits, half = top bit (any bijection works; the fold un-permutes)
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const uint32_t x = __funnelshift_l(lo, hi, 2 * j) >> (32 - 2 * (K + 1));
+                const uint32_t addend = (x >> (2 * (K + 1) - 1)) ? 0x10000u : 1u;
+                atomicAdd(hist + (x & ((1u << (2 * (K + 1) - 1)) - 1u)), addend);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j < 15 || cur.n == 16) {
+                    const uint32_t x = __funnelshift_l(lo, hi, 2 * j) >> (32 - 2 * K);
+                    if (MODE == XOR_SINK) sink ^= x * (j + 1);
+                    else atomicAdd(hist + x, 1u);
+                }
+            }
+        }
+        cur = nxt;
+        wnxt = wnn;
+    }
+}
+
+template <int MODE, int K, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+bench_kernel(const uint8_t *__restrict__ arena, uint32_t n_chunks, unsigned long long *g_out, long long *clk) {
+    extern __shared__ uint32_t hist[];
+    constexpr int NBINS = (MODE == PAIR16 || MODE == ATOMS_ONLY_PAIR) ? (1 << (2 * (K + 1) - 1)) : (1 << (2 * K));
+    for (int i = threadIdx.x; i < NBINS; i += THREADS) hist[i] = 0;
+    __syncthreads();
+    const long long t0 = clock64();
+    const uint32_t nwarps = gridDim.x * (THREADS / 32);
+    const uint32_t gw = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t per = (n_chunks + nwarps - 1) / nwarps;
+    const uint32_t c0 = gw * per, c1 = min(c0 + per, n_chunks);
+    uint32_t sink = 0;
+    if (MODE == ATOMS_ONLY || MODE == ATOMS_ONLY_PAIR) {
+        // same number of atomics as the real kernel would issue for this range, random bins, no loads
+        uint32_t s = (blockIdx.x * THREADS + threadIdx.x) * 2654435761u + 12345u;
+        const int per_iter = (MODE == ATOMS_ONLY) ? 16 : 8;
+        for (uint32_t c = c0; c < c1; ++c) {
+#pragma unroll
+            for (int j = 0; j < per_iter; j++) {
+                s = s * 1664525u + 1013904223u;
+                const uint32_t x = s >> (32 - ((MODE == ATOMS_ONLY) ? 2 * K : 2 * (K + 1) - 1));
+                atomicAdd(hist + x, (MODE == ATOMS_ONLY) ? 1u : ((s & 4096u) ? 0x10000u : 1u));
+            }
+        }
+    } else if (MODE == FULL_PROD) {
+        auto emit = [&](uint32_t x) { atomicAdd(hist + x, 1u); };
+        if (c0 < c1) fasta_process_range<K, false>(arena, c0, c1, 0u, emit);
+    } else {
+        if (c0 < c1) simple_range<MODE, K>(arena, c0, c1, hist, sink);
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    unsigned long long acc = sink;
+    for (int i = threadIdx.x; i < NBINS; i += THREADS) acc += hist[i];
+    if (acc == 0x123456789ull) g_out[1] = acc;   // keep everything alive
+    atomicAdd(g_out, acc & 0xFFFF);
+    if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE, int K, int THREADS, int MIN_CTAS>
+void run(const char *name, const uint8_t *arena, size_t bytes, int sms, unsigned long long *g_out, long long *d_clk) {
+    constexpr size_t smem = sizeof(uint32_t) * ((MODE == PAIR16 || MODE == ATOMS_ONLY_PAIR) ? (1u << (2 * (K + 1) - 1)) : (1u << (2 * K)));
+    auto kern = bench_kernel<MODE, K, THREADS, MIN_CTAS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    const int ctas = occ < MIN_CTAS ? occ : MIN_CTAS;
+    if (ctas < 1) { printf("%-34s cannot launch (occupancy 0)\n", name); return; }
+    const int grid = sms * ctas;
+    const uint32_t n_chunks = (uint32_t)(bytes / CHUNK);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    std::vector<long long> clk(grid);
+    long long maxclk = 0;
+    for (int it = 0; it < 5; it++) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, THREADS, smem>>>(arena, n_chunks, g_out, d_clk);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 1 && ms < best) {
+            best = ms;
+            CK(cudaMemcpy(clk.data(), d_clk, grid * sizeof(long long), cudaMemcpyDeviceToHost));
+            maxclk = 0;
+            for (auto c : clk) if (c > maxclk) maxclk = c;
+        }
+    }
+    const double bases = (double)bytes * 80.0 / 81.0;
+    const double gbs = (double)bytes / best / 1e6;
+    const double bpc = bases / ((double)maxclk * sms);
+    printf("%-34s thr=%4d ctas/SM=%d  %8.3f ms  %8.1f GB/s  %6.3f Tbases/s  %6.2f bases/clk/SM  clk=%.0f MHz  (%.1f%% of 6550)\n", name, THREADS,
+           ctas, best, gbs, bases / best / 1e9, bpc, (double)maxclk / best / 1e3, 100.0 * gbs * 1.02 / 6550.0);
+}
+
+int main(int argc, char **argv) {
+    size_t mib = argc > 1 ? (size_t)atol(argv[1]) : 1024;
+    size_t bytes = mib << 20;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("device %s  SMs %d  max clk %d MHz  arena %zu MiB\n", prop.name, prop.multiProcessorCount, prop.clockRate / 1000, mib);
+    uint8_t *arena;
+    CK(cudaMalloc(&arena, bytes + 4 * CHUNK));
+    CK(cudaMemset(arena, 0, bytes + 4 * CHUNK));
+    gen_fasta<<<prop.multiProcessorCount * 8, 256>>>(arena, bytes, 80);
+    CK(cudaDeviceSynchronize());
+    unsigned long long *g_out; long long *d_clk;
+    CK(cudaMalloc(&g_out, 16)); CK(cudaMemset(g_out, 0, 16));
+    CK(cudaMalloc(&d_clk, sizeof(long long) * 4096));
+    const int sms = prop.multiProcessorCount;
+    run<LOAD_ONLY, 7, 512, 2>("load only (LDG.128 stream)", arena, bytes, sms, g_out, d_clk);
+    run<DECODE_ONLY, 7, 512, 2>("load+decode16", arena, bytes, sms, g_out, d_clk);
+    run<XOR_SINK, 7, 512, 2>("load+decode+extract (xor sink)", arena, bytes, sms, g_out, d_clk);
+    run<ATOMS_ONLY, 7, 512, 2>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
+    run<ATOMS_ONLY, 7, 1024, 1>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
+    run<ATOMS_ONLY, 7, 256, 3>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
+    run<ATOMS_ONLY, 5, 512, 2>("atomics only u32 1024 bins", arena, bytes, sms, g_out, d_clk);
+    run<ATOMS_ONLY_PAIR, 7, 1024, 1>("atomics only pair16 32768 words", arena, bytes, sms, g_out, d_clk);
+    run<SIMPLE_U32, 7, 512, 2>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
+    run<SIMPLE_U32, 7, 1024, 1>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
+    run<SIMPLE_U32, 7, 256, 3>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
+    run<SIMPLE_U32, 7, 256, 2>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
+    run<PAIR16, 7, 1024, 1>("simple fast path pair16", arena, bytes, sms, g_out, d_clk);
+    run<PAIR16, 7, 512, 1>("simple fast path pair16", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 512, 2>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 1024, 1>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 256, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 5, 512, 2>("production range processor k=5", arena, bytes, sms, g_out, d_clk);
+    printf("done\n");
+    return 0;
+}
