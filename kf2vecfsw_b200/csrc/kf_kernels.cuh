@@ -20,6 +20,7 @@
 #else
 #include <cuda_runtime.h>
 #define KF_DYN_SMEM(type, name) extern __shared__ type name[]
+#define KF_NOINLINE __noinline__
 #endif
 #include <stdint.h>
 
@@ -42,7 +43,6 @@ struct Lane {
     uint32_t bits;     // up to 16 bases, 2 bits each, first base in bits 31:30, zero-filled tail
     uint32_t n;        // 16, or 15 when one '\n' was removed
     uint32_t dirty;    // 1: holds a BREAK byte or more than one '\n' -> byte walker
-    uint32_t last_nl;  // byte 15 is '\n'
 };
 
 // V == 0 for a byte  <=>  the byte is one of ACGTacgt.  Checked bits: 7,6,4,3,0 (bit 5 = case and
@@ -68,7 +68,6 @@ __device__ __forceinline__ Lane decode16(const uint4 w) {
     Lane L;
     L.n = 16;
     L.dirty = 0;
-    L.last_nl = ((w.w >> 24) == 0x0Au) ? 1u : 0u;
     const uint32_t anyV = V0 | V1 | V2 | V3;
     if (anyV) {
         uint32_t wi, Vw, ww, rest;
@@ -106,8 +105,9 @@ __device__ __forceinline__ bool is_base(uint32_t c) {
 // FASTA line state.  State at a byte position = (hdr: inside a '>' header line, ls: at a line start)
 // ------------------------------------------------------------------------------------------------
 // State at the first byte of every lane of one chunk, given the state at the chunk's first byte.
-__device__ __forceinline__ void fasta_resolve(const uint4 w, bool carry_hdr, bool carry_ls, int lane,
-                                              bool &in_hdr, bool &in_ls, bool &out_hdr) {
+// Returns in_hdr | in_ls << 1 | out_hdr << 2 (state at this lane's first byte; state after the chunk).
+__device__ KF_NOINLINE uint32_t fasta_resolve(const uint4 w, bool carry_hdr, bool carry_ls, int lane) {
+    bool in_hdr, in_ls, out_hdr;
     bool has_nl = false;
     int last = -1;
 #pragma unroll
@@ -140,12 +140,14 @@ __device__ __forceinline__ void fasta_resolve(const uint4 w, bool carry_hdr, boo
     state_before(lane, in_hdr, in_ls);
     bool dummy;
     state_before(32, out_hdr, dummy);
+    return (in_hdr ? 1u : 0u) | (in_ls ? 2u : 0u) | (out_hdr ? 4u : 0u);
 }
 
 // State at the first byte of chunk c (file starts at chunk file_c0): scan back to the previous '\n'.
-__device__ __forceinline__ void fasta_backscan(const uint8_t *__restrict__ arena, uint32_t c, uint32_t file_c0,
-                                               int lane, bool &hdr, bool &ls) {
-    if (c == file_c0) { hdr = false; ls = true; return; }
+// Returns hdr | ls << 1.
+__device__ KF_NOINLINE uint32_t fasta_backscan(const uint8_t *__restrict__ arena, uint32_t c, uint32_t file_c0,
+                                            int lane) {
+    if (c == file_c0) return 2u;
     const uint4 *base = reinterpret_cast<const uint4 *>(arena);
     for (uint32_t b = c; b-- > file_c0;) {
         const uint4 w = __ldg(base + (size_t)b * 32 + lane);
@@ -158,18 +160,16 @@ __device__ __forceinline__ void fasta_backscan(const uint8_t *__restrict__ arena
             const int j = 31 - __clz((int)B);
             const int lastj = __shfl_sync(FULL, last, j);
             const uint64_t q = (uint64_t)b * CHUNK + (uint64_t)j * 16 + (uint64_t)lastj;   // last '\n' before chunk c
-            if (q + 1 == (uint64_t)c * CHUNK) { hdr = false; ls = true; }
-            else { hdr = (arena[q + 1] == (uint8_t)'>'); ls = false; }
-            return;
+            if (q + 1 == (uint64_t)c * CHUNK) return 2u;
+            return (arena[q + 1] == (uint8_t)'>') ? 1u : 0u;
         }
     }
-    hdr = (arena[(uint64_t)file_c0 * CHUNK] == (uint8_t)'>');   // still on the file's first line
-    ls = false;
+    return (arena[(uint64_t)file_c0 * CHUNK] == (uint8_t)'>') ? 1u : 0u;   // still on the file's first line
 }
 
 // Byte walker for one lane: counts every k-mer whose first base lies in [p0, p0+16).
 template <int K, class Emit>
-__device__ __forceinline__ void fasta_walk_lane(const uint8_t *__restrict__ arena, uint64_t p0, bool in_hdr,
+__device__ KF_NOINLINE void fasta_walk_lane(const uint8_t *__restrict__ arena, uint64_t p0, bool in_hdr,
                                                 bool at_ls, Emit emit) {
     constexpr uint32_t MASK = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
     uint32_t kmer = 0;
@@ -200,59 +200,102 @@ __device__ __forceinline__ void fasta_walk_lane(const uint8_t *__restrict__ aren
 // ------------------------------------------------------------------------------------------------
 // One warp over the chunk range [c0, c1) of a FASTA file
 // ------------------------------------------------------------------------------------------------
-template <int K, bool FORCE_WALKER, class Emit>
+// Byte offset (4 * k-mer) of the k-mer starting at base j of the 32-base window hi:lo (first base in hi
+// bits 31:30).  j is a compile-time constant after unrolling: one shift or funnel shift plus one mask.
+template <int K>
+__device__ __forceinline__ uint32_t kmer_off_at(uint32_t hi, uint32_t lo, int j) {
+    constexpr uint32_t MASK4 = ((1u << (2 * K)) - 1u) << 2;
+    const int r = 62 - 2 * K - 2 * j;   // >= 8 for K <= 12, j <= 15
+    return ((r >= 32) ? (hi >> (r - 32)) : __funnelshift_r(lo, hi, r)) & MASK4;
+}
+
+// PF = 512-byte chunks kept in flight per warp (register ring; the loop is unrolled PF times so the ring
+// rotates at compile time).  Sinks take the byte offset 4*kmer.
+template <int K, bool FORCE_WALKER, int PF, class Sink>
 __device__ __forceinline__ void fasta_process_range(const uint8_t *__restrict__ arena, uint32_t c0, uint32_t c1,
-                                                    uint32_t file_c0, Emit emit) {
+                                                    uint32_t file_c0, Sink sink) {
+    static_assert(PF >= 2 && PF <= 6, "prefetch depth");
     const int lane = threadIdx.x & 31;
-    const uint4 *base = reinterpret_cast<const uint4 *>(arena);
-    bool carry_hdr, carry_ls;
-    fasta_backscan(arena, c0, file_c0, lane, carry_hdr, carry_ls);
-    uint4 wcur = __ldg(base + (size_t)c0 * 32 + lane);
-    uint4 wnxt = __ldg(base + (size_t)(c0 + 1) * 32 + lane);
-    Lane cur = decode16(wcur);
-    uint32_t prev_last_nl = carry_ls ? 1u : 0u;
-    for (uint32_t c = c0; c < c1; ++c) {
-        const uint4 wnn = __ldg(base + (size_t)(c + 2) * 32 + lane);   // prefetch distance 2
-        const Lane nxt = decode16(wnxt);
-        const unsigned any_dirty = __ballot_sync(FULL, cur.dirty);
-        bool in_hdr = false, in_ls = false, next_hdr = false;
-        if (any_dirty | (unsigned)carry_hdr) {
-            const bool cls = __shfl_sync(FULL, prev_last_nl, 31) != 0;
-            fasta_resolve(wcur, carry_hdr, cls, lane, in_hdr, in_ls, next_hdr);
-        }
-        const uint32_t slowflag = cur.dirty | (in_hdr ? 1u : 0u);
-        const uint32_t xw = (cur.bits & ~3u) | slowflag;
-        const uint32_t nx0 = (nxt.bits & ~3u) | nxt.dirty | (next_hdr ? 1u : 0u);
-        const uint32_t nbw = __shfl_sync(FULL, lane == 0 ? nx0 : xw, (lane + 1) & 31);
-        const bool slow = FORCE_WALKER || slowflag || (nbw & 1u);
-        if (!slow) {
-            const uint32_t nb = nbw & ~3u;
-            uint32_t hi = cur.bits, lo = nb;
-            if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
+    const uint4 *base = reinterpret_cast<const uint4 *>(arena) + lane;
+    bool carry_hdr = (fasta_backscan(arena, c0, file_c0, lane) & 1u) != 0;
+    // slot[u] holds chunk (group base + u); after chunk cc is consumed its slot is refilled with chunk cc+PF.
+    // Loads are clamped to chunk c1+1, which the arena's two NUL tail chunks keep in bounds.
+    const uint32_t cmax = c1 + 1;
+    uint4 slot[PF];
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j < 15 || cur.n == 16) {
-                    const uint32_t x = __funnelshift_l(lo, hi, 2 * j) >> (32 - 2 * K);
-                    emit(x);
+    for (int i = 0; i < PF; i++) slot[i] = __ldg(base + (size_t)min(c0 + i, cmax) * 32);
+    Lane cur = decode16(slot[0]);
+    auto emit = [&](uint32_t x) { sink(x << 2); };
+    for (uint32_t cg = c0; cg < c1; cg += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const uint32_t c = cg + u;
+            if (c < c1) {
+                const uint4 wcur = slot[u];
+                const Lane nxt = decode16(slot[(u + 1) % PF]);
+                const unsigned any_dirty = __ballot_sync(FULL, cur.dirty);
+                uint32_t st = 0;   // in_hdr | in_ls << 1 | next chunk starts inside a header << 2
+                if (any_dirty | (unsigned)carry_hdr) {
+                    const bool cls = (c == file_c0) || arena[(uint64_t)c * CHUNK - 1] == 0x0Au;
+                    st = fasta_resolve(wcur, carry_hdr, cls, lane);
                 }
+                const uint32_t slowflag = cur.dirty | (st & 1u);
+                const uint32_t xw = (cur.bits & ~3u) | slowflag;
+                const uint32_t nx0 = (nxt.bits & ~3u) | nxt.dirty | ((st >> 2) & 1u);
+                const uint32_t nbw = __shfl_sync(FULL, lane == 0 ? nx0 : xw, (lane + 1) & 31);
+                const bool slow = FORCE_WALKER || slowflag || (nbw & 1u);
+                if (!slow) {
+                    const uint32_t nb = nbw & ~3u;
+                    uint32_t hi = cur.bits, lo = nb;
+                    if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
+#pragma unroll
+                    for (int j = 0; j < 15; j++) sink(kmer_off_at<K>(hi, lo, j));
+                    if (cur.n == 16) sink(kmer_off_at<K>(hi, lo, 15));
+                } else {
+                    fasta_walk_lane<K>(arena, (uint64_t)c * CHUNK + (uint64_t)lane * 16, (st & 1u) != 0, (st & 2u) != 0, emit);
+                }
+                carry_hdr = (st & 4u) != 0;
+                cur = nxt;
+                slot[u] = __ldg(base + (size_t)min(c + PF, cmax) * 32);
             }
-        } else {
-            fasta_walk_lane<K>(arena, (uint64_t)c * CHUNK + (uint64_t)lane * 16, in_hdr, in_ls, emit);
         }
-        prev_last_nl = cur.last_nl;
-        carry_hdr = next_hdr;
-        cur = nxt;
-        wcur = wnxt;
-        wnxt = wnn;
     }
 }
+
+// Sinks: where a counted forward k-mer goes.
+struct SmemSink {   // per-CTA privatised u32 histogram in shared memory
+#ifdef KF_EMU
+    uint32_t *hist;
+    __device__ __forceinline__ void operator()(uint32_t off) const { atomicAdd(hist + (off >> 2), 1u); }
+#else
+    uint32_t base;  // shared-window byte address of bin 0
+    __device__ __forceinline__ void operator()(uint32_t off) const {
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + off) : "memory");
+    }
+#endif
+};
+__device__ __forceinline__ SmemSink make_smem_sink(uint32_t *hist) {
+    SmemSink s;
+#ifdef KF_EMU
+    s.hist = hist;
+#else
+    s.base = (uint32_t)__cvta_generic_to_shared(hist);
+#endif
+    return s;
+}
+struct GmemSink {   // dense u32 forward counts of one file in global memory (k >= 8)
+    uint32_t *g;
+    __device__ __forceinline__ void operator()(uint32_t off) const {
+        atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g) + off), 1u);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Counting kernels
 // ------------------------------------------------------------------------------------------------
 // k <= 7: per-CTA privatised u32 histogram in shared memory, flushed to the per-file u64 forward
 // counts when the CTA moves to another file.  Persistent: CTA b owns tiles [cta_begin[b], cta_begin[b+1]).
-template <int K, int THREADS, int MIN_CTAS, bool FORCE_WALKER>
+template <int K, int THREADS, int MIN_CTAS, bool FORCE_WALKER, int PF = 3>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles,
                         const int *__restrict__ cta_begin, unsigned long long *__restrict__ g_fwd) {
@@ -272,7 +315,7 @@ count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
         }
         __syncthreads();
     };
-    auto emit = [&](uint32_t x) { atomicAdd(hist + x, 1u); };
+    const SmemSink emit = make_smem_sink(hist);
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
         const Tile T = tiles[t];
@@ -284,7 +327,7 @@ count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
         const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
         const uint32_t cend = T.first_chunk + T.n_chunks;
         const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-        if (c0 < c1) fasta_process_range<K, FORCE_WALKER>(arena, c0, c1, T.file_chunk0, emit);
+        if (c0 < c1) fasta_process_range<K, FORCE_WALKER, PF>(arena, c0, c1, T.file_chunk0, emit);
     }
     if (cur_file >= 0) flush(cur_file);
 }
@@ -301,13 +344,13 @@ count_fasta_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
         const Tile T = tiles[t];
-        uint32_t *g = g_fwd32 + (size_t)(T.file - file_base) * NB;
-        auto emit = [&](uint32_t x) { atomicAdd(g + x, 1u); };
+        GmemSink emit;
+        emit.g = g_fwd32 + (size_t)(T.file - file_base) * NB;
         const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
         const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
         const uint32_t cend = T.first_chunk + T.n_chunks;
         const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-        if (c0 < c1) fasta_process_range<K, FORCE_WALKER>(arena, c0, c1, T.file_chunk0, emit);
+        if (c0 < c1) fasta_process_range<K, FORCE_WALKER, 3>(arena, c0, c1, T.file_chunk0, emit);
     }
 }
 

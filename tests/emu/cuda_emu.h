@@ -18,6 +18,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define KF_NOINLINE
 
 struct uint4 { uint32_t x, y, z, w; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; };
@@ -91,6 +92,11 @@ inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
     sh &= 31;
     return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;
 }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 #define __shared__ static

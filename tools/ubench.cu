@@ -76,7 +76,7 @@ __device__ __forceinline__ void simple_range(const uint8_t *__restrict__ arena, 
     }
 }
 
-template <int MODE, int K, int THREADS, int MIN_CTAS>
+template <int MODE, int K, int THREADS, int MIN_CTAS, int PF>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 bench_kernel(const uint8_t *__restrict__ arena, uint32_t n_chunks, unsigned long long *g_out, long long *clk) {
     extern __shared__ uint32_t hist[];
@@ -102,8 +102,8 @@ bench_kernel(const uint8_t *__restrict__ arena, uint32_t n_chunks, unsigned long
             }
         }
     } else if (MODE == FULL_PROD) {
-        auto emit = [&](uint32_t x) { atomicAdd(hist + x, 1u); };
-        if (c0 < c1) fasta_process_range<K, false>(arena, c0, c1, 0u, emit);
+        const SmemSink sink = make_smem_sink(hist);
+        if (c0 < c1) fasta_process_range<K, false, PF>(arena, c0, c1, 0u, sink);
     } else {
         if (c0 < c1) simple_range<MODE, K>(arena, c0, c1, hist, sink);
     }
@@ -116,10 +116,10 @@ bench_kernel(const uint8_t *__restrict__ arena, uint32_t n_chunks, unsigned long
     if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
 }
 
-template <int MODE, int K, int THREADS, int MIN_CTAS>
+template <int MODE, int K, int THREADS, int MIN_CTAS, int PF = 3>
 void run(const char *name, const uint8_t *arena, size_t bytes, int sms, unsigned long long *g_out, long long *d_clk) {
     constexpr size_t smem = sizeof(uint32_t) * ((MODE == PAIR16 || MODE == ATOMS_ONLY_PAIR) ? (1u << (2 * (K + 1) - 1)) : (1u << (2 * K)));
-    auto kern = bench_kernel<MODE, K, THREADS, MIN_CTAS>;
+    auto kern = bench_kernel<MODE, K, THREADS, MIN_CTAS, PF>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
@@ -149,7 +149,7 @@ void run(const char *name, const uint8_t *arena, size_t bytes, int sms, unsigned
     const double bases = (double)bytes * 80.0 / 81.0;
     const double gbs = (double)bytes / best / 1e6;
     const double bpc = bases / ((double)maxclk * sms);
-    printf("%-34s thr=%4d ctas/SM=%d  %8.3f ms  %8.1f GB/s  %6.3f Tbases/s  %6.2f bases/clk/SM  clk=%.0f MHz  (%.1f%% of 6550)\n", name, THREADS,
+    printf("%-34s PF=%d thr=%4d ctas/SM=%d  %8.3f ms  %8.1f GB/s  %6.3f Tbases/s  %6.2f bases/clk/SM  clk=%.0f MHz  (%.1f%% of 6550)\n", name, PF, THREADS,
            ctas, best, gbs, bases / best / 1e9, bpc, (double)maxclk / best / 1e3, 100.0 * gbs * 1.02 / 6550.0);
 }
 
@@ -172,20 +172,17 @@ int main(int argc, char **argv) {
     run<DECODE_ONLY, 7, 512, 2>("load+decode16", arena, bytes, sms, g_out, d_clk);
     run<XOR_SINK, 7, 512, 2>("load+decode+extract (xor sink)", arena, bytes, sms, g_out, d_clk);
     run<ATOMS_ONLY, 7, 512, 2>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
-    run<ATOMS_ONLY, 7, 1024, 1>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
-    run<ATOMS_ONLY, 7, 256, 3>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
-    run<ATOMS_ONLY, 5, 512, 2>("atomics only u32 1024 bins", arena, bytes, sms, g_out, d_clk);
-    run<ATOMS_ONLY_PAIR, 7, 1024, 1>("atomics only pair16 32768 words", arena, bytes, sms, g_out, d_clk);
     run<SIMPLE_U32, 7, 512, 2>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
-    run<SIMPLE_U32, 7, 1024, 1>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
-    run<SIMPLE_U32, 7, 256, 3>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
-    run<SIMPLE_U32, 7, 256, 2>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
-    run<PAIR16, 7, 1024, 1>("simple fast path pair16", arena, bytes, sms, g_out, d_clk);
-    run<PAIR16, 7, 512, 1>("simple fast path pair16", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 512, 2>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 1024, 1>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 256, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 5, 512, 2>("production range processor k=5", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 512, 2, 2>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 512, 2, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 512, 2, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 1024, 1, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 256, 3, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 256, 3, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 256, 3, 6>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 384, 2, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 7, 384, 2, 6>("production range processor", arena, bytes, sms, g_out, d_clk);
+    run<FULL_PROD, 5, 512, 2, 3>("production range processor k=5", arena, bytes, sms, g_out, d_clk);
     printf("done\n");
     return 0;
 }
