@@ -41,12 +41,14 @@ extern "C" {
 #define KF_FLAG_PSEUDOCOUNT 1u   /* main.py:332-334  counts += 0.5 before normalising           */
 #define KF_FLAG_RAW_CNT 2u       /* main.py:340-342  skip the normalisation                      */
 #define KF_FLAG_FORCE_WALKER 4u  /* debug: disable the vectorised fast path (byte walker only)   */
+#define KF_FLAG_NO_LINEGRID 8u   /* debug: skip the fixed-line-width kernel (generic kernel only) */
 
 /* limits */
 #define KF_MIN_K 1
 #define KF_MAX_K 12              /* dense canonical output up to k=12 (8,390,656 columns)        */
 #define KF_MAX_K_SMEM 7          /* 4^k u32 bins privatised in shared memory up to here          */
 #define KF_CHUNK 512             /* arena alignment unit: one warp-load of 32 x 16 bytes         */
+#define KF_TAIL_PAD 4096         /* NUL bytes required after the last file of a device arena     */
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
 /* Selects the CUDA device, checks it is sm_100, creates the library's stream and workspace.
@@ -84,7 +86,7 @@ int kf_count_files(const char *const *paths, int n, int k, uint32_t flags,
 /* ---- counting, device-resident arena (kernel-only path; trainer hand-off) --------------------- */
 /* Arena layout contract: file i occupies d_arena[offsets[i] .. offsets[i]+lens[i]); offsets[i] is a
  * multiple of KF_CHUNK; files are in increasing offset order and do not overlap; every byte of the
- * arena that belongs to no file is 0; at least 2*KF_CHUNK zero bytes follow the last file
+ * arena that belongs to no file is 0; at least KF_TAIL_PAD zero bytes follow the last file
  * (arena_bytes says how much is allocated).  formats[i] is '>' or '@' (first byte of file i).
  * Outputs are device pointers (any may be NULL): d_counts [n][V] uint64, d_freq [n][V] double,
  * d_feat [n][V] float = fp32(freq * 1e4) (train_classifier_model.py:149,323), d_totals [n] uint64.
@@ -115,6 +117,9 @@ int kf_write_kf(const char *out_path, const char *sample, const double *row, int
  * Call with out == NULL to get the exact size.  Returns bytes written or a negative error. */
 int64_t kf_synth_fasta(uint64_t seed, int64_t genome_id, int64_t n_bases, int line_width, uint8_t *out,
                        size_t out_len);
+/* Same with the contig count capped at max_contigs and n_runs N-runs (kf_synth_fasta = 50, 10). */
+int64_t kf_synth_fasta_ex(uint64_t seed, int64_t genome_id, int64_t n_bases, int line_width, int max_contigs,
+                          int n_runs, uint8_t *out, size_t out_len);
 /* 4-line FASTQ: n_reads x read_len sampled from a seed-derived genome of genome_len bases, random
  * strand, per-base N 0.2 %, 1 % of reads with an N-run, qualities '!'..'J' (may start with '@'/'+'). */
 int64_t kf_synth_fastq(uint64_t seed, int64_t sample_id, int64_t genome_len, int64_t n_reads,

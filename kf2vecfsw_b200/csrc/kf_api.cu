@@ -18,6 +18,7 @@ namespace {
 constexpr int THREADS_SMEM = 512;   // 16 warps; 2 CTAs/SM -> 32 warps/SM, 64 regs/thread
 constexpr int CTAS_PER_SM = 2;
 constexpr int THREADS_GMEM = 512;
+constexpr int THREADS_LG = 512;     // line-grid kernel: 1 CTA/SM (128 KiB pair histogram + per-warp TMA staging)
 constexpr uint32_t TILE_CHUNKS = 1024;                 // 512 KiB per tile: 64 chunks per warp
 constexpr size_t GMEM_WS_LIMIT = (size_t)12 << 30;     // forward-count workspace cap for k >= 8
 
@@ -32,6 +33,12 @@ struct Ctx {
     Tile *d_tiles = nullptr; size_t tiles_cap = 0;
     int *d_cta_begin = nullptr; size_t cta_cap = 0;
     uint32_t *d_canon[KF_MAX_K + 1] = {nullptr};
+    uint64_t *d_file_off = nullptr; size_t foff_cap = 0;
+    uint64_t *d_file_len = nullptr; size_t flen_cap = 0;
+    uint8_t *d_formats = nullptr; size_t fmt_cap = 0;
+    uint32_t *d_file_P = nullptr; size_t fP_cap = 0;
+    uint32_t *d_width_counts = nullptr;
+    unsigned long long *d_scratch = nullptr; size_t scratch_cap = 0;
     // end-to-end staging
     uint8_t *d_arena = nullptr; size_t arena_cap = 0;
     unsigned long long *d_counts = nullptr; size_t counts_cap = 0;
@@ -118,6 +125,19 @@ void build_plan(const uint64_t *offsets, const uint64_t *lens, const uint8_t *fo
     while (cta < grid) { cta++; cta_begin[(size_t)cta] = (int)tiles.size(); }
 }
 
+template <int LW>
+int launch_linegrid(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
+    using G = LineGrid<LW>;
+    constexpr int NW = THREADS_LG / 32;
+    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * 2 * G::STAGE + 2 * NW * sizeof(uint64_t) + 2 * sizeof(unsigned long long) + 16;
+    auto kern = count_fasta_linegrid_kernel<LW, THREADS_LG>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
+                                                             (unsigned long long *)g.d_fwd, g.d_scratch, CTAS_PER_SM, g.d_width_counts);
+    CK(cudaGetLastError());
+    return KF_OK;
+}
+
 template <int K>
 int launch_smem(const uint8_t *d_arena, int grid, bool force_walker, cudaStream_t s) {
     constexpr size_t smem = sizeof(uint32_t) << (2 * K);
@@ -125,11 +145,11 @@ int launch_smem(const uint8_t *d_arena, int grid, bool force_walker, cudaStream_
     if (force_walker) {
         auto kern = count_fasta_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM, true>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd);
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, g.d_file_P, g.d_width_counts);
     } else {
         auto kern = count_fasta_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM, false>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd);
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, g.d_file_P, g.d_width_counts);
     }
     CK(cudaGetLastError());
     return KF_OK;
@@ -193,23 +213,54 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         CK(cudaDeviceSynchronize());
         if (!tiles.empty()) CK(cudaMemcpy(g.d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(g.d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+        // per-file tables are indexed by batch-global file id
+        if ((rc = ensure(g.d_file_off, g.foff_cap, (size_t)f1 * sizeof(uint64_t))) != KF_OK) return rc;
+        if ((rc = ensure(g.d_file_len, g.flen_cap, (size_t)f1 * sizeof(uint64_t))) != KF_OK) return rc;
+        if ((rc = ensure(g.d_formats, g.fmt_cap, (size_t)f1)) != KF_OK) return rc;
+        if ((rc = ensure(g.d_file_P, g.fP_cap, (size_t)f1 * sizeof(uint32_t))) != KF_OK) return rc;
+        CK(cudaMemcpy(g.d_file_off, offsets, (size_t)f1 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(g.d_file_len, lens, (size_t)f1 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(g.d_formats, formats, (size_t)f1, cudaMemcpyHostToDevice));
         g.pc_k = k; g.pc_grid = grid; g.pc_f0 = f0; g.pc_f1 = f1; g.pc_ntiles = (int)tiles.size();
         g.pc_offsets.assign(offsets + f0, offsets + f1);
         g.pc_lens.assign(lens + f0, lens + f1);
         g.pc_formats.assign(formats + f0, formats + f1);
     }
     CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));
+    const bool force_walker = (flags & KF_FLAG_FORCE_WALKER) != 0;
+    const bool use_lg = smem_path && k == 7 && !force_walker && !(flags & KF_FLAG_NO_LINEGRID);
     if (g.pc_ntiles > 0) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
+        // line width per file (0 = generic kernel), then one line-grid launch per supported width
+        CK(cudaMemsetAsync(g.d_width_counts, 0, 4 * sizeof(uint32_t), s));
+        probe_line_width_kernel<<<(f1 + 127) / 128, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, (int)f1,
+                                                                use_lg ? 0u : 1u, g.d_file_P, g.d_width_counts);
+        CK(cudaGetLastError());
+        g.last_launches++;
+        if (use_lg) {
+            const size_t sc_bytes = (size_t)(grid / CTAS_PER_SM) * 16384 * sizeof(unsigned long long);
+            if (sc_bytes > g.scratch_cap) {
+                if ((rc = ensure(g.d_scratch, g.scratch_cap, sc_bytes)) != KF_OK) return rc;
+                CK(cudaMemsetAsync(g.d_scratch, 0, g.scratch_cap, s));   // kept zero by the kernel afterwards
+            }
+            void *saved = g.d_fwd;
+            g.d_fwd = (void *)((unsigned long long *)saved - (size_t)f0 * NB);
+            rc = launch_linegrid<80>(d_arena, grid, s);
+            if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
+            if (rc == KF_OK) rc = launch_linegrid<70>(d_arena, grid, s);
+            g.d_fwd = saved;
+            if (rc != KF_OK) return rc;
+            g.last_launches += 3;
+        }
         // file indices inside tiles are batch-global; forward rows are relative to f0
         if (smem_path) {
             // smem kernels index g_fwd by absolute file id: shift the base pointer
             void *saved = g.d_fwd;
             g.d_fwd = (void *)((unsigned long long *)saved - (size_t)f0 * NB);
-            rc = launch_count(k, d_arena, grid, (flags & KF_FLAG_FORCE_WALKER) != 0, f0, s);
+            rc = launch_count(k, d_arena, grid, force_walker, f0, s);
             g.d_fwd = saved;
         } else {
-            rc = launch_count(k, d_arena, grid, (flags & KF_FLAG_FORCE_WALKER) != 0, f0, s);
+            rc = launch_count(k, d_arena, grid, force_walker, f0, s);
         }
         if (rc != KF_OK) return rc;
         CK(cudaEventRecord(g.ev_k1, s));
@@ -237,7 +288,7 @@ int count_device_locked(const uint8_t *d_arena, size_t arena_bytes, const uint64
         if (offsets[i] % CHUNK != 0 || offsets[i] < prev_end) return KF_ERR_LAYOUT;
         prev_end = offsets[i] + lens[i];
     }
-    if (prev_end + 2 * CHUNK > arena_bytes) return KF_ERR_LAYOUT;
+    if (prev_end + KF_TAIL_PAD > arena_bytes) return KF_ERR_LAYOUT;
     if ((prev_end + CHUNK - 1) / CHUNK + 2 >= 0xFFFFFFFFull) return KF_ERR_ARG;
     g.last_launches = 0;
     g.ev_valid = false;
@@ -277,6 +328,7 @@ int kf_init(int device) {
     CK(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
     CK(cudaEventCreate(&g.ev_k0));
     CK(cudaEventCreate(&g.ev_k1));
+    CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
     g.sm_count = prop.multiProcessorCount;
     g.device = device;
     return KF_OK;
@@ -288,6 +340,7 @@ int kf_shutdown(void) {
     cudaDeviceSynchronize();
     cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
     cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals);
+    cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_scratch); cudaFree(g.d_width_counts);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
     cudaEventDestroy(g.ev_k0); cudaEventDestroy(g.ev_k1);
@@ -339,7 +392,7 @@ int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens_in, int n, i
         lens[(size_t)i] = L;
         off += (L + CHUNK - 1) / CHUNK * CHUNK;
     }
-    const size_t arena_bytes = off + 2 * CHUNK;
+    const size_t arena_bytes = off + KF_TAIL_PAD;
     int rc;
     if ((rc = ensure(g.d_arena, g.arena_cap, arena_bytes)) != KF_OK) return rc;
     if ((rc = ensure(g.d_counts, g.counts_cap, (size_t)n * V * sizeof(unsigned long long))) != KF_OK) return rc;

@@ -110,10 +110,11 @@ struct GenomePlan {
     std::vector<std::pair<int64_t, int64_t>> nruns;  // [start, end) in genome coordinates
 };
 
-static void plan_genome(uint64_t seed, int64_t id, int64_t n_bases, GenomePlan &P) {
+static void plan_genome(uint64_t seed, int64_t id, int64_t n_bases, GenomePlan &P, int max_contigs = 50, int n_runs = 10) {
     SplitMix r(mix_seed(seed, (uint64_t)id, 1));
     P.gc = 0.30 + 0.40 * r.uniform();
     int64_t c = 1 + (int64_t)r.below(50);
+    if (c > max_contigs) c = max_contigs;
     if (n_bases < 1000 * c) c = n_bases / 1000 > 0 ? n_bases / 1000 : 1;
     std::vector<double> w((size_t)c);
     double sw = 0;
@@ -129,7 +130,7 @@ static void plan_genome(uint64_t seed, int64_t id, int64_t n_bases, GenomePlan &
     }
     P.nruns.clear();
     if (n_bases > 200) {
-        for (int i = 0; i < 10; i++) {
+        for (int i = 0; i < n_runs; i++) {
             int64_t len = 1 + (int64_t)r.below(100);
             int64_t s = (int64_t)r.below((uint64_t)(n_bases - len));
             P.nruns.push_back({s, s + len});
@@ -242,9 +243,14 @@ int kf_write_kf(const char *out_path, const char *sample, const double *row, int
 
 int64_t kf_synth_fasta(uint64_t seed, int64_t genome_id, int64_t n_bases, int line_width, uint8_t *out,
                        size_t out_len) {
-    if (n_bases < 0 || line_width < 1) return KF_ERR_ARG;
+    return kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, 50, 10, out, out_len);
+}
+
+int64_t kf_synth_fasta_ex(uint64_t seed, int64_t genome_id, int64_t n_bases, int line_width, int max_contigs,
+                          int n_runs, uint8_t *out, size_t out_len) {
+    if (n_bases < 0 || line_width < 1 || max_contigs < 1 || n_runs < 0) return KF_ERR_ARG;
     kf::GenomePlan P;
-    kf::plan_genome(seed, genome_id, n_bases, P);
+    kf::plan_genome(seed, genome_id, n_bases, P, max_contigs, n_runs);
     // size
     int64_t total = 0;
     std::vector<std::string> hdr(P.contig_len.size());

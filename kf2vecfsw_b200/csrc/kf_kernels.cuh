@@ -167,19 +167,46 @@ __device__ KF_NOINLINE uint32_t fasta_backscan(const uint8_t *__restrict__ arena
     return (arena[(uint64_t)file_c0 * CHUNK] == (uint8_t)'>') ? 1u : 0u;   // still on the file's first line
 }
 
-// Byte walker for one lane: counts every k-mer whose first base lies in [p0, p0+16).
-template <int K, class Emit>
-__device__ KF_NOINLINE void fasta_walk_lane(const uint8_t *__restrict__ arena, uint64_t p0, bool in_hdr,
-                                                bool at_ls, Emit emit) {
+// Where sequence bytes are read from.  GlobalSrc: the arena in HBM.  WindowSrc: the same, but bytes that lie in
+// the window [w0, w0+wlen) the line-grid kernel has staged in shared memory are served from there, so its
+// off-grid handling does not pay global round trips under a saturated memory system.
+struct GlobalSrc {
+    const uint8_t *arena;
+    __device__ __forceinline__ uint4 load16(uint32_t chunk, int lane) const {
+        return __ldg(reinterpret_cast<const uint4 *>(arena) + (size_t)chunk * 32 + lane);
+    }
+    __device__ __forceinline__ uint32_t byte(uint64_t p) const { return arena[p]; }
+};
+struct WindowSrc {
+    const uint8_t *arena;
+    const uint8_t *win;
+    uint64_t w0;     // multiple of 16
+    uint32_t wlen;
+    __device__ __forceinline__ uint4 load16(uint32_t chunk, int lane) const {
+        const uint64_t d = (uint64_t)chunk * CHUNK + (uint64_t)lane * 16 - w0;
+        if (d <= (uint64_t)(wlen - 16)) return *reinterpret_cast<const uint4 *>(win + d);   // (d wraps when below w0)
+        return __ldg(reinterpret_cast<const uint4 *>(arena) + (size_t)chunk * 32 + lane);
+    }
+    __device__ __forceinline__ uint32_t byte(uint64_t p) const {
+        const uint64_t d = p - w0;
+        return d < (uint64_t)wlen ? win[d] : arena[p];
+    }
+};
+
+// Byte walker for one lane: counts every k-mer whose first base lies in [p0, p1); (in_hdr, at_ls) is the
+// line state at p0.  Walks past p1 only as far as the k-mers it owns reach.
+template <int K, class Src, class Emit>
+__device__ KF_NOINLINE void fasta_walk_lane(const Src src, uint64_t p0, uint64_t p1, bool in_hdr, bool at_ls,
+                                            Emit emit) {
     constexpr uint32_t MASK = (K >= 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
     uint32_t kmer = 0;
     int run = 0, owned = 0;
     uint64_t p = p0;
-    const uint64_t own_end = p0 + 16;
+    const uint64_t own_end = p1;
     for (;;) {
         const bool own = p < own_end;
         if (!own && (owned == 0 || run - K + 1 >= owned)) break;
-        const uint32_t c = arena[p];
+        const uint32_t c = src.byte(p);
         p++;
         if (in_hdr) {
             if (c == 0x0Au) { in_hdr = false; at_ls = true; }
@@ -211,19 +238,23 @@ __device__ __forceinline__ uint32_t kmer_off_at(uint32_t hi, uint32_t lo, int j)
 
 // PF = 512-byte chunks kept in flight per warp (register ring; the loop is unrolled PF times so the ring
 // rotates at compile time).  Sinks take the byte offset 4*kmer.
-template <int K, bool FORCE_WALKER, int PF, class Sink>
-__device__ __forceinline__ void fasta_process_range(const uint8_t *__restrict__ arena, uint32_t c0, uint32_t c1,
-                                                    uint32_t file_c0, Sink sink) {
+// Optional ownership clip [own_lo, own_hi) in arena bytes (own_lo must be a line start): only k-mers whose
+// first base lies inside it are counted; lanes cut by a bound use the walker on their part.
+template <int K, bool FORCE_WALKER, int PF, class Sink, class Src>
+__device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, uint32_t c1, uint32_t file_c0, Sink sink,
+                                                    uint64_t own_lo = 0, uint64_t own_hi = ~0ull,
+                                                    bool skip_backscan = false) {
     static_assert(PF >= 2 && PF <= 6, "prefetch depth");
     const int lane = threadIdx.x & 31;
-    const uint4 *base = reinterpret_cast<const uint4 *>(arena) + lane;
-    bool carry_hdr = (fasta_backscan(arena, c0, file_c0, lane) & 1u) != 0;
+    // With an ownership clip that starts at a line start inside (or at the start of) chunk c0, the state at the
+    // chunk's first byte does not matter: the '\n' before own_lo decides every owned lane's state.
+    bool carry_hdr = skip_backscan ? false : (fasta_backscan(src.arena, c0, file_c0, lane) & 1u) != 0;
     // slot[u] holds chunk (group base + u); after chunk cc is consumed its slot is refilled with chunk cc+PF.
     // Loads are clamped to chunk c1+1, which the arena's two NUL tail chunks keep in bounds.
     const uint32_t cmax = c1 + 1;
     uint4 slot[PF];
 #pragma unroll
-    for (int i = 0; i < PF; i++) slot[i] = __ldg(base + (size_t)min(c0 + i, cmax) * 32);
+    for (int i = 0; i < PF; i++) slot[i] = src.load16(min(c0 + i, cmax), lane);
     Lane cur = decode16(slot[0]);
     auto emit = [&](uint32_t x) { sink(x << 2); };
     for (uint32_t cg = c0; cg < c1; cg += PF) {
@@ -236,27 +267,33 @@ __device__ __forceinline__ void fasta_process_range(const uint8_t *__restrict__ 
                 const unsigned any_dirty = __ballot_sync(FULL, cur.dirty);
                 uint32_t st = 0;   // in_hdr | in_ls << 1 | next chunk starts inside a header << 2
                 if (any_dirty | (unsigned)carry_hdr) {
-                    const bool cls = (c == file_c0) || arena[(uint64_t)c * CHUNK - 1] == 0x0Au;
+                    const bool cls = (c == file_c0) || src.byte((uint64_t)c * CHUNK - 1) == 0x0Au;
                     st = fasta_resolve(wcur, carry_hdr, cls, lane);
                 }
                 const uint32_t slowflag = cur.dirty | (st & 1u);
                 const uint32_t xw = (cur.bits & ~3u) | slowflag;
                 const uint32_t nx0 = (nxt.bits & ~3u) | nxt.dirty | ((st >> 2) & 1u);
                 const uint32_t nbw = __shfl_sync(FULL, lane == 0 ? nx0 : xw, (lane + 1) & 31);
-                const bool slow = FORCE_WALKER || slowflag || (nbw & 1u);
-                if (!slow) {
+                const uint64_t pb = (uint64_t)c * CHUNK + (uint64_t)lane * 16;
+                const bool outside = pb + 16 <= own_lo || pb >= own_hi;
+                const bool cut = pb < own_lo || pb + 16 > own_hi;
+                const bool slow = FORCE_WALKER || slowflag || (nbw & 1u) || cut;
+                if (outside) {
+                } else if (!slow) {
                     const uint32_t nb = nbw & ~3u;
                     uint32_t hi = cur.bits, lo = nb;
                     if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
 #pragma unroll
                     for (int j = 0; j < 15; j++) sink(kmer_off_at<K>(hi, lo, j));
                     if (cur.n == 16) sink(kmer_off_at<K>(hi, lo, 15));
+                } else if (pb < own_lo) {
+                    fasta_walk_lane<K>(src, own_lo, pb + 16 < own_hi ? pb + 16 : own_hi, false, true, emit);
                 } else {
-                    fasta_walk_lane<K>(arena, (uint64_t)c * CHUNK + (uint64_t)lane * 16, (st & 1u) != 0, (st & 2u) != 0, emit);
+                    fasta_walk_lane<K>(src, pb, pb + 16 < own_hi ? pb + 16 : own_hi, (st & 1u) != 0, (st & 2u) != 0, emit);
                 }
                 carry_hdr = (st & 4u) != 0;
                 cur = nxt;
-                slot[u] = __ldg(base + (size_t)min(c + PF, cmax) * 32);
+                slot[u] = src.load16(min(c + PF, cmax), lane);
             }
         }
     }
@@ -298,10 +335,12 @@ struct GmemSink {   // dense u32 forward counts of one file in global memory (k 
 template <int K, int THREADS, int MIN_CTAS, bool FORCE_WALKER, int PF = 3>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles,
-                        const int *__restrict__ cta_begin, unsigned long long *__restrict__ g_fwd) {
+                        const int *__restrict__ cta_begin, unsigned long long *__restrict__ g_fwd,
+                        const uint32_t *__restrict__ file_P, const uint32_t *__restrict__ width_counts) {
     KF_DYN_SMEM(uint32_t, hist);
     constexpr int NB = 1 << (2 * K);
     constexpr int NWARPS = THREADS / 32;
+    if (width_counts && width_counts[0] == 0) return;   // every file went to a line-grid launch
     for (int i = threadIdx.x; i < NB; i += THREADS) hist[i] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5;
@@ -319,6 +358,7 @@ count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
         const Tile T = tiles[t];
+        if (file_P && file_P[T.file] != 0) continue;   // taken by a line-grid launch
         if ((int)T.file != cur_file) {
             if (cur_file >= 0) flush(cur_file);
             cur_file = (int)T.file;
@@ -327,7 +367,7 @@ count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
         const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
         const uint32_t cend = T.first_chunk + T.n_chunks;
         const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-        if (c0 < c1) fasta_process_range<K, FORCE_WALKER, PF>(arena, c0, c1, T.file_chunk0, emit);
+        if (c0 < c1) fasta_process_range<K, FORCE_WALKER, PF>(GlobalSrc{arena}, c0, c1, T.file_chunk0, emit);
     }
     if (cur_file >= 0) flush(cur_file);
 }
@@ -350,8 +390,493 @@ count_fasta_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
         const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
         const uint32_t cend = T.first_chunk + T.n_chunks;
         const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-        if (c0 < c1) fasta_process_range<K, FORCE_WALKER, 3>(arena, c0, c1, T.file_chunk0, emit);
+        if (c0 < c1) fasta_process_range<K, FORCE_WALKER, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, emit);
     }
+}
+
+// ================================================================================================
+// Line-grid kernel (k = 7): fixed-width FASTA, one line per lane
+// ================================================================================================
+// Most FASTA is written with a fixed line width (NCBI 80, Ensembl 60, UCSC/others 70).  When a warp knows
+// the width LW it gives every lane one whole line: the '\n' sits at a compile-time byte, so nothing has to
+// be searched or deleted, lanes never exchange data (each lane also decodes the first 6 bases of the next
+// line as look-ahead), and LW being even lets a lane count its LW 7-mers as LW/2 8-mers ("pairs": the
+// 8-mer at base 2i is the 7-mer at 2i followed by the one at 2i+1).  Halving the shared atomics matters
+// because their bank-conflict wavefronts are the first limiter of the generic kernel (profiles/r01_*).
+//
+//   staging  : per-warp buffer in shared memory filled by one TMA bulk copy (cp.async.bulk + mbarrier)
+//              of 32 lines; all lanes pull their line into registers, then the next copy is issued, so
+//              the copy of window i+1 overlaps the decode/count of window i.
+//   histogram: 65,536 8-mer bins as 32,768 u32 words: word = v >> 1; the low half counts every pair of
+//              the word, the high half those with v & 1 (addend 1 or 0x10001).  A half can wrap, so at
+//              every flush the sum of the low halves is compared with the number of pairs issued; on a
+//              mismatch the CTA discards the histogram and recounts its tiles of that file with the
+//              generic path into global memory (exact, slow, practically never taken).
+//   irregular: lines that break the grid (record ends, headers, other widths) and lanes with non-ACGT
+//              bytes go through the generic range processor / byte walker with a global-memory sink.
+
+#ifdef KF_EMU
+__device__ inline void __syncwarp_emu() { emu::exchange(0, 0); }
+#define KF_SYNCWARP() __syncwarp_emu()
+#define KF_LDCG(p) (*(p))
+__device__ inline void stage_bar_init(uint64_t *) {}
+__device__ inline void stage_issue(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ inline void stage_wait(uint64_t *, uint32_t) { KF_SYNCWARP(); }
+__device__ inline uint32_t smem_addr(const void *) { return 0; }
+__device__ inline void red_shared_add(uint32_t *hist, uint32_t, uint32_t off, uint32_t v) { atomicAdd(hist + (off >> 2), v); }
+#else
+#define KF_SYNCWARP() __syncwarp()
+#define KF_LDCG(p) __ldcg(p)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stage_bar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one lane: arm the barrier with the byte count and start the bulk copy global -> shared (TMA)
+__device__ __forceinline__ void stage_issue(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of dst vs async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KF_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KF_DONE;\n\t"
+        "bra KF_WAIT;\n\t"
+        "KF_DONE:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return smem_u32(p); }
+__device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32_t off, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + off), "r"(v) : "memory");
+}
+#endif
+
+struct Gmem64Sink {   // rare paths of the line-grid kernel: a u64 row in global memory (+ "row is dirty" flag)
+    unsigned long long *g;
+    uint32_t *flag;
+    __device__ __forceinline__ void operator()(uint32_t off) const {
+        atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(g) + 2 * (size_t)off), 1ull);
+        *flag = 1u;
+#ifdef KF_EMU_DEBUG
+        extern std::atomic<long> g_dbg_emits;
+        g_dbg_emits++;
+#endif
+    }
+};
+
+template <int LW>
+struct LineGrid {
+    static_assert(LW % 2 == 0 && LW >= 32 && LW <= 120, "line width");
+    static constexpr int P = LW + 1;                 // bytes per line incl. '\n'
+    static constexpr int LA = 6;                     // look-ahead bases for the last pair
+    static constexpr int NBASES = LW + LA;
+    static constexpr int NWA = (P + LA + 3) / 4;     // aligned words a lane decodes
+    static constexpr int NPK = (NBASES + 15) / 16;   // packed registers
+    static constexpr int NPAIR = LW / 2;
+    static constexpr int NEED = 31 * P + 4 * NWA + 4;             // bytes a window must hold from its first line start
+    static constexpr int STAGE = ((NEED + 16 + 112 + 15) / 16) * 16;  // + alignment + slack to find the first line start
+};
+
+// First line start at or after byte q (a line start is file_begin or the byte after a '\n'); file_end if none.
+template <class Src>
+__device__ KF_NOINLINE uint64_t fasta_line_start_at_or_after(const Src src, uint64_t q, uint64_t file_begin,
+                                                             uint64_t file_end, int lane) {
+    if (q <= file_begin) return file_begin;
+    if (q >= file_end) return file_end;
+    const uint64_t from = q - 1;   // a '\n' at q-1 makes q itself a line start
+    for (uint64_t c = from / CHUNK; c * CHUNK < file_end; ++c) {
+        const uint4 w = src.load16((uint32_t)c, lane);
+        const uint64_t pb = c * CHUNK + (uint64_t)lane * 16;
+        int first = 16;
+#pragma unroll
+        for (int i = 15; i >= 0; i--)
+            if (byte_of(w, i) == 0x0Au && pb + i >= from) first = i;
+        const unsigned Bm = __ballot_sync(FULL, first < 16);
+        if (Bm) {
+            const int j = __ffs((int)Bm) - 1;
+            const int fj = __shfl_sync(FULL, first, j);
+            const uint64_t r = c * CHUNK + (uint64_t)j * 16 + (uint64_t)fj + 1;
+            return r < file_end ? r : file_end;
+        }
+    }
+    return file_end;
+}
+
+// Exact but slow: the generic range processor over the lines starting in [lo, hi), global sink.
+template <int K, class Src>
+__device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64_t hi, uint32_t file_c0, Gmem64Sink gs) {
+    if (lo >= hi) return;
+    const uint32_t c0 = (uint32_t)(lo / CHUNK), c1 = (uint32_t)((hi + CHUNK - 1) / CHUNK);
+    fasta_process_range<K, false, 2>(src, c0, c1, file_c0, gs, lo, hi, true);
+}
+
+// Per-warp staging state: two buffers used strictly alternately (the window loop is unrolled by two, so which
+// buffer is "current" is a compile-time fact and nothing is shuffled between registers).
+struct StageBuf {
+    uint8_t *buf;
+    uint64_t *bar;
+};
+template <int LW>
+struct LgWarpStage {
+    StageBuf b0, b1;
+    uint32_t par0, par1;   // mbarrier phase parity to wait for next
+};
+
+// One window of 32 lines starting at line start B, staged in `cur` at byte offset woff.  On return B is the
+// next line start to process; if B < Xe its window is already on its way into `oth` (pend_oth) at offset woff.
+template <int LW>
+__device__ __forceinline__ void lg_window(const uint8_t *__restrict__ arena, uint64_t &B, uint32_t &woff, const uint64_t Xe,
+                                          const uint64_t F0, const uint64_t F1, const StageBuf cur, uint32_t &par_cur,
+                                          bool &pend_cur, const StageBuf oth, uint32_t &par_oth, bool &pend_oth,
+                                          uint32_t *hist16, Gmem64Sink gs, uint32_t &npairs, int &strikes) {
+    using G = LineGrid<LW>;
+    constexpr int K = 7;
+    const int lane = threadIdx.x & 31;
+    if (pend_cur) { stage_wait(cur.bar, par_cur); par_cur ^= 1u; pend_cur = false; }
+    // ---- pull my line (+ look-ahead) into registers, byte-aligned ----
+    const uint32_t o = woff + (uint32_t)lane * G::P;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(cur.buf) + (o >> 2);
+    const uint32_t ash = (o & 3u) * 8u;
+    uint32_t x[G::NWA + 1];
+#pragma unroll
+    for (int i = 0; i <= G::NWA; i++) x[i] = sw[i];
+    // next window into the other buffer while this one is decoded (all lanes finished with `oth` one window ago)
+    const uint64_t Bn = B + 32ull * G::P;
+    if (Bn < Xe) {
+        KF_SYNCWARP();
+        if (lane == 0) stage_issue(oth.buf, arena + (Bn & ~15ull), G::STAGE, oth.bar);
+        pend_oth = true;
+    }
+#pragma unroll
+    for (int i = 0; i < G::NWA; i++) x[i] = __funnelshift_r(x[i], x[i + 1], ash);
+    // ---- decode ----
+    uint32_t anyV = 0;
+    uint32_t pk[G::NWA];
+#pragma unroll
+    for (int i = 0; i < G::NWA; i++) {
+        uint32_t V;
+        decode_word(x[i], pk[i], V);
+        // bytes of this word that are sequence: line bases [0,LW) and look-ahead bytes (LW, LW+LA]
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int byte = 4 * i + b;
+            if (byte < LW || (byte > LW && byte <= LW + G::LA)) m |= 0xFFu << (8 * b);
+        }
+        if (m == 0xFFFFFFFFu) anyV |= V;
+        else if (m != 0) anyV |= V & m;
+    }
+    const bool nl_ok = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au;
+    // ---- pack: base stream = line bases then look-ahead bases (the '\n' byte is skipped statically) ----
+    uint32_t PK[G::NPK + 1];
+    constexpr int NFULL = (LW / 4) / 4;   // groups of four full words -> one register, three byte permutes
+#pragma unroll
+    for (int gq = 0; gq < NFULL; gq++) {
+        const uint32_t r1 = __byte_perm(pk[4 * gq + 3], pk[4 * gq + 2], 0x0073);
+        const uint32_t r2 = __byte_perm(pk[4 * gq + 1], pk[4 * gq], 0x0073);
+        PK[gq] = __byte_perm(r1, r2, 0x5410);
+    }
+#pragma unroll
+    for (int i = NFULL; i <= G::NPK; i++) PK[i] = 0;
+#pragma unroll
+    for (int i = 4 * NFULL; i < G::NWA; i++) {
+        const uint32_t g8 = pk[i] >> 24;   // 4 codes, first in bits 7:6
+#pragma unroll
+        for (int seg = 0; seg < 2; seg++) {
+            int b0 = (seg == 0) ? 0 : LW + 1 - 4 * i;                  // line bases | look-ahead bases
+            int b1 = (seg == 0) ? LW - 4 * i : LW + 1 + G::LA - 4 * i;
+            b0 = b0 < 0 ? 0 : b0;
+            b1 = b1 > 4 ? 4 : b1;
+            if (b1 > b0) {
+                const int n = b1 - b0;
+                const int byte = 4 * i + b0;
+                const int pos = byte < LW ? byte : byte - 1;          // sequence bytes before this one
+                const uint32_t val = (g8 >> (8 - 2 * b1)) & ((1u << (2 * n)) - 1u);
+                const int sh = 32 - 2 * (pos & 15) - 2 * n;
+                if (sh >= 0) PK[pos >> 4] |= val << sh;
+                else { PK[pos >> 4] |= val >> (-sh); PK[(pos >> 4) + 1] |= val << (32 + sh); }
+            }
+        }
+    }
+    // ---- who is on the grid: lines that start before Xe ----
+    const uint64_t rem = Xe - B;                                  // > 0
+    const uint32_t nact = rem >= 32ull * G::P ? 32u : (uint32_t)((rem + G::P - 1) / G::P);
+    const bool active = (uint32_t)lane < nact;
+    const unsigned bad = __ballot_sync(FULL, active && !nl_ok);
+    const uint32_t f = bad ? (uint32_t)(__ffs((int)bad) - 1) : nact;
+    const uint64_t wbase = B - woff;
+    if ((uint32_t)lane < f) {
+        if (anyV == 0) {
+            const uint32_t hbase = smem_addr(hist16);
+#pragma unroll
+            for (int i = 0; i < G::NPAIR; i++) {
+                const int r = (4 * i) & 31, q = (4 * i) >> 5;
+                const int sh = 47 - r;   // 8-mer v lands on bits 16:1
+                const uint32_t sv = (sh >= 32) ? (PK[q] >> (sh - 32)) : __funnelshift_r(PK[q + 1], PK[q], sh);
+                red_shared_add(hist16, hbase, sv & 0x1FFFCu, (sv & 2u) * 0x8000u + 1u);
+            }
+            npairs += G::NPAIR;
+        } else {
+            const WindowSrc wsrc{arena, cur.buf, wbase, (uint32_t)G::STAGE};
+            const uint64_t sl = B + (uint64_t)lane * G::P;
+            auto emit = [&](uint32_t xk) { gs(xk << 2); };
+            fasta_walk_lane<K>(wsrc, sl, sl + G::P, false, true, emit);
+        }
+    }
+    if (f == nact) {
+        B += (uint64_t)nact * G::P;   // == Bn when the window was full; >= Xe otherwise
+        woff = (uint32_t)(B & 15u);
+        strikes = 0;
+    } else {
+        // the line at sf breaks the grid: handle it and any header lines that follow from the staged window
+        const WindowSrc wsrc{arena, cur.buf, wbase, (uint32_t)G::STAGE};
+        const uint64_t sf = B + (uint64_t)f * G::P;
+        uint64_t q = fasta_line_start_at_or_after(wsrc, sf + 1, F0, F1, lane);
+        while (q < Xe && wsrc.byte(q) == (uint32_t)'>') q = fasta_line_start_at_or_after(wsrc, q + 1, F0, F1, lane);
+        lg_generic_region<K>(wsrc, sf, q, (uint32_t)(F0 / CHUNK), gs);
+        strikes = (f == 0) ? strikes + 1 : 0;
+        // the prefetch (if any) went to the wrong place: drain it and fetch the window of q instead
+        if (pend_oth) { stage_wait(oth.bar, par_oth); par_oth ^= 1u; pend_oth = false; }
+        B = q;
+        woff = (uint32_t)(q & 15u);
+        if (q < Xe && strikes < 4) {
+            KF_SYNCWARP();
+            if (lane == 0) stage_issue(oth.buf, arena + (q & ~15ull), G::STAGE, oth.bar);
+            pend_oth = true;
+        }
+    }
+}
+
+// One warp over the lines that start in [X0, X1) of a file [F0, F1).
+template <int LW>
+__device__ __forceinline__ void lg_process_range(const uint8_t *__restrict__ arena, uint64_t X0, uint64_t X1, uint64_t F0,
+                                                 uint64_t F1, LgWarpStage<LW> &S, uint32_t *hist16, Gmem64Sink gs,
+                                                 uint32_t &npairs) {
+    using G = LineGrid<LW>;
+    constexpr int K = 7;
+    const int lane = threadIdx.x & 31;
+    const uint64_t Xe = X1 < F1 ? X1 : F1;
+    if (X0 >= Xe) return;
+    bool pend0 = false, pend1 = false;
+    // ---- first line start at or after X0, found in the first staged window when possible ----
+    uint64_t B;
+    uint32_t woff;
+    {
+        const uint64_t base = (X0 <= F0) ? (F0 & ~15ull) : ((X0 - 1) & ~15ull);
+        KF_SYNCWARP();
+        if (lane == 0) stage_issue(S.b0.buf, arena + base, G::STAGE, S.b0.bar);
+        pend0 = true;
+        if (X0 <= F0) {
+            B = F0;
+        } else {
+            stage_wait(S.b0.bar, S.par0); S.par0 ^= 1u; pend0 = false;
+            const uint32_t o0 = (uint32_t)((X0 - 1) - base);
+            int first = 3;
+#pragma unroll
+            for (int j = 2; j >= 0; j--)
+                if (S.b0.buf[o0 + 3 * lane + j] == 0x0Au) first = j;
+            const unsigned Bm = __ballot_sync(FULL, first < 3);
+            if (Bm) {
+                const int jl = __ffs((int)Bm) - 1;
+                const int fj = __shfl_sync(FULL, first, jl);
+                B = (X0 - 1) + 3ull * jl + (uint64_t)fj + 1;
+                if (B > F1) B = F1;
+            } else {
+                B = fasta_line_start_at_or_after(GlobalSrc{arena}, X0 + 95, F0, F1, lane);
+            }
+        }
+        woff = (uint32_t)(B - base);
+        if (B < Xe && (uint64_t)woff + G::NEED > (uint64_t)G::STAGE) {   // line start beyond the slack: fetch its own window
+            KF_SYNCWARP();
+            if (lane == 0) stage_issue(S.b0.buf, arena + (B & ~15ull), G::STAGE, S.b0.bar);
+            pend0 = true;
+            woff = (uint32_t)(B & 15u);
+        }
+    }
+    int strikes = 0;
+    while (B < Xe && strikes < 4) {
+        lg_window<LW>(arena, B, woff, Xe, F0, F1, S.b0, S.par0, pend0, S.b1, S.par1, pend1, hist16, gs, npairs, strikes);
+        if (!(B < Xe && strikes < 4)) break;
+        lg_window<LW>(arena, B, woff, Xe, F0, F1, S.b1, S.par1, pend1, S.b0, S.par0, pend0, hist16, gs, npairs, strikes);
+    }
+    if (pend0) { stage_wait(S.b0.bar, S.par0); S.par0 ^= 1u; }
+    if (pend1) { stage_wait(S.b1.bar, S.par1); S.par1 ^= 1u; }
+    if (B < Xe) {   // this stretch is not on the grid: finish the range generically
+        const uint64_t E = fasta_line_start_at_or_after(GlobalSrc{arena}, X1, F0, F1, lane);
+        lg_generic_region<K>(GlobalSrc{arena}, B, E, (uint32_t)(F0 / CHUNK), gs);
+    }
+}
+
+template <int LW, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+count_fasta_linegrid_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
+                            const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
+                            const uint64_t *__restrict__ file_len, unsigned long long *__restrict__ g_fwd,
+                            unsigned long long *__restrict__ g_scratch, int cta_stride,
+                            const uint32_t *__restrict__ width_counts) {
+    using G = LineGrid<LW>;
+    if (width_counts[(LW - 50) / 10] == 0) return;   // no file of this width in the batch (uniform exit)
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int NWORDS = 32768;
+    constexpr int NB7 = 16384;
+    KF_DYN_SMEM(uint32_t, smem);
+    uint32_t *hist16 = smem;
+    uint8_t *stage_base = reinterpret_cast<uint8_t *>(smem + NWORDS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_base + (size_t)NWARPS * 2 * G::STAGE);
+    unsigned long long *s_acc = reinterpret_cast<unsigned long long *>(bars + 2 * NWARPS);   // [0] pairs issued, [1] low-half sum
+    uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_acc + 2);                              // rare-path row is non-zero
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < NWORDS; i += THREADS) hist16[i] = 0;
+    if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *s_flag = 0;
+    LgWarpStage<LW> S;
+    S.b0 = StageBuf{stage_base + (size_t)(2 * warp) * G::STAGE, bars + 2 * warp};
+    S.b1 = StageBuf{stage_base + (size_t)(2 * warp + 1) * G::STAGE, bars + 2 * warp + 1};
+    S.par0 = S.par1 = 0u;
+    if (lane == 0) { stage_bar_init(S.b0.bar); stage_bar_init(S.b1.bar); }
+    __syncthreads();
+    // rare-path k-mers (walker, off-grid lines) go to this CTA's private u64 row so that a failed checksum can
+    // discard them together with the pair histogram
+    unsigned long long *scratch = g_scratch + (size_t)blockIdx.x * NB7;
+    uint32_t npairs = 0;
+    int cur_file = -1, first_tile = 0;
+
+    auto warp_range = [&](uint32_t first_chunk, uint32_t n_chunks, uint64_t &X0, uint64_t &X1) {
+        const uint32_t cpw = (n_chunks + NWARPS - 1) / NWARPS;
+        const uint32_t c0 = first_chunk + (uint32_t)warp * cpw;
+        const uint32_t cend = first_chunk + n_chunks;
+        const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
+        X0 = (uint64_t)c0 * CHUNK;
+        X1 = (uint64_t)c1 * CHUNK;
+        return c0 < c1;
+    };
+    auto flush = [&](int file, int t_first, int t_last) {
+        atomicAdd(s_acc, (unsigned long long)npairs);
+        npairs = 0;
+        __syncthreads();
+        unsigned long long low = 0;
+        for (int i = threadIdx.x; i < NWORDS; i += THREADS) low += hist16[i] & 0xFFFFu;
+        atomicAdd(s_acc + 1, low);
+        __syncthreads();
+        const bool ok = s_acc[0] == s_acc[1];
+        const bool rare = *s_flag != 0;
+        unsigned long long *g = g_fwd + (size_t)file * NB7;
+        if (rare) __threadfence();
+        if (ok) {
+            // 7-mer x = prefix of the 8-mers 4x..4x+3 (words 2x, 2x+1: sum of the low halves) and suffix of the
+            // 8-mers a*16384 + x (word a*8192 + (x >> 1); odd x in the high half, even x = low - high)
+#pragma unroll 4
+            for (int xk = threadIdx.x; xk < NB7; xk += THREADS) {
+                const uint2 pw = *reinterpret_cast<const uint2 *>(hist16 + 2 * xk);
+                unsigned long long c = (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu);
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const uint32_t w = hist16[a * 8192 + (xk >> 1)];
+                    c += (xk & 1) ? (w >> 16) : ((w & 0xFFFFu) - (w >> 16));
+                }
+                if (rare) c += KF_LDCG(scratch + xk);
+                if (c) atomicAdd(g + xk, c);
+            }
+        }
+        if (rare)
+            for (int xk = threadIdx.x; xk < NB7; xk += THREADS) scratch[xk] = 0;
+        __syncthreads();
+        uint4 *h4 = reinterpret_cast<uint4 *>(hist16);
+        for (int i = threadIdx.x; i < NWORDS / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
+        if (threadIdx.x == 0) *s_flag = 0;
+        __syncthreads();
+        if (!ok) {
+            // a 16-bit half wrapped: recount this CTA's tiles of the file exactly, straight into global memory
+            Gmem64Sink gs;
+            gs.g = g;
+            gs.flag = s_flag + 1;   // nobody reads this one
+            const uint64_t F0 = file_off[file], F1 = F0 + file_len[file];
+            const GlobalSrc src{arena};
+            for (int t = t_first; t <= t_last; ++t) {
+                const Tile T = tiles[t];
+                if ((int)T.file != file) continue;
+                uint64_t X0, X1;
+                if (!warp_range(T.first_chunk, T.n_chunks, X0, X1)) continue;
+                const uint64_t lo = fasta_line_start_at_or_after(src, X0, F0, F1, lane);
+                const uint64_t hi = fasta_line_start_at_or_after(src, X1, F0, F1, lane);
+                lg_generic_region<7>(src, lo, hi, T.file_chunk0, gs);
+            }
+        }
+    };
+
+    // the tile plan is cut for the generic kernel's grid; this CTA takes cta_stride consecutive shares of it.
+    // Consecutive tiles of one file are contiguous in the arena: they are processed as ONE range split over
+    // the warps, so the per-range costs (first line start, first un-prefetched window, ragged last window)
+    // are paid once per file piece instead of once per 512 KiB tile.
+    const int t1 = cta_begin[(blockIdx.x + 1) * cta_stride];
+    int last_tile = -1;
+    for (int t = cta_begin[blockIdx.x * cta_stride]; t < t1;) {
+        const Tile T = tiles[t];
+        if (file_P[T.file] != (uint32_t)G::P) { ++t; continue; }
+        uint32_t n_chunks = T.n_chunks;
+        int te = t + 1;
+        while (te < t1 && tiles[te].file == T.file && tiles[te].first_chunk == T.first_chunk + n_chunks) {
+            n_chunks += tiles[te].n_chunks;
+            ++te;
+        }
+        if ((int)T.file != cur_file) {
+            if (cur_file >= 0) flush(cur_file, first_tile, last_tile);
+            cur_file = (int)T.file;
+            first_tile = t;
+        }
+        last_tile = te - 1;
+        uint64_t X0, X1;
+        if (warp_range(T.first_chunk, n_chunks, X0, X1)) {
+            Gmem64Sink gs;
+            gs.g = scratch;
+            gs.flag = s_flag;
+            const uint64_t F0 = file_off[T.file];
+            lg_process_range<LW>(arena, X0, X1, F0, F0 + file_len[T.file], S, hist16, gs, npairs);
+        }
+        t = te;
+    }
+    if (cur_file >= 0) flush(cur_file, first_tile, last_tile);
+}
+
+// Line width of each FASTA file, judged from its first lines: P = LW + 1 if the three lines after the
+// header are LW bases wide (LW one of 60/70/80), else 0 (generic kernel).  One thread per file.
+__global__ void probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
+                                        const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
+                                        uint32_t force_generic, uint32_t *__restrict__ file_P,
+                                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80 */) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    uint32_t P = 0;
+    if (!force_generic && formats[f] == (uint8_t)'>') {
+        const uint8_t *d = arena + file_off[f];
+        const uint64_t L = file_len[f];
+        uint64_t p = 0;
+        const uint64_t cap = L < 65536 ? L : 65536;
+        while (p < cap && d[p] != 0x0Au) p++;
+        if (p < cap) {
+            p++;
+            uint32_t w0 = 0;
+            bool ok = true;
+            for (int line = 0; line < 3 && ok; line++) {
+                uint32_t w = 0;
+                while (p + w < L && w <= 128 && d[p + w] != 0x0Au) w++;
+                if (p + w >= L || w > 128) { ok = false; break; }
+                if (line == 0) w0 = w;
+                else if (w != w0) ok = false;
+                p += w + 1;
+            }
+            if (ok && (w0 == 60 || w0 == 70 || w0 == 80)) P = w0 + 1;
+        }
+    }
+    file_P[f] = P;
+    atomicAdd(width_counts + (P ? (P - 51) / 10 : 0), 1u);
 }
 
 // ------------------------------------------------------------------------------------------------

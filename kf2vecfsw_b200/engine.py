@@ -16,6 +16,8 @@ KF_FLAG_PSEUDOCOUNT = 1
 KF_FLAG_RAW_CNT = 2
 KF_FLAG_FORCE_WALKER = 4
 KF_CHUNK = 512
+KF_TAIL_PAD = 4096
+KF_FLAG_NO_LINEGRID = 8
 KF_MAX_K = 12
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -83,6 +85,9 @@ def _load():
     L.kf_synth_fasta.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                  ctypes.c_size_t]
     L.kf_synth_fasta.restype = ctypes.c_int64
+    L.kf_synth_fasta_ex.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+    L.kf_synth_fasta_ex.restype = ctypes.c_int64
     L.kf_synth_fastq.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                  ctypes.c_void_p, ctypes.c_size_t]
     L.kf_synth_fastq.restype = ctypes.c_int64
@@ -95,9 +100,9 @@ def _check(rc: int, what: str = ""):
         raise KfError(rc, what)
 
 
-def _flags(pseudocount: bool, raw_cnt: bool, force_walker: bool = False) -> int:
+def _flags(pseudocount: bool, raw_cnt: bool, force_walker: bool = False, no_linegrid: bool = False) -> int:
     return (KF_FLAG_PSEUDOCOUNT if pseudocount else 0) | (KF_FLAG_RAW_CNT if raw_cnt else 0) | \
-           (KF_FLAG_FORCE_WALKER if force_walker else 0)
+           (KF_FLAG_FORCE_WALKER if force_walker else 0) | (KF_FLAG_NO_LINEGRID if no_linegrid else 0)
 
 
 # ---- lifecycle -----------------------------------------------------------------------------------
@@ -153,7 +158,7 @@ def _as_u8(b) -> np.ndarray:
 
 def count_buffers(bufs: Sequence, k: int = 7, pseudocount: bool = False, raw_cnt: bool = False,
                   want_counts: bool = True, want_freq: bool = True, force_walker: bool = False,
-                  out_counts: Optional[np.ndarray] = None, out_freq: Optional[np.ndarray] = None
+                  no_linegrid: bool = False, out_counts: Optional[np.ndarray] = None, out_freq: Optional[np.ndarray] = None
                   ) -> Tuple[Optional[np.ndarray], Optional[np.ndarray], np.ndarray, np.ndarray]:
     """End-to-end call on host buffers (one per input file).  Returns (counts u64 [n,V] | None,
     freq f64 [n,V] | None, totals u64 [n], status i32 [n])."""
@@ -168,7 +173,7 @@ def count_buffers(bufs: Sequence, k: int = 7, pseudocount: bool = False, raw_cnt
     freq = out_freq if out_freq is not None else (np.empty((n, V), dtype=np.float64) if want_freq else None)
     totals = np.zeros(n, dtype=np.uint64)
     status = np.zeros(n, dtype=np.int32)
-    rc = L.kf_count_buffers(ptrs, lens, n, k, _flags(pseudocount, raw_cnt, force_walker),
+    rc = L.kf_count_buffers(ptrs, lens, n, k, _flags(pseudocount, raw_cnt, force_walker, no_linegrid),
                             counts.ctypes.data if counts is not None else None,
                             freq.ctypes.data if freq is not None else None, totals.ctypes.data, status.ctypes.data)
     _check(rc, "kf_count_buffers")
@@ -206,7 +211,7 @@ class DeviceArena:
         self.offsets = np.zeros(self.n, dtype=np.uint64)
         if self.n > 1:
             self.offsets[1:] = np.cumsum(padded)[:-1]
-        self.nbytes = int(padded.sum()) + 2 * KF_CHUNK
+        self.nbytes = int(padded.sum()) + KF_TAIL_PAD
         self.formats = np.array([a[0] if a.size else 0 for a in arrs], dtype=np.uint8)
         self.tensor = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
         for a, off in zip(arrs, self.offsets):
@@ -221,7 +226,8 @@ class DeviceArena:
 
 
 def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_cnt: bool = False,
-                 counts=None, freq=None, feat=None, totals=None, force_walker: bool = False, stream=None):
+                 counts=None, freq=None, feat=None, totals=None, force_walker: bool = False, no_linegrid: bool = False,
+                 stream=None):
     """Enqueues count + fold/normalise for the arena on ``stream`` (default: torch's current stream).
     Output tensors (torch, on the arena's device) are optional: counts int64/uint64 [n,V], freq float64
     [n,V], feat float32 [n,V] (= fp32(freq*1e4), the matrix the trainers consume), totals int64 [n]."""
@@ -233,7 +239,8 @@ def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_
     ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     rc = L.kf_count_device(ctypes.c_void_p(arena.tensor.data_ptr()), arena.nbytes, arena.offsets.ctypes.data,
                            arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, k,
-                           _flags(pseudocount, raw_cnt, force_walker), ptr(counts), ptr(freq), ptr(feat), ptr(totals),
+                           _flags(pseudocount, raw_cnt, force_walker, no_linegrid), ptr(counts), ptr(freq), ptr(feat),
+                           ptr(totals),
                            ctypes.c_void_p(stream.cuda_stream))
     _check(rc, "kf_count_device")
 
@@ -266,21 +273,23 @@ def write_kf(path: str, sample: str, row: np.ndarray, int_mode: bool = False, ap
 
 
 # ---- synthetic inputs --------------------------------------------------------------------------------------
-def synth_fasta(seed: int, genome_id: int, n_bases: int, line_width: int = 80, out: Optional[np.ndarray] = None):
+def synth_fasta(seed: int, genome_id: int, n_bases: int, line_width: int = 80, out: Optional[np.ndarray] = None,
+                max_contigs: int = 50, n_runs: int = 10):
     L = _load()
-    size = L.kf_synth_fasta(seed, genome_id, n_bases, line_width, None, 0)
+    size = L.kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, max_contigs, n_runs, None, 0)
     if size < 0:
         raise KfError(int(size), "kf_synth_fasta")
     if out is None:
         out = np.empty(size, dtype=np.uint8)
-    n = L.kf_synth_fasta(seed, genome_id, n_bases, line_width, out.ctypes.data, out.size)
+    n = L.kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, max_contigs, n_runs, out.ctypes.data, out.size)
     if n < 0:
         raise KfError(int(n), "kf_synth_fasta")
     return out[:n]
 
 
-def synth_fasta_size(seed: int, genome_id: int, n_bases: int, line_width: int = 80) -> int:
-    return int(_load().kf_synth_fasta(seed, genome_id, n_bases, line_width, None, 0))
+def synth_fasta_size(seed: int, genome_id: int, n_bases: int, line_width: int = 80, max_contigs: int = 50,
+                     n_runs: int = 10) -> int:
+    return int(_load().kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, max_contigs, n_runs, None, 0))
 
 
 def synth_fastq(seed: int, sample_id: int, genome_len: int, n_reads: int, read_len: int = 150):

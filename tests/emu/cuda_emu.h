@@ -21,6 +21,8 @@
 #define KF_NOINLINE
 
 struct uint4 { uint32_t x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 struct dim3 { unsigned x = 1, y = 1, z = 1; };
 
 namespace emu {
@@ -81,6 +83,8 @@ inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
     }
     return r;
 }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline void __threadfence() {}
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 inline uint32_t __brev(uint32_t x) {

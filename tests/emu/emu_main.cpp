@@ -1,7 +1,7 @@
 // emu_main.cpp -- TEST INFRASTRUCTURE.  Runs the real kernel code of kf_kernels.cuh under the host
 // emulation (cuda_emu.h) with the real tile planner's layout rules, on one or more FASTA files, and
 // prints the canonical counts (one line per file) so tests/ can compare them with the oracle.
-//   usage: emu_main <k> <threads_per_cta> <grid> <force_walker 0|1> <tile_chunks> file...
+//   usage: emu_main <k> <threads_per_cta> <grid> <force_walker 0|1> <tile_chunks> <use_linegrid 0|1> file...
 #include "cuda_emu.h"
 #include "../../kf2vecfsw_b200/csrc/kf_kernels.cuh"
 
@@ -37,17 +37,31 @@ using namespace kf;
 
 template <int K, int THREADS>
 static void run(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
-                bool fw, unsigned long long *fwd) {
+                bool fw, unsigned long long *fwd, const uint32_t *file_P, const uint32_t *wc) {
     size_t smem = sizeof(uint32_t) << (2 * K);
-    if (fw) emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, true>(arena, tiles.data(), cta_begin.data(), fwd); });
-    else    emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, false>(arena, tiles.data(), cta_begin.data(), fwd); });
+    if (fw) emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, true>(arena, tiles.data(), cta_begin.data(), fwd, file_P, wc); });
+    else    emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, false>(arena, tiles.data(), cta_begin.data(), fwd, file_P, wc); });
+}
+
+template <int LW, int THREADS>
+static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
+                   const uint32_t *file_P, const uint64_t *off, const uint64_t *len, unsigned long long *fwd,
+                   unsigned long long *scratch, const uint32_t *wc) {
+    using G = LineGrid<LW>;
+    constexpr int NW = THREADS / 32;
+    size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * 2 * G::STAGE + 2 * NW * sizeof(uint64_t) + 2 * sizeof(unsigned long long) + 16;
+    emu::launch(grid, THREADS, smem, [&]() {
+        count_fasta_linegrid_kernel<LW, THREADS>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, scratch, 1, wc);
+    });
 }
 
 int main(int argc, char **argv) {
-    if (argc < 7) { fprintf(stderr, "usage\n"); return 2; }
+    if (argc < 8) { fprintf(stderr, "usage\n"); return 2; }
     int k = atoi(argv[1]), threads = atoi(argv[2]), grid = atoi(argv[3]);
     bool fw = atoi(argv[4]) != 0;
     uint32_t tile_chunks = (uint32_t)atoi(argv[5]);
+    bool use_lg = atoi(argv[6]) != 0;
+    argv += 1; argc -= 1;
     int n = argc - 6;
     std::vector<uint64_t> off(n), len(n);
     std::vector<uint8_t> arena;
@@ -61,7 +75,7 @@ int main(int argc, char **argv) {
         fclose(f);
         len[i] = (uint64_t)sz;
     }
-    arena.resize(arena.size() + 2 * CHUNK, 0);
+    arena.resize(arena.size() + 4096, 0);
     // same cutting rule as kf_api.cu:build_plan (chunk-balanced contiguous CTA ranges, tiles <= tile_chunks)
     uint64_t total = 0;
     for (int i = 0; i < n; i++) total += (len[i] + CHUNK - 1) / CHUNK;
@@ -82,7 +96,29 @@ int main(int argc, char **argv) {
     while (cta < grid) { cta++; cta_begin[cta] = (int)tiles.size(); }
     size_t NB = (size_t)1 << (2 * k);
     std::vector<unsigned long long> fwd((size_t)n * NB, 0);
-#define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data()); break;
+    // same launch sequence as kf_api.cu:run_files -- probe, one line-grid launch per width, generic kernel
+    std::vector<uint8_t> formats(n);
+    for (int i = 0; i < n; i++) formats[i] = len[i] ? arena[off[i]] : 0;
+    std::vector<uint32_t> file_P(n, 0);
+    std::vector<uint32_t> wc(4, 0);
+    const bool lg = use_lg && k == 7 && !fw;
+    emu::launch((n + 31) / 32, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data()); });
+    if (lg) {
+        std::vector<unsigned long long> scratch((size_t)grid * 16384, 0);
+        if (threads == 64) {
+            run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+            run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+            run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+        } else {
+            run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+            run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+            run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+        }
+        for (auto v : scratch) if (v) { fprintf(stderr, "scratch not zero after run\n"); return 3; }
+        int nlg = 0; for (auto P : file_P) nlg += P != 0;
+        fprintf(stderr, "linegrid files: %d of %d\n", nlg, n);
+    }
+#define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_P.data(), wc.data()); break;
     switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }
     std::vector<uint32_t> canon; canonical_codes(k, canon);
     long long V = (long long)canon.size();

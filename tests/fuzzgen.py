@@ -59,3 +59,33 @@ def rand_fastq(rng: random.Random) -> bytes:
     if rng.random() < 0.3:
         out = out[:-1]
     return bytes(out)
+
+
+def rand_fasta_grid(rng: random.Random) -> bytes:
+    """Mostly fixed-width FASTA (60/70/80 columns) with the irregularities real files have: short last
+    lines, several records, N runs, lower case, IUPAC, an occasional record in another width, blank lines,
+    CRLF records, long headers, missing final newline."""
+    out = bytearray()
+    lw = rng.choice([60, 70, 80])
+    nrec = rng.randint(1, 5)
+    for r in range(nrec):
+        hl = rng.choice([5, 20, 79, 80, 81, 100, 600]) if rng.random() < 0.4 else rng.randint(1, 60)
+        hdr = ''.join(rng.choice('ACGTacgtN >|_.0123456789xyz') for _ in range(hl))
+        out += b'>' + hdr.encode() + b'\n'
+        L = rng.choice([0, 1, 7, 79, 80, 81, 160, 161, 2400, 2592, 5000, 20000, 40000]) if rng.random() < 0.6 \
+            else rng.randint(0, 30000)
+        alphabet = 'ACGT' * 30 + 'acgt' * 3 + ('N' if rng.random() < 0.5 else '') + ('RY-' if rng.random() < 0.2 else '')
+        seq = ''.join(rng.choice(alphabet) for _ in range(L))
+        if rng.random() < 0.4 and L > 200:
+            p = rng.randint(0, L - 100)
+            n = rng.randint(1, 90)
+            seq = seq[:p] + 'N' * n + seq[p + n:]
+        w = lw if rng.random() < 0.85 else rng.choice([60, 70, 80, 50, 100])
+        eol = b'\r\n' if rng.random() < 0.05 else b'\n'
+        for i in range(0, len(seq), w):
+            out += seq[i:i + w].encode() + eol
+            if rng.random() < 0.01:
+                out += b'\n'
+    if rng.random() < 0.3 and out.endswith(b'\n'):
+        out = out[:-1]
+    return bytes(out)

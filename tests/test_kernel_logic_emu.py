@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import kf_oracle as o
-from fuzzgen import rand_fasta
+from fuzzgen import rand_fasta, rand_fasta_grid
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
@@ -26,8 +26,9 @@ def emu_binary():
                                "-pthread"] + srcs + ["-o", BIN])
 
 
-def run_emu(k, threads, grid, force_walker, tile_chunks, files):
-    out = subprocess.run([BIN, str(k), str(threads), str(grid), str(int(force_walker)), str(tile_chunks)] + files,
+def run_emu(k, threads, grid, force_walker, tile_chunks, files, linegrid=True):
+    out = subprocess.run([BIN, str(k), str(threads), str(grid), str(int(force_walker)), str(tile_chunks),
+                          str(int(linegrid))] + files,
                          capture_output=True, text=True, check=True).stdout.strip().split("\n")
     res = []
     for i in range(len(files)):
@@ -68,3 +69,33 @@ def test_emulated_kernels_fuzz(seed0, tmp_path):
             for f, (tot, counts, _) in zip(files, res):
                 ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
                 assert np.array_equal(counts, ref), (s, fw, k, grid, thr, tile, f)
+
+
+def test_emulated_linegrid_fuzz(tmp_path):
+    """Fixed-width FASTA with real-file irregularities through the line-grid kernel (TMA staging emulated by memcpy)."""
+    for s in range(300, 330):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 3)):
+            p = str(tmp_path / ("g%d_%d.fa" % (s, i)))
+            open(p, "wb").write(rand_fasta_grid(rng))
+            files.append(p)
+        grid, thr, tile = rng.randint(1, 4), rng.choice([32, 64]), rng.choice([3, 8, 64])
+        res = run_emu(7, thr, grid, False, tile, files, linegrid=True)
+        for f, (tot, counts, _) in zip(files, res):
+            ref = o.canonical_counts_bytes(open(f, "rb").read(), 7)
+            assert np.array_equal(counts, ref), (s, grid, thr, tile, f)
+
+
+def test_emulated_linegrid_u16_overflow_is_detected_and_recounted(tmp_path):
+    """More than 65,535 identical 8-mer pairs in one flush interval wrap a 16-bit half of the pair histogram;
+    the low-half checksum must catch it and the CTA must recount exactly."""
+    seq = "A" * 300000 + "ACGTTGCAAGGCTTAACCGGTTAA" * 500 + "N" * 50 + "C" * 160001
+    data = (">polyA\n" + "\n".join(seq[i:i + 80] for i in range(0, len(seq), 80)) + "\n").encode()
+    p = str(tmp_path / "a.fa")
+    open(p, "wb").write(data)
+    ref = o.canonical_counts_bytes(data, 7)
+    assert int(ref.max()) > 2 * 65535
+    for grid, thr in ((1, 64), (3, 32)):
+        tot, counts, _ = run_emu(7, thr, grid, False, 64, [p], linegrid=True)[0]
+        assert np.array_equal(counts, ref)

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 
 using namespace kf;
 
@@ -103,7 +104,7 @@ bench_kernel(const uint8_t *__restrict__ arena, uint32_t n_chunks, unsigned long
         }
     } else if (MODE == FULL_PROD) {
         const SmemSink sink = make_smem_sink(hist);
-        if (c0 < c1) fasta_process_range<K, false, PF>(arena, c0, c1, 0u, sink);
+        if (c0 < c1) fasta_process_range<K, false, PF>(GlobalSrc{arena}, c0, c1, 0u, sink);
     } else {
         if (c0 < c1) simple_range<MODE, K>(arena, c0, c1, hist, sink);
     }
@@ -153,6 +154,51 @@ void run(const char *name, const uint8_t *arena, size_t bytes, int sms, unsigned
            ctas, best, gbs, bases / best / 1e9, bpc, (double)maxclk / best / 1e3, 100.0 * gbs * 1.02 / 6550.0);
 }
 
+// line-grid kernel on the same arena (one file, tiles of 1024 chunks, one CTA per SM)
+template <int THREADS>
+void run_lg(const uint8_t *arena, size_t bytes, int sms) {
+    using G = LineGrid<80>;
+    constexpr int NW = THREADS / 32;
+    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * 2 * G::STAGE + 2 * NW * sizeof(uint64_t) + 2 * sizeof(unsigned long long) + 16;
+    auto kern = count_fasta_linegrid_kernel<80, THREADS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t n_chunks = (uint32_t)(bytes / CHUNK);
+    std::vector<Tile> tiles; std::vector<int> cta_begin(sms + 1, 0);
+    for (int b = 0; b < sms; b++) {
+        cta_begin[b] = (int)tiles.size();
+        uint32_t lo = (uint32_t)((uint64_t)n_chunks * b / sms), hi = (uint32_t)((uint64_t)n_chunks * (b + 1) / sms);
+        for (uint32_t c = lo; c < hi; c += 1024) tiles.push_back(Tile{c, std::min<uint32_t>(1024, hi - c), 0u, 0u});
+    }
+    cta_begin[sms] = (int)tiles.size();
+    Tile *d_tiles; int *d_cb; uint32_t *d_P; uint64_t *d_off, *d_len; unsigned long long *d_fwd, *d_scr;
+    CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(Tile))); CK(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_cb, cta_begin.size() * sizeof(int))); CK(cudaMemcpy(d_cb, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+    uint32_t P = 81; uint64_t off = 0, len = bytes;
+    CK(cudaMalloc(&d_P, 4)); CK(cudaMemcpy(d_P, &P, 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_off, 8)); CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_len, 8)); CK(cudaMemcpy(d_len, &len, 8, cudaMemcpyHostToDevice));
+    uint32_t *d_wc; uint32_t wc[4] = {1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 16)); CK(cudaMemcpy(d_wc, wc, 16, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_fwd, 16384 * 8)); CK(cudaMemset(d_fwd, 0, 16384 * 8));
+    CK(cudaMalloc(&d_scr, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_scr, 0, (size_t)sms * 16384 * 8));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int it = 0; it < 5; it++) {
+        CK(cudaMemset(d_fwd, 0, 16384 * 8));
+        CK(cudaEventRecord(e0));
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_scr, 1, d_wc);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 1 && ms < best) best = ms;
+    }
+    std::vector<unsigned long long> h(16384);
+    CK(cudaMemcpy(h.data(), d_fwd, 16384 * 8, cudaMemcpyDeviceToHost));
+    unsigned long long tot = 0; for (auto v : h) tot += v;
+    const double bases = (double)bytes * 80.0 / 81.0, gbs = (double)bytes / best / 1e6;
+    printf("%-34s      thr=%4d ctas/SM=1  %8.3f ms  %8.1f GB/s  %6.3f Tbases/s  %6.2f bases/clk/SM@1.965GHz  total 7-mers %llu  (%.1f%% of 6550)\n",
+           "line-grid kernel LW=80 pair16", THREADS, best, gbs, bases / best / 1e9, bases / (best * 1e-3 * 1.965e9 * sms), tot, 100.0 * gbs * 1.02 / 6550.0);
+    cudaFree(d_tiles); cudaFree(d_cb); cudaFree(d_P); cudaFree(d_off); cudaFree(d_len); cudaFree(d_fwd); cudaFree(d_scr);
+}
+
 int main(int argc, char **argv) {
     size_t mib = argc > 1 ? (size_t)atol(argv[1]) : 1024;
     size_t bytes = mib << 20;
@@ -183,6 +229,9 @@ int main(int argc, char **argv) {
     run<FULL_PROD, 7, 384, 2, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
     run<FULL_PROD, 7, 384, 2, 6>("production range processor", arena, bytes, sms, g_out, d_clk);
     run<FULL_PROD, 5, 512, 2, 3>("production range processor k=5", arena, bytes, sms, g_out, d_clk);
+    run_lg<512>(arena, bytes, sms);
+    run_lg<768>(arena, bytes, sms);
+    run_lg<1024>(arena, bytes, sms);
     printf("done\n");
     return 0;
 }
