@@ -32,7 +32,7 @@ extern "C" {
 #define KF_ERR_CUDA (-3)         /* a CUDA runtime call failed; kf_last_cuda_error() has the text */
 #define KF_ERR_IO (-4)           /* file could not be read / written */
 #define KF_ERR_FORMAT (-5)       /* first byte is neither '>' nor '@' (jellyfish: "unsupported format") */
-#define KF_ERR_FASTQ (-6)        /* FASTQ is not in 4-line layout (multi-line FASTQ is not supported on GPU) */
+#define KF_ERR_FASTQ (-6)        /* FASTQ is not in 4-line layout: a line after a sequence line does not start with '+' */
 #define KF_ERR_NOMEM (-7)        /* host or device allocation failed */
 #define KF_ERR_LAYOUT (-8)       /* device arena violates the layout contract of kf_count_device */
 #define KF_ERR_EMPTY (-9)        /* zero-length input (jellyfish fails on it; the reference then crashes) */
@@ -95,6 +95,11 @@ int kf_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *
                     const uint64_t *lens, const uint8_t *formats, int n, int k, uint32_t flags,
                     uint64_t *d_counts, double *d_freq, float *d_feat, uint64_t *d_totals,
                     void *stream);
+/* Per-file status of the last kf_count_device call on this arena (waits for the device): KF_OK, KF_ERR_EMPTY,
+ * KF_ERR_FORMAT (first byte neither '>' nor '@'; such files are skipped and yield all-zero rows) or
+ * KF_ERR_FASTQ.  jellyfish reports these through its exit code, which main.py:309-311 ignores. */
+int kf_last_file_status(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *lens, const uint8_t *formats, int n,
+                        int *status_out);
 /* Number of kernels kf_count_device launched in its last call (for bench.py's gpu_launches). */
 int kf_last_launch_count(void);
 /* Device time of the counting kernel(s) of the last kf_count_device / kf_count_buffers call, from CUDA

@@ -39,6 +39,15 @@ struct Ctx {
     uint32_t *d_file_P = nullptr; size_t fP_cap = 0;
     uint32_t *d_width_counts = nullptr;
     unsigned long long *d_scratch = nullptr; size_t scratch_cap = 0;
+    // FASTQ plan: 32 KiB tiles, their '\n' counts / line types, per-file tile ranges, layout-violation offsets
+    Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
+    int *d_fq_cta_begin = nullptr; size_t fq_cta_cap = 0;
+    uint32_t *d_fq_tile_nl = nullptr; size_t fq_nl_cap = 0;
+    int *d_fq_file_tile_begin = nullptr; size_t fq_ftb_cap = 0;
+    unsigned long long *d_fq_err = nullptr; size_t fq_err_cap = 0;
+    int pc_fq_ntiles = 0, pc_fq_nfiles = 0;
+    std::vector<unsigned long long> h_fq_err;     // copied back by fetch_status
+    int fq_err_n = 0;                             // files covered by d_fq_err in the last call (0: no FASTQ)
     // end-to-end staging
     uint8_t *d_arena = nullptr; size_t arena_cap = 0;
     unsigned long long *d_counts = nullptr; size_t counts_cap = 0;
@@ -123,6 +132,65 @@ void build_plan(const uint64_t *offsets, const uint64_t *lens, const uint8_t *fo
         }
     }
     while (cta < grid) { cta++; cta_begin[(size_t)cta] = (int)tiles.size(); }
+}
+
+// FASTQ files [f0,f1): tiles of FQ_TILE_CHUNKS chunks in file order, contiguous tile-balanced CTA ranges, and the
+// tile range of every FASTQ file (for the per-file running newline count).
+constexpr uint32_t FQ_TILE_CHUNKS = 64;   // 32 KiB
+void build_fastq_plan(const uint64_t *offsets, const uint64_t *lens, const uint8_t *formats, uint32_t f0, uint32_t f1,
+                      int grid, std::vector<Tile> &tiles, std::vector<int> &cta_begin, std::vector<int> &file_tile_begin) {
+    tiles.clear();
+    file_tile_begin.assign(1, 0);
+    for (uint32_t f = f0; f < f1; f++) {
+        if (formats[f] != '@' || lens[f] == 0) continue;
+        const uint64_t fc0 = offsets[f] / CHUNK;
+        const uint64_t nch = (lens[f] + CHUNK - 1) / CHUNK;
+        for (uint64_t pos = 0; pos < nch; pos += FQ_TILE_CHUNKS) {
+            Tile t;
+            t.first_chunk = (uint32_t)(fc0 + pos);
+            t.n_chunks = (uint32_t)std::min<uint64_t>(FQ_TILE_CHUNKS, nch - pos);
+            t.file = f;
+            t.file_chunk0 = (uint32_t)fc0;
+            tiles.push_back(t);
+        }
+        file_tile_begin.push_back((int)tiles.size());
+    }
+    cta_begin.assign((size_t)grid + 1, 0);
+    for (int b = 0; b <= grid; b++) cta_begin[(size_t)b] = (int)((uint64_t)tiles.size() * (uint64_t)b / (uint64_t)grid);
+}
+
+template <int K>
+int launch_fastq(const uint8_t *d_arena, int grid, uint32_t file_base, cudaStream_t s) {
+    if constexpr (K <= KF_MAX_K_SMEM) {
+        constexpr size_t smem = sizeof(uint32_t) << (2 * K);
+        auto kern = count_fastq_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl,
+                                              (unsigned long long *)g.d_fwd - (size_t)file_base * ((size_t)1 << (2 * K)), g.d_fq_err);
+    } else {
+        count_fastq_gmem_kernel<K, THREADS_GMEM><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl,
+                                                                              (uint32_t *)g.d_fwd, file_base, g.d_fq_err);
+    }
+    CK(cudaGetLastError());
+    return KF_OK;
+}
+
+int launch_fastq_k(int k, const uint8_t *d_arena, int grid, uint32_t file_base, cudaStream_t s) {
+    switch (k) {
+        case 1: return launch_fastq<1>(d_arena, grid, file_base, s);
+        case 2: return launch_fastq<2>(d_arena, grid, file_base, s);
+        case 3: return launch_fastq<3>(d_arena, grid, file_base, s);
+        case 4: return launch_fastq<4>(d_arena, grid, file_base, s);
+        case 5: return launch_fastq<5>(d_arena, grid, file_base, s);
+        case 6: return launch_fastq<6>(d_arena, grid, file_base, s);
+        case 7: return launch_fastq<7>(d_arena, grid, file_base, s);
+        case 8: return launch_fastq<8>(d_arena, grid, file_base, s);
+        case 9: return launch_fastq<9>(d_arena, grid, file_base, s);
+        case 10: return launch_fastq<10>(d_arena, grid, file_base, s);
+        case 11: return launch_fastq<11>(d_arena, grid, file_base, s);
+        case 12: return launch_fastq<12>(d_arena, grid, file_base, s);
+        default: return KF_ERR_ARG;
+    }
 }
 
 template <int LW>
@@ -221,6 +289,22 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         CK(cudaMemcpy(g.d_file_off, offsets, (size_t)f1 * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(g.d_file_len, lens, (size_t)f1 * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(g.d_formats, formats, (size_t)f1, cudaMemcpyHostToDevice));
+        {
+            std::vector<Tile> fq_tiles;
+            std::vector<int> fq_cta_begin, fq_ftb;
+            build_fastq_plan(offsets, lens, formats, f0, f1, grid, fq_tiles, fq_cta_begin, fq_ftb);
+            g.pc_fq_ntiles = (int)fq_tiles.size();
+            g.pc_fq_nfiles = (int)fq_ftb.size() - 1;
+            if (g.pc_fq_ntiles > 0) {
+                if ((rc = ensure(g.d_fq_tiles, g.fq_tiles_cap, fq_tiles.size() * sizeof(Tile))) != KF_OK) return rc;
+                if ((rc = ensure(g.d_fq_cta_begin, g.fq_cta_cap, fq_cta_begin.size() * sizeof(int))) != KF_OK) return rc;
+                if ((rc = ensure(g.d_fq_tile_nl, g.fq_nl_cap, fq_tiles.size() * sizeof(uint32_t))) != KF_OK) return rc;
+                if ((rc = ensure(g.d_fq_file_tile_begin, g.fq_ftb_cap, fq_ftb.size() * sizeof(int))) != KF_OK) return rc;
+                CK(cudaMemcpy(g.d_fq_tiles, fq_tiles.data(), fq_tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(g.d_fq_cta_begin, fq_cta_begin.data(), fq_cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(g.d_fq_file_tile_begin, fq_ftb.data(), fq_ftb.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
         g.pc_k = k; g.pc_grid = grid; g.pc_f0 = f0; g.pc_f1 = f1; g.pc_ntiles = (int)tiles.size();
         g.pc_offsets.assign(offsets + f0, offsets + f1);
         g.pc_lens.assign(lens + f0, lens + f1);
@@ -267,6 +351,18 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         g.ev_valid = true;
         g.last_launches++;
     }
+    if (g.pc_fq_ntiles > 0) {
+        if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
+        fastq_tile_newlines_kernel<<<g.sm_count * 8, 256, 0, s>>>(d_arena, g.d_fq_tiles, g.pc_fq_ntiles, g.d_fq_tile_nl);
+        CK(cudaGetLastError());
+        fastq_tile_types_kernel<<<g.pc_fq_nfiles, 1024, 0, s>>>(g.d_fq_tile_nl, g.d_fq_file_tile_begin);
+        CK(cudaGetLastError());
+        if ((rc = launch_fastq_k(k, d_arena, grid, f0, s)) != KF_OK) return rc;
+        CK(cudaEventRecord(g.ev_k1, s));
+        g.ev_valid = true;
+        g.last_launches += 3;
+        g.fq_err_n = (int)f1;
+    }
     if (smem_path)
         fold_normalize_kernel<unsigned long long><<<nf, 1024, 0, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
                                                                        f0, d_counts, d_freq, d_feat, d_totals);
@@ -292,7 +388,13 @@ int count_device_locked(const uint8_t *d_arena, size_t arena_bytes, const uint64
     if ((prev_end + CHUNK - 1) / CHUNK + 2 >= 0xFFFFFFFFull) return KF_ERR_ARG;
     g.last_launches = 0;
     g.ev_valid = false;
+    g.fq_err_n = 0;
     if (n == 0) return KF_OK;
+    {
+        int rc0 = ensure(g.d_fq_err, g.fq_err_cap, (size_t)n * sizeof(unsigned long long));
+        if (rc0 != KF_OK) return rc0;
+        CK(cudaMemsetAsync(g.d_fq_err, 0xFF, (size_t)n * sizeof(unsigned long long), s));
+    }
     const size_t NB = (size_t)1 << (2 * k);
     if (k <= KF_MAX_K_SMEM) return run_files(d_arena, offsets, lens, formats, 0, (uint32_t)n, k, flags, d_counts, d_freq, d_feat, d_totals, s);
     // large k: bound the dense forward-count workspace
@@ -386,8 +488,7 @@ int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens_in, int n, i
         if (L == 0 || !bufs[i]) { status_out[i] = KF_ERR_EMPTY; L = 0; formats[(size_t)i] = 0; }
         else {
             formats[(size_t)i] = bufs[i][0];
-            if (bufs[i][0] == '@') { status_out[i] = KF_ERR_FASTQ; L = 0; }          // FASTQ kernel: not in this build yet
-            else if (bufs[i][0] != '>') { status_out[i] = KF_ERR_FORMAT; L = 0; }
+            if (bufs[i][0] != '>' && bufs[i][0] != '@') { status_out[i] = KF_ERR_FORMAT; L = 0; }
         }
         lens[(size_t)i] = L;
         off += (L + CHUNK - 1) / CHUNK * CHUNK;
@@ -411,6 +512,48 @@ int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens_in, int n, i
     if (freq_out) CK(cudaMemcpyAsync(freq_out, g.d_freq, (size_t)n * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
     if (totals_out) CK(cudaMemcpyAsync(totals_out, g.d_totals, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
+    // 4-line FASTQ layout check: a violation inside the file is an error unless only line ends follow it
+    if (g.fq_err_n > 0) {
+        g.h_fq_err.resize((size_t)n);
+        CK(cudaMemcpy(g.h_fq_err.data(), g.d_fq_err, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; i++) {
+            if (formats[(size_t)i] != '@' || status_out[i] != KF_OK) continue;
+            const unsigned long long e = g.h_fq_err[(size_t)i];
+            if (e == ~0ull || e < offsets[(size_t)i] || e - offsets[(size_t)i] >= lens[(size_t)i]) continue;
+            bool only_eol = true;
+            for (uint64_t p = e - offsets[(size_t)i]; p < lens[(size_t)i] && only_eol; p++)
+                only_eol = bufs[i][p] == '\n' || bufs[i][p] == '\r';
+            if (!only_eol) status_out[i] = KF_ERR_FASTQ;
+        }
+    }
+    return KF_OK;
+}
+
+int kf_last_file_status(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *lens, const uint8_t *formats, int n,
+                        int *status_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (!status_out || n < 0 || (n > 0 && (!offsets || !lens || !formats))) return KF_ERR_ARG;
+    for (int i = 0; i < n; i++)
+        status_out[i] = lens[i] == 0 ? KF_ERR_EMPTY : (formats[i] == '>' || formats[i] == '@') ? KF_OK : KF_ERR_FORMAT;
+    if (g.fq_err_n <= 0 || n == 0) return KF_OK;
+    CK(cudaDeviceSynchronize());
+    const int m = std::min(n, g.fq_err_n);
+    g.h_fq_err.resize((size_t)m);
+    CK(cudaMemcpy(g.h_fq_err.data(), g.d_fq_err, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; i++) {
+        if (formats[i] != '@' || status_out[i] != KF_OK) continue;
+        const unsigned long long e = g.h_fq_err[(size_t)i];
+        if (e == ~0ull || e < offsets[i] || e - offsets[i] >= lens[i]) continue;
+        const uint64_t rest = offsets[i] + lens[i] - e;
+        bool only_eol = rest <= 256 && d_arena != nullptr;
+        if (only_eol) {
+            uint8_t tail[256];
+            CK(cudaMemcpy(tail, d_arena + e, (size_t)rest, cudaMemcpyDeviceToHost));
+            for (uint64_t p = 0; p < rest && only_eol; p++) only_eol = tail[p] == '\n' || tail[p] == '\r';
+        }
+        if (!only_eol) status_out[i] = KF_ERR_FASTQ;
+    }
     return KF_OK;
 }
 

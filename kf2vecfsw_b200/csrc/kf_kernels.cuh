@@ -879,6 +879,251 @@ __global__ void probe_line_width_kernel(const uint8_t *__restrict__ arena, const
     atomicAdd(width_counts + (P ? (P - 51) / 10 : 0), 1u);
 }
 
+// ================================================================================================
+// FASTQ (4-line records): line type from newline parity, mask-based k-mer validity, no byte walker
+// ================================================================================================
+// A 4-line FASTQ file is a sequence of lines of type 0 '@header', 1 sequence, 2 '+...', 3 qualities, so the
+// type of a byte is (number of '\n' before it) mod 4.  Header and quality lines may hold ANY byte but '\n'
+// (qualities legitimately contain A/C/G/T and may begin with '@' or '+'), so nothing about the record
+// structure can be read off the bytes themselves: the newline count is the only sound source.  It is made
+// available in two steps: fastq_tile_newlines_kernel counts the '\n' of every 32 KiB tile, fastq_tile_types_kernel
+// turns the per-file running sum into the line type at each tile's first byte, and the counting kernel carries
+// the count from there (warp prefix sum per 512-byte chunk).
+//
+// Per 16-byte lane: bad16 has a bit for every byte that is not "A/C/G/T inside a sequence line"; the k-mer that
+// starts at byte j is counted iff bad[j .. j+K-1] is clear (the K-1 look-ahead bits and bases come from the
+// next lane by shuffle).  In 4-line FASTQ a '\n' ends the sequence, so unlike FASTA nothing is ever deleted
+// from the base stream and every lane takes the same branch-free path.
+// The layout is checked as a side effect: the line after every sequence line must begin with '+'; the lowest
+// offending byte offset per file lands in fq_err (the host maps it to KF_ERR_FASTQ).
+
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every byte of v that is non-zero
+    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t movemask4(uint32_t f) {       // f has 0x80 flags; -> 4-bit mask, byte 0 in bit 0
+    return ((f >> 7) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t newline_mask16(const uint4 w) {
+    const uint32_t n0 = ~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n1 = ~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n2 = ~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n3 = ~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u;
+    return movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12);
+}
+
+struct FqLane {
+    uint32_t bits;    // 16 bases, 2 bits each, first base in bits 31:30 (garbage where the byte is not a base)
+    uint32_t inv;     // 16-bit: byte is not A/C/G/T
+    uint32_t nl;      // 16-bit: byte is '\n' (subset of inv)
+};
+__device__ __forceinline__ FqLane fq_decode16(const uint4 w) {
+    uint32_t p0, p1, p2, p3, V0, V1, V2, V3;
+    decode_word(w.x, p0, V0);
+    decode_word(w.y, p1, V1);
+    decode_word(w.z, p2, V2);
+    decode_word(w.w, p3, V3);
+    const uint32_t r1 = __byte_perm(p3, p2, 0x0073);
+    const uint32_t r2 = __byte_perm(p1, p0, 0x0073);
+    FqLane L;
+    L.bits = __byte_perm(r1, r2, 0x5410);
+    L.inv = 0;
+    L.nl = 0;
+    if (V0 | V1 | V2 | V3) {
+        L.inv = movemask4(nonzero_bytes(V0)) | (movemask4(nonzero_bytes(V1)) << 4) | (movemask4(nonzero_bytes(V2)) << 8) |
+                (movemask4(nonzero_bytes(V3)) << 12);
+        L.nl = newline_mask16(w);
+    }
+    return L;
+}
+
+// One warp over the chunks [c0, c1) of a FASTQ file; type0 = line type at the first byte of chunk c0.
+// fq_err: lowest byte offset (arena coordinates) where the 4-line layout is violated.
+template <int K, int PF, class Sink>
+__device__ __forceinline__ void fastq_process_range(const uint8_t *__restrict__ arena, uint32_t c0, uint32_t c1, uint32_t type0,
+                                                    Sink sink, unsigned long long *fq_err) {
+    static_assert(PF >= 2 && PF <= 6, "prefetch depth");
+    const int lane = threadIdx.x & 31;
+    const GlobalSrc src{arena};
+    const uint32_t cmax = c1 + 1;   // the arena's NUL tail keeps chunk c1+1 in bounds
+    uint4 slot[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) slot[i] = src.load16(min(c0 + i, cmax), lane);
+    FqLane cur = fq_decode16(slot[0]);
+    uint32_t carry = type0;   // line type at the first byte of the current chunk
+    for (uint32_t cg = c0; cg < c1; cg += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const uint32_t c = cg + u;
+            if (c < c1) {
+                const uint4 wcur = slot[u];
+                const uint4 wnxt = slot[(u + 1) % PF];
+                const FqLane nxt = fq_decode16(wnxt);
+                // ---- line type at this lane's first byte: carry + '\n' in the lanes before ----
+                const uint32_t nlc = (uint32_t)__popc(cur.nl);
+                uint32_t incl = nlc;
+                if (__ballot_sync(FULL, nlc != 0)) {
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                }
+                const uint32_t t0 = (carry + incl - nlc) & 3u;
+                carry = (carry + __shfl_sync(FULL, incl, 31)) & 3u;
+                // ---- what the next lane starts with: first byte (for the '+' check), bases, bad bits ----
+                const uint32_t myfirst = wcur.x & 0xFFu, nxfirst = wnxt.x & 0xFFu;
+                const uint32_t nb_first = __shfl_sync(FULL, lane == 0 ? nxfirst : myfirst, (lane + 1) & 31);
+                // ---- bytes of this lane that belong to a sequence line ----
+                uint32_t seq = 0;
+                {
+                    uint32_t t = t0, start = 0, m = cur.nl;
+                    for (;;) {
+                        const uint32_t pos = m ? (uint32_t)(__ffs((int)m) - 1) : 16u;
+                        if (t == 1u) seq |= ((1u << pos) - 1u) & ~((1u << start) - 1u);
+                        if (!m) break;
+                        m &= m - 1u;
+                        start = pos + 1u;
+                        t = (t + 1u) & 3u;
+                        if (t == 2u) {   // a sequence line just ended: the next line must be the '+' line
+                            const uint32_t b = start < 16u ? byte_of(wcur, (int)start) : nb_first;
+                            if (b != (uint32_t)'+') atomicMin(fq_err, (unsigned long long)c * CHUNK + (unsigned long long)lane * 16 + start);
+                        }
+                    }
+                }
+                const uint32_t bad = (cur.inv | ~seq) & 0xFFFFu;
+                // the next lane's bad bits need ITS line types; only its bytes before its first '\n' matter here and
+                // they continue this lane's last line, so: type after my last byte == 1 and the byte is a base
+                const uint32_t t_end = (t0 + nlc) & 3u;
+                // next lane (or lane 0 of the next chunk): invalid-or-after-newline bits of its first bytes
+                const uint32_t my_lead = cur.inv | (cur.nl ? (0xFFFFu & ~((1u << (__ffs((int)cur.nl) - 1)) - 1u)) : 0u);
+                const uint32_t nx_lead = nxt.inv | (nxt.nl ? (0xFFFFu & ~((1u << (__ffs((int)nxt.nl) - 1)) - 1u)) : 0u);
+                const uint32_t nb_lead = __shfl_sync(FULL, lane == 0 ? nx_lead : my_lead, (lane + 1) & 31);
+                const uint32_t nb_bits = __shfl_sync(FULL, lane == 0 ? nxt.bits : cur.bits, (lane + 1) & 31);
+                // look-ahead bytes count only while the sequence line goes on: they do iff this lane ends inside one
+                const uint32_t ahead_bad = (t_end == 1u) ? nb_lead : 0xFFFFu;
+                uint32_t o = bad | (ahead_bad << 16);
+                {   // o[j] |= o[j+1 .. j+K-1]
+                    int cover = 1;
+#pragma unroll
+                    for (int it = 0; it < 4; it++) {
+                        if (cover < K) {
+                            const int s = (cover < K - cover) ? cover : K - cover;
+                            o |= o >> s;
+                            cover += s;
+                        }
+                    }
+                }
+                const uint32_t ok = ~o & 0xFFFFu;
+                if (ok) {
+                    const uint32_t hi = cur.bits, lo = nb_bits;
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if ((ok >> j) & 1u) sink(kmer_off_at<K>(hi, lo, j));
+                }
+                cur = nxt;
+                slot[u] = src.load16(min(c + PF, cmax), lane);
+            }
+        }
+    }
+}
+
+// '\n' count of every FASTQ tile (one warp per tile).
+__global__ void __launch_bounds__(256)
+fastq_tile_newlines_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, int n_tiles,
+                           uint32_t *__restrict__ tile_nl) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n_tiles; t += gridDim.x * wpb) {
+        const Tile T = tiles[t];
+        const uint4 *p = reinterpret_cast<const uint4 *>(arena) + (size_t)T.first_chunk * 32 + lane;
+        uint32_t n = 0;
+#pragma unroll 4
+        for (uint32_t c = 0; c < T.n_chunks; c++) {
+            const uint4 w = __ldg(p + (size_t)c * 32);
+            n += (uint32_t)__popc(~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u) + (uint32_t)__popc(~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u) +
+                 (uint32_t)__popc(~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u) + (uint32_t)__popc(~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
+        if (lane == 0) tile_nl[t] = n;
+    }
+}
+
+// Line type at the first byte of every tile: running '\n' count of the file, mod 4.  One CTA per FASTQ file;
+// file_tile_begin[f] .. file_tile_begin[f+1] are its tiles (in file order).  In place: tile_nl -> type.
+__global__ void __launch_bounds__(1024)
+fastq_tile_types_kernel(uint32_t *__restrict__ tile_nl, const int *__restrict__ file_tile_begin) {
+    __shared__ uint32_t part[1024];
+    const int t0 = file_tile_begin[blockIdx.x], t1 = file_tile_begin[blockIdx.x + 1];
+    const int n = t1 - t0;
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int a = t0 + (int)threadIdx.x * per;
+    const int b = (a + per < t1) ? a + per : t1;
+    uint32_t s = 0;
+    for (int t = a; t < b; t++) s += tile_nl[t];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < (int)blockDim.x; i++) { const uint32_t v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (int t = a; t < b; t++) { const uint32_t v = tile_nl[t]; tile_nl[t] = run & 3u; run += v; }
+}
+
+// FASTQ counting, k <= 7: per-CTA shared-memory histogram; CTA b owns tiles [cta_begin[b], cta_begin[b+1]),
+// its warps take them round-robin, the histogram is flushed when the CTA moves to another file.
+template <int K, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
+                        const uint32_t *__restrict__ tile_type, unsigned long long *__restrict__ g_fwd,
+                        unsigned long long *__restrict__ fq_err) {
+    KF_DYN_SMEM(uint32_t, hist);
+    constexpr int NB = 1 << (2 * K);
+    constexpr int NWARPS = THREADS / 32;
+    for (int i = threadIdx.x; i < NB; i += THREADS) hist[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const SmemSink emit = make_smem_sink(hist);
+    const int t1 = cta_begin[blockIdx.x + 1];
+    for (int t = cta_begin[blockIdx.x]; t < t1;) {
+        const uint32_t file = tiles[t].file;
+        int te = t + 1;
+        while (te < t1 && tiles[te].file == file) ++te;
+        for (int tt = t + warp; tt < te; tt += NWARPS) {
+            const Tile T = tiles[tt];
+            fastq_process_range<K, 3>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[tt], emit, fq_err + file);
+        }
+        __syncthreads();
+        unsigned long long *g = g_fwd + (size_t)file * NB;
+        for (int i = threadIdx.x; i < NB; i += THREADS) {
+            const uint32_t v = hist[i];
+            if (v) { atomicAdd(g + i, (unsigned long long)v); hist[i] = 0; }
+        }
+        __syncthreads();
+        t = te;
+    }
+}
+
+// FASTQ counting, k >= 8: forward counts in global memory.
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+count_fastq_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
+                        const uint32_t *__restrict__ tile_type, uint32_t *__restrict__ g_fwd32, uint32_t file_base,
+                        unsigned long long *__restrict__ fq_err) {
+    constexpr size_t NB = (size_t)1 << (2 * K);
+    constexpr int NWARPS = THREADS / 32;
+    const int warp = threadIdx.x >> 5;
+    const int t1 = cta_begin[blockIdx.x + 1];
+    for (int t = cta_begin[blockIdx.x] + warp; t < t1; t += NWARPS) {
+        const Tile T = tiles[t];
+        GmemSink emit;
+        emit.g = g_fwd32 + (size_t)(T.file - file_base) * NB;
+        fastq_process_range<K, 3>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[t], emit, fq_err + T.file);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fold to canonical + total + pseudocount + normalise (main.py:327-342), one CTA per file
 // ------------------------------------------------------------------------------------------------

@@ -75,6 +75,8 @@ def _load():
     L.kf_count_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_last_file_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p]
     L.kf_last_launch_count.restype = ctypes.c_int
     L.kf_last_count_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float)]
     L.kf_format_row.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char_p,
@@ -243,6 +245,15 @@ def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_
                            ptr(totals),
                            ctypes.c_void_p(stream.cuda_stream))
     _check(rc, "kf_count_device")
+
+
+def last_file_status(arena: DeviceArena) -> np.ndarray:
+    """Per-file status of the last ``count_device`` call on ``arena`` (waits for the device)."""
+    status = np.zeros(arena.n, dtype=np.int32)
+    _check(_load().kf_last_file_status(ctypes.c_void_p(arena.tensor.data_ptr()), arena.offsets.ctypes.data,
+                                       arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, status.ctypes.data),
+           "kf_last_file_status")
+    return status
 
 
 def last_launch_count() -> int:

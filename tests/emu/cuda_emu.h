@@ -104,3 +104,14 @@ inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 #define __shared__ static
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, int d) {
+    int l = (int)(threadIdx.x & 31);
+    T r = (T)emu::exchange((uint64_t)v, l - d < 0 ? l : l - d);
+    return r;
+}
+inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}

@@ -78,11 +78,12 @@ int main(int argc, char **argv) {
     arena.resize(arena.size() + 4096, 0);
     // same cutting rule as kf_api.cu:build_plan (chunk-balanced contiguous CTA ranges, tiles <= tile_chunks)
     uint64_t total = 0;
-    for (int i = 0; i < n; i++) total += (len[i] + CHUNK - 1) / CHUNK;
+    for (int i = 0; i < n; i++) if (!len[i] || arena[off[i]] == '>') total += (len[i] + CHUNK - 1) / CHUNK;
     std::vector<Tile> tiles; std::vector<int> cta_begin(grid + 1, 0);
     uint64_t done = 0; int cta = 0;
     auto cta_hi = [&](int b) { return total * (uint64_t)(b + 1) / (uint64_t)grid; };
     for (int f = 0; f < n; f++) {
+        if (len[f] && arena[off[f]] != '>') continue;   // FASTA plan only (kf_api.cu:build_plan)
         uint64_t fc0 = off[f] / CHUNK, nch = (len[f] + CHUNK - 1) / CHUNK, pos = 0;
         while (pos < nch) {
             while (cta < grid - 1 && done >= cta_hi(cta)) { cta++; cta_begin[cta] = (int)tiles.size(); }
@@ -120,6 +121,32 @@ int main(int argc, char **argv) {
     }
 #define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_P.data(), wc.data()); break;
     switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }
+    // FASTQ files: same sequence as kf_api.cu (tile newline counts -> tile line types -> counting kernel)
+    {
+        std::vector<Tile> fq; std::vector<int> ftb(1, 0);
+        uint32_t fq_tile = tile_chunks > 64 ? 64 : tile_chunks;
+        for (int f = 0; f < n; f++) {
+            if (!len[f] || arena[off[f]] != '@') continue;
+            uint64_t fc0 = off[f] / CHUNK, nch = (len[f] + CHUNK - 1) / CHUNK;
+            for (uint64_t pos = 0; pos < nch; pos += fq_tile)
+                fq.push_back(Tile{(uint32_t)(fc0 + pos), (uint32_t)std::min<uint64_t>(fq_tile, nch - pos), (uint32_t)f, (uint32_t)fc0});
+            ftb.push_back((int)fq.size());
+        }
+        if (!fq.empty()) {
+            std::vector<int> cb(grid + 1);
+            for (int b = 0; b <= grid; b++) cb[b] = (int)((uint64_t)fq.size() * b / grid);
+            std::vector<uint32_t> nl(fq.size(), 0);
+            std::vector<unsigned long long> err(n, ~0ull);
+            emu::launch(2, 64, 0, [&]() { fastq_tile_newlines_kernel(arena.data(), fq.data(), (int)fq.size(), nl.data()); });
+            emu::launch((unsigned)ftb.size() - 1, 64, 0, [&]() { fastq_tile_types_kernel(nl.data(), ftb.data()); });
+            size_t smem = sizeof(uint32_t) << (2 * k);
+#define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), err.data()); }); \
+                          else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), err.data()); }); break;
+            switch (k) { RUNQ(3) RUNQ(4) RUNQ(5) RUNQ(7) default: return 2; }
+            for (int f = 0; f < n; f++)
+                if (err[f] != ~0ull && err[f] - off[f] < len[f]) fprintf(stderr, "fastq layout violation file %d at %llu\n", f, err[f] - off[f]);
+        }
+    }
     std::vector<uint32_t> canon; canonical_codes(k, canon);
     long long V = (long long)canon.size();
     std::vector<unsigned long long> counts((size_t)n * V), totals(n);

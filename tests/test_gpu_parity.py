@@ -10,7 +10,7 @@ import pytest
 
 import kf_oracle as o
 import c_oracle
-from fuzzgen import rand_fasta, rand_fasta_grid
+from fuzzgen import rand_fasta, rand_fasta_grid, rand_fastq
 
 pytestmark = pytest.mark.gpu
 
@@ -180,3 +180,44 @@ def test_linegrid_u16_overflow_recount(eng):
     ref = c_oracle.count_buffer(data, 7)
     assert status[0] == 0 and np.array_equal(counts[0], ref)
     assert int(ref.max()) > 40_000_000
+
+
+# ---- FASTQ (BASELINE.json configs[3]: process_query_data preprocessing path) -----------------------------------
+@pytest.mark.parametrize("seed0", [0, 9000])
+def test_fuzz_fastq(eng, seed0):
+    for s in range(seed0, seed0 + 40):
+        rng = random.Random(s)
+        bufs = [rand_fastq(rng) if rng.random() < 0.8 else rand_fasta(rng) for _ in range(rng.randint(1, 12))]
+        k = rng.choice([1, 3, 5, 7, 7, 8, 9])
+        check_against_oracle(eng, bufs, k)
+
+
+def test_synthetic_fastq_reads_vs_c_oracle(eng):
+    """Config-4 style reads: 150 bp, random strand, 0.2 % N per base, 1 % reads with an N run, qualities that may
+    start with '@' or '+'; sized so the C oracle finishes in seconds."""
+    samples = [eng.synth_fastq(20261018, i, 1_000_000, 60_000, 150) for i in range(3)]
+    assert any(b"\n@" in bytes(s[:200000]).replace(b"\n@g", b"") for s in samples)   # a quality line starts with '@'
+    for k in (7, 9):
+        counts, freq, totals, status = eng.count_buffers(samples, k=k)
+        assert (status == 0).all()
+        ref, _, st = c_oracle.count_buffers_mt(samples, k, threads=4, want_freq=False)
+        assert np.array_equal(counts, ref)
+    # property: reads are independent records -- reversing the record order leaves the row unchanged
+    recs = bytes(samples[0]).split(b"\n")
+    recs = [b"\n".join(recs[i:i + 4]) for i in range(0, len(recs) - 1, 4)]
+    rev = b"\n".join(reversed(recs)) + b"\n"
+    a = eng.count_buffers([samples[0]], k=7)[0]
+    b = eng.count_buffers([rev], k=7)[0]
+    assert np.array_equal(a, b)
+
+
+def test_fastq_edge_inputs_and_layout_check(eng):
+    ok = [b"@r\nACGTACGTAC\n+\nIIIIIIIIII\n", b"@r\nACGTACGTAC\n+\nIIIIIIIIII", b"@r\n\n+\n\n", b"@r\nACGTACG\n+r\n@@@@@@@\n",
+          b"@r\nACGTACGTAC\n+\n+IIIIIIIII\n@s\nTTTTTTTTTT\n+\n@IIIIIIIII\n\n\n", b"@only header", b"@h\nACGTACGTACGT",
+          b"@r\n" + b"ACGTTGCA" * 5000 + b"\n+\n" + b"I" * 40000 + b"\n"]
+    check_against_oracle(eng, ok, 7)
+    check_against_oracle(eng, ok, 4)
+    # multi-line FASTQ is not in 4-line layout: reported per file, never silently miscounted
+    bad = b"@r\nACGTACGTAC\nACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIII\n@s\nACGTACGTAC\n+\nIIIIIIIIII\n"
+    counts, freq, totals, status = eng.count_buffers([ok[0], bad], k=7)
+    assert list(status) == [0, -6]

@@ -99,3 +99,24 @@ def test_emulated_linegrid_u16_overflow_is_detected_and_recounted(tmp_path):
     for grid, thr in ((1, 64), (3, 32)):
         tot, counts, _ = run_emu(7, thr, grid, False, 64, [p], linegrid=True)[0]
         assert np.array_equal(counts, ref)
+
+
+def test_emulated_fastq_fuzz(tmp_path):
+    """4-line FASTQ through the FASTQ kernels (tile newline counts -> tile line types -> mask-based counting):
+    N runs, lower case, qualities that start with '@' / '+' / '>', empty and shorter-than-k reads, files without
+    a final newline, FASTA and FASTQ mixed in one batch, tiles of 1..64 chunks."""
+    from fuzzgen import rand_fastq
+    for s in range(500, 540):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 3)):
+            fq = rng.random() < 0.8
+            p = str(tmp_path / ("q%d_%d.%s" % (s, i, "fq" if fq else "fa")))
+            open(p, "wb").write(rand_fastq(rng) if fq else rand_fasta(rng))
+            files.append(p)
+        k = rng.choice([3, 4, 5, 7])
+        grid, thr, tile = rng.randint(1, 4), rng.choice([32, 64]), rng.choice([1, 2, 3, 5, 64])
+        res = run_emu(k, thr, grid, False, tile, files)
+        for f, (tot, counts, _) in zip(files, res):
+            ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
+            assert np.array_equal(counts, ref), (s, k, grid, thr, tile, f)
