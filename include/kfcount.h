@@ -83,6 +83,15 @@ int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens, int n, int 
 int kf_count_files(const char *const *paths, int n, int k, uint32_t flags,
                    uint64_t *counts_out, double *freq_out, uint64_t *totals_out, int *status_out);
 
+/* ---- chunked-genome mode: one row per sliding window (get_chunks, main.py:813-881) -------------------------- */
+/* Replaces, per 10-kbp chunk, `seqkit sliding` + `seqkit split` + the jellyfish count/dump pair the reference runs
+ * on every chunk file (main.py:824-838, 869-881).  seq is the linearised, N-collapsed, gap-stripped sequence of one
+ * or more contigs (main.py:732-753, prepared by the host); window i is seq[win_off[i] .. win_off[i]+win_len[i]) and
+ * may overlap its neighbours.  Every byte that is not A/C/G/T (either case) breaks the k-mer window; k-mers never
+ * extend beyond their window.  Outputs as kf_count_buffers, one row per window (any may be NULL). */
+int kf_count_windows(const uint8_t *seq, size_t seq_len, const uint64_t *win_off, const uint32_t *win_len, int n, int k,
+                     uint32_t flags, uint64_t *counts_out, double *freq_out, uint64_t *totals_out);
+
 /* ---- counting, device-resident arena (kernel-only path; trainer hand-off) --------------------- */
 /* Arena layout contract: file i occupies d_arena[offsets[i] .. offsets[i]+lens[i]); offsets[i] is a
  * multiple of KF_CHUNK; files are in increasing offset order and do not overlap; every byte of the
@@ -115,6 +124,15 @@ int64_t kf_format_row(const char *sample, const double *row, int64_t V, int int_
                       size_t out_len);
 int kf_write_kf(const char *out_path, const char *sample, const double *row, int64_t V, int int_mode,
                 int append);
+
+/* ---- .kf reader: utils.py:436-437 (my_read_csv), classify.py:102-114, query.py:148-158 ---------------------- */
+/* Parses "label,v1,...,vV\n" rows from a text buffer (one or many .kf files concatenated, as query.py:153 does with
+ * `cat`).  out [rows][V] double (may be NULL), feat_out [rows][V] float = float(v * 1e4) as the trainers build it
+ * (train_classifier_model.py:149,323; may be NULL), label_off/label_len locate each label inside text (may be NULL).
+ * Conversion is correctly rounded (repr()-written values round-trip bit-exactly).  Returns the number of rows in
+ * the text (only the first max_rows are stored), or KF_ERR_FORMAT (wrong column count / unparsable value). */
+int64_t kf_parse_kf(const char *text, size_t len, int64_t V, int64_t max_rows, double *out, float *feat_out,
+                    int64_t *label_off, int32_t *label_len);
 
 /* ---- synthetic inputs (bench / tests) ---------------------- */
 /* Deterministic bacterial-size FASTA: GC ~ U(0.30,0.70) from seed, n_bases split into 1..50 contigs,

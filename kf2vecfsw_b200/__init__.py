@@ -10,6 +10,9 @@ from .engine import (  # noqa: F401
     count_buffers,
     count_device,
     count_files,
+    count_windows,
+    parse_kf,
+    last_file_status,
     DeviceArena,
     format_row,
     init,
@@ -24,5 +27,8 @@ from .engine import (  # noqa: F401
     write_kf,
 )
 from .frequencies import get_frequencies, frequency_matrix  # noqa: F401
+from .chunks import get_chunks  # noqa: F401
+from .kmers import get_kmers  # noqa: F401
+from .loader import load_kf_dir, load_kf_files, read_chunk_kf, read_kf  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,159 @@
+"""Drop-in for kf2vec's ``get_chunks(args)`` (reference ``kf2vec/main.py:654-929``): the chunked-genome mode.
+
+The reference shells out, per genome, to ``seqtk seq -l 0`` (linearise, :732), ``awk gsub(/[N|n]+/,"N")``
+(collapse N runs, :740), ``seqkit seq -m 10000 -g`` (drop gaps, drop contigs under 10 kbp, :753),
+``seqkit split`` (:784), ``seqtk comp`` + ``seqkit sliding`` per contig (:808-824), ``seqkit split`` again
+(:837) and then runs ``get_frequencies(raw_cnt=True)`` -- one ``jellyfish count`` + ``dump`` pair per 10-kbp
+chunk (:869-881) -- before concatenating the chunk rows (:895-915).  Here the text preparation is a few
+``bytes`` operations on the host and all windows of a genome go to the GPU in ONE call
+(``kf_count_windows``); the output file, row labels, row order within a contig, thresholds and log lines
+are the reference's.  Contig order follows the input file (the reference's ``os.listdir`` order is arbitrary).
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+import re
+import sys
+import time
+from typing import List, Tuple
+
+import numpy as np
+
+from . import engine
+from .frequencies import list_inputs, DEFAULT_K
+
+CHUNK_SZ = 10000     # main.py:100
+CHUNK_CNT_THR = 5    # main.py:101
+_N_RUN = re.compile(rb"[N|n]+")   # main.py:740 -- the awk class holds 'N', '|' and 'n'
+_GAPS = b"-. "                    # seqkit seq -g (main.py:753)
+
+
+def hms(sec_elapsed):   # utils.py:320-328
+    h = int(sec_elapsed / (60 * 60))
+    m = int((sec_elapsed % (60 * 60)) / 60)
+    s = int(sec_elapsed % 60)
+    return h, m, s
+
+
+def fasta_records(data: bytes) -> List[Tuple[str, bytes]]:
+    """(header text without '>', linearised sequence) per record -- seqtk seq -l 0 (main.py:732)."""
+    recs: List[Tuple[str, bytes]] = []
+    for block in data.split(b"\n>") if data.startswith(b">") else []:
+        if block.startswith(b">"):
+            block = block[1:]
+        head, _, body = block.partition(b"\n")
+        recs.append((head.decode("latin-1"), body.replace(b"\n", b"").replace(b"\r", b"")))
+    return recs
+
+
+def window_plan(length: int) -> List[Tuple[int, int]]:
+    """1-based inclusive windows of one contig: main.py:813-824 (seqkit sliding emits full windows only)."""
+    total_chunks = math.ceil(length / CHUNK_SZ)
+    ovrlap = int(math.ceil((total_chunks * CHUNK_SZ - length) / (total_chunks - 1))) if total_chunks != 1 else 0
+    step = CHUNK_SZ - ovrlap
+    out, s = [], 0
+    while s + CHUNK_SZ <= length:
+        out.append((s + 1, s + CHUNK_SZ))
+        s += step
+    return out
+
+
+def plan_genome(sample: str, data: bytes):
+    """Host-side text preparation of one genome.  Returns (sequence buffer, window offsets, window lengths, labels)."""
+    parts, offs, lens, labels = [], [], [], []
+    base = 0
+    for header, seq in fasta_records(data):
+        seq = _N_RUN.sub(b"N", seq).translate(None, _GAPS)
+        if len(seq) < CHUNK_SZ:                                   # seqkit seq -m 10000 (main.py:753)
+            continue
+        cid = header.split()[0] if header.split() else ""
+        for (a, b) in window_plan(len(seq)):
+            offs.append(base + a - 1)
+            lens.append(b - a + 1)
+            # file name seqkit split gives the chunk, minus '.fna' (main.py:895-896)
+            labels.append("{}.part_{}.part_{}_sliding__{}-{}".format(sample, cid, cid, a, b))
+        parts.append(seq)
+        base += len(seq)
+    return b"".join(parts), np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint32), labels
+
+
+def chunk_rows(sample: str, data: bytes, k: int = DEFAULT_K, pseudocount: bool = False):
+    """(labels, raw counts u64 [n, V]) for one genome; ([], None) if it has fewer than 5 chunks."""
+    seq, offs, lens, labels = plan_genome(sample, data)
+    if len(labels) < CHUNK_CNT_THR:
+        return labels, None
+    counts, _, _ = engine.count_windows(np.frombuffer(seq, dtype=np.uint8), offs, lens, k=k)
+    return labels, counts
+
+
+def get_chunks(args) -> None:
+    """Reference: kf2vec/main.py:654-929."""
+    since = time.time()
+    if not os.path.exists(args.input_dir):
+        print("No such directory '{}'".format(args.input_dir), file=sys.stderr)
+        exit(0)
+    if not os.path.exists(args.output_dir):
+        print("No such directory '{}'".format(args.output_dir), file=sys.stderr)
+        exit(0)
+
+    log = logging.getLogger("kf2vecfsw_b200.get_chunks")
+    log.setLevel(logging.INFO)
+    log.propagate = False
+    for h in list(log.handlers):
+        log.removeHandler(h)
+    fh = logging.FileHandler(os.path.join(args.output_dir, 'get_chunks_{}.log'.format(
+        os.path.basename(os.path.normpath(args.input_dir)))), 'w+')
+    sh = logging.StreamHandler()
+    for h in (fh, sh):
+        h.setFormatter(logging.Formatter('%(message)s'))
+        log.addHandler(h)
+
+    def stamp():
+        return '{:02d}:{:02d}:{:02d}'.format(*hms(time.time() - since))
+
+    k = getattr(args, 'k', DEFAULT_K)
+    pseudocount = bool(getattr(args, 'pseudocount', False))
+    log.info('\n==> Making a list of sample names. Time: {}\n'.format(stamp()))
+    files_names, samples_names = list_inputs(args.input_dir)
+    log.info('\n==> Start processing samples. Time: {}\n'.format(stamp()))
+
+    for fname, sample in zip(files_names, samples_names):
+        log.info('\n==> Start processing. Sample: {}'.format(fname))
+        with open(os.path.join(args.input_dir, fname), "rb") as f:
+            data = f.read()
+        log.info('>>> Formatting to single line. Sample: {}'.format(fname))
+        log.info('>>> Replacing stretches of N. Sample: {}'.format(fname))
+        log.info('>>> Filtering contigs below threshold {}. Sample: {}'.format(str(CHUNK_SZ), fname))
+        seq, offs, lens, labels = plan_genome(sample, data)
+        if len(seq) == 0:
+            log.info('\n==> Excluded {}. No contigs above threshold length. Time: {}\n'.format(fname, stamp()))
+            continue
+        log.info('>>> Splitting into contigs. Sample: {}'.format(fname))
+        log.info('>>> Getting contig ids. Sample: {}'.format(fname))
+        log.info('>>> Computing contig statistics. Sample: {}'.format(fname))
+        if len(labels) < CHUNK_CNT_THR:
+            log.info('\n==> Excluded {}. {} chunks is too low. {} is required. Time: {}\n'.format(
+                fname, len(labels), CHUNK_CNT_THR, stamp()))
+            continue
+        log.info('\n==> Done chunk processing for {}. Time: {}\n'.format(fname, stamp()))
+
+        counts, _, _ = engine.count_windows(np.frombuffer(seq, dtype=np.uint8), offs, lens, k=k)
+        log.info('\n==> Done computing k-mer frequences for {}. Time: {}\n'.format(fname, stamp()))
+
+        # get_frequencies(raw_cnt=True) rows (main.py:327-357): pandas keeps int64 only when no k-mer is missing
+        out_path = os.path.join(args.output_dir, "{}.{}".format(sample, "kf"))
+        if os.path.exists(out_path):
+            os.remove(out_path)
+        vals = counts.astype(np.float64)
+        if pseudocount:
+            vals += 0.5
+        for i, label in enumerate(labels):
+            int_mode = (not pseudocount) and bool(np.all(counts[i] > 0))
+            engine.write_kf(out_path, label, vals[i], int_mode=int_mode, append=True)
+
+    log.info('\n==> Done getting chunks. Time: {}\n'.format(stamp()))
+    for h in (fh, sh):
+        log.removeHandler(h)
+        h.close()

@@ -49,6 +49,9 @@ struct Ctx {
     std::vector<unsigned long long> h_fq_err;     // copied back by fetch_status
     int fq_err_n = 0;                             // files covered by d_fq_err in the last call (0: no FASTQ)
     // end-to-end staging
+    uint8_t *d_seq = nullptr; size_t seq_cap = 0;              // kf_count_windows: linearised sequence
+    uint64_t *d_win_off = nullptr; size_t woff_cap = 0;
+    uint32_t *d_win_len = nullptr; size_t wlen_cap = 0;
     uint8_t *d_arena = nullptr; size_t arena_cap = 0;
     unsigned long long *d_counts = nullptr; size_t counts_cap = 0;
     double *d_freq = nullptr; size_t freq_cap = 0;
@@ -441,7 +444,8 @@ int kf_shutdown(void) {
     if (g.device < 0) return KF_OK;
     cudaDeviceSynchronize();
     cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
-    cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals);
+    cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals); cudaFree(g.d_seq); cudaFree(g.d_win_off); cudaFree(g.d_win_len);
+    cudaFree(g.d_fq_tiles); cudaFree(g.d_fq_cta_begin); cudaFree(g.d_fq_tile_nl); cudaFree(g.d_fq_file_tile_begin); cudaFree(g.d_fq_err);
     cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_scratch); cudaFree(g.d_width_counts);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
@@ -554,6 +558,48 @@ int kf_last_file_status(const uint8_t *d_arena, const uint64_t *offsets, const u
         }
         if (!only_eol) status_out[i] = KF_ERR_FASTQ;
     }
+    return KF_OK;
+}
+
+int kf_count_windows(const uint8_t *seq, size_t seq_len, const uint64_t *win_off, const uint32_t *win_len, int n, int k,
+                     uint32_t flags, uint64_t *counts_out, double *freq_out, uint64_t *totals_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (n < 0 || k < KF_MIN_K || k > KF_MAX_K || (n > 0 && (!seq || !win_off || !win_len))) return KF_ERR_ARG;
+    if (n == 0) return KF_OK;
+    uint32_t max_len = 0;
+    for (int i = 0; i < n; i++) {
+        if (win_off[i] > seq_len || win_len[i] > seq_len - win_off[i]) return KF_ERR_ARG;
+        max_len = std::max(max_len, win_len[i]);
+    }
+    const int64_t V = kf_vocab_size(k);
+    const uint64_t slot = ((uint64_t)max_len + 2 + CHUNK - 1) / CHUNK * CHUNK;
+    const size_t arena_bytes = (size_t)n * slot + KF_TAIL_PAD;
+    int rc;
+    if ((rc = ensure(g.d_seq, g.seq_cap, seq_len + 16)) != KF_OK) return rc;
+    if ((rc = ensure(g.d_win_off, g.woff_cap, (size_t)n * sizeof(uint64_t))) != KF_OK) return rc;
+    if ((rc = ensure(g.d_win_len, g.wlen_cap, (size_t)n * sizeof(uint32_t))) != KF_OK) return rc;
+    if ((rc = ensure(g.d_arena, g.arena_cap, arena_bytes)) != KF_OK) return rc;
+    if ((rc = ensure(g.d_counts, g.counts_cap, (size_t)n * V * sizeof(unsigned long long))) != KF_OK) return rc;
+    if ((rc = ensure(g.d_freq, g.freq_cap, (size_t)n * V * sizeof(double))) != KF_OK) return rc;
+    if ((rc = ensure(g.d_totals, g.totals_cap, (size_t)n * sizeof(unsigned long long))) != KF_OK) return rc;
+    CK(cudaMemcpyAsync(g.d_seq, seq, seq_len, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.d_win_off, win_off, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.d_win_len, win_len, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemsetAsync(g.d_arena + (size_t)n * slot, 0, KF_TAIL_PAD, g.stream));
+    gather_windows_kernel<<<std::min(n, g.sm_count * 8), 256, 0, g.stream>>>(g.d_seq, g.d_win_off, g.d_win_len, n, slot, g.d_arena);
+    CK(cudaGetLastError());
+    std::vector<uint64_t> offsets((size_t)n), lens((size_t)n);
+    std::vector<uint8_t> formats((size_t)n, (uint8_t)'>');
+    for (int i = 0; i < n; i++) { offsets[(size_t)i] = (uint64_t)i * slot; lens[(size_t)i] = (uint64_t)win_len[i] + 2; }
+    rc = count_device_locked(g.d_arena, arena_bytes, offsets.data(), lens.data(), formats.data(), n, k, flags, g.d_counts,
+                             freq_out ? g.d_freq : nullptr, nullptr, g.d_totals, g.stream);
+    if (rc != KF_OK) return rc;
+    g.last_launches++;
+    if (counts_out) CK(cudaMemcpyAsync(counts_out, g.d_counts, (size_t)n * V * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    if (freq_out) CK(cudaMemcpyAsync(freq_out, g.d_freq, (size_t)n * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    if (totals_out) CK(cudaMemcpyAsync(totals_out, g.d_totals, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
     return KF_OK;
 }
 

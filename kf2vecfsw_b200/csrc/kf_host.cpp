@@ -241,6 +241,53 @@ int kf_write_kf(const char *out_path, const char *sample, const double *row, int
     return (w == (size_t)n && rc == 0) ? KF_OK : KF_ERR_IO;
 }
 
+// ---- .kf reader (utils.py:436-437 my_read_csv; classify.py:102-114; query.py:148-158) ----------------------------
+// Parses the rows "label,v1,...,vV\n" of a .kf text buffer.  Values are converted with std::from_chars (correctly
+// rounded, so repr()-formatted numbers round-trip bit-exactly); "nan" parses to NaN; integers ("5") are accepted.
+// out rows are written as double [row][V]; if feat_out is given it receives float(value * 1e4), the tensor the
+// trainers build (train_classifier_model.py:149,323).  label_off/label_len locate each row's label in text.
+// Returns the number of rows parsed (may exceed max_rows: then only the first max_rows were stored), or a negative
+// error: KF_ERR_FORMAT when a row has other than V values or a value does not parse.
+int64_t kf_parse_kf(const char *text, size_t len, int64_t V, int64_t max_rows, double *out, float *feat_out,
+                    int64_t *label_off, int32_t *label_len) {
+    if (!text || V < 0 || max_rows < 0) return KF_ERR_ARG;
+    const char *p = text, *end = text + len;
+    int64_t row = 0;
+    while (p < end) {
+        const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char *le = eol;
+        if (le > p && le[-1] == '\r') le--;
+        if (le == p) { p = eol + 1; continue; }   // blank line
+        const char *c = (const char *)memchr(p, ',', (size_t)(le - p));
+        const bool store = row < max_rows;
+        if (store && label_off) label_off[row] = (int64_t)(p - text);
+        if (store && label_len) label_len[row] = (int32_t)((c ? c : le) - p);
+        int64_t nv = 0;
+        const char *q = c ? c + 1 : le;
+        while (c && q <= le) {
+            const char *ve = (const char *)memchr(q, ',', (size_t)(le - q));
+            if (!ve) ve = le;
+            double v;
+            if (ve - q == 3 && (q[0] == 'n' || q[0] == 'N') && (q[1] == 'a' || q[1] == 'A') && (q[2] == 'n' || q[2] == 'N')) v = NAN;
+            else {
+                auto r = std::from_chars(q, ve, v);
+                if (r.ec != std::errc() || r.ptr != ve) return KF_ERR_FORMAT;
+            }
+            if (nv >= V) return KF_ERR_FORMAT;
+            if (store && out) out[row * V + nv] = v;
+            if (store && feat_out) feat_out[row * V + nv] = (float)(v * 1e4);
+            nv++;
+            if (ve == le) break;
+            q = ve + 1;
+        }
+        if (nv != V) return KF_ERR_FORMAT;
+        row++;
+        p = eol + 1;
+    }
+    return row;
+}
+
 int64_t kf_synth_fasta(uint64_t seed, int64_t genome_id, int64_t n_bases, int line_width, uint8_t *out,
                        size_t out_len) {
     return kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, 50, 10, out, out_len);

@@ -1125,6 +1125,24 @@ count_fastq_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Chunked-genome mode (kf2vec/main.py:813-881): every sliding window of a linearised contig becomes a one-record
+// pseudo-file ">\n<window bytes>" in a scratch arena, so the counting kernels above see it as an ordinary input
+// and each window yields one row.  One CTA per window; src windows may overlap and need no alignment.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_windows_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ win_off, const uint32_t *__restrict__ win_len,
+                      int n, uint64_t slot_bytes, uint8_t *__restrict__ arena) {
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
+        uint8_t *dst = arena + (uint64_t)w * slot_bytes;
+        const uint8_t *src = seq + win_off[w];
+        const uint32_t len = win_len[w];
+        if (threadIdx.x == 0) { dst[0] = (uint8_t)'>'; dst[1] = 0x0Au; }
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) { const uint8_t c = src[i]; dst[2 + i] = c == 0x0Au ? (uint8_t)'N' : c; }   // a stray '\n' must break, not join
+        for (uint64_t i = 2 + (uint64_t)len + threadIdx.x; i < slot_bytes; i += blockDim.x) dst[i] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fold to canonical + total + pseudocount + normalise (main.py:327-342), one CTA per file
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t revcomp_std(uint32_t x, int k) {

@@ -75,6 +75,8 @@ def _load():
     L.kf_count_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_count_windows.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.kf_last_file_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p]
     L.kf_last_launch_count.restype = ctypes.c_int
@@ -84,6 +86,9 @@ def _load():
     L.kf_format_row.restype = ctypes.c_int64
     L.kf_write_kf.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                               ctypes.c_int]
+    L.kf_parse_kf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_parse_kf.restype = ctypes.c_int64
     L.kf_synth_fasta.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                  ctypes.c_size_t]
     L.kf_synth_fasta.restype = ctypes.c_int64
@@ -197,6 +202,26 @@ def count_files(paths: Sequence[str], k: int = 7, pseudocount: bool = False, raw
     return counts, freq, totals, status
 
 
+def count_windows(seq, win_off, win_len, k: int = 7, pseudocount: bool = False, raw_cnt: bool = True,
+                  want_freq: bool = False):
+    """Chunked-genome mode: one row per window seq[win_off[i] : win_off[i] + win_len[i]] of a linearised sequence.
+    Returns (counts u64 [n,V], freq f64 [n,V] | None, totals u64 [n])."""
+    _require_init()
+    seq = _as_u8(seq)
+    win_off = np.ascontiguousarray(win_off, dtype=np.uint64)
+    win_len = np.ascontiguousarray(win_len, dtype=np.uint32)
+    n = int(win_off.size)
+    V = vocab_size(k)
+    counts = np.empty((n, V), dtype=np.uint64)
+    freq = np.empty((n, V), dtype=np.float64) if want_freq else None
+    totals = np.zeros(n, dtype=np.uint64)
+    _check(_load().kf_count_windows(seq.ctypes.data if seq.size else None, seq.size, win_off.ctypes.data,
+                                    win_len.ctypes.data, n, k, _flags(pseudocount, raw_cnt), counts.ctypes.data,
+                                    freq.ctypes.data if freq is not None else None, totals.ctypes.data),
+           "kf_count_windows")
+    return counts, freq, totals
+
+
 # ---- counting: device-resident arena ------------------------------------------------------------------
 class DeviceArena:
     """A batch of input files laid out in HBM per the contract of ``kf_count_device``: every file starts
@@ -281,6 +306,25 @@ def write_kf(path: str, sample: str, row: np.ndarray, int_mode: bool = False, ap
     row = np.ascontiguousarray(row, dtype=np.float64)
     _check(_load().kf_write_kf(os.fsencode(path), sample.encode(), row.ctypes.data, row.size, 1 if int_mode else 0,
                                1 if append else 0), "kf_write_kf(%s)" % path)
+
+
+def parse_kf(text: bytes, V: int, want_rows: bool = True, want_feat: bool = False):
+    """Rows of one or more concatenated .kf files.  Returns (labels, rows f64 [n,V] | None, feat f32 [n,V] | None)
+    where feat = float32(value * 1e4) (train_classifier_model.py:149,323)."""
+    L = _load()
+    n = int(L.kf_parse_kf(text, len(text), V, 0, None, None, None, None))
+    if n < 0:
+        raise KfError(n, "kf_parse_kf")
+    rows = np.empty((n, V), dtype=np.float64) if want_rows else None
+    feat = np.empty((n, V), dtype=np.float32) if want_feat else None
+    off = np.zeros(n, dtype=np.int64)
+    ln = np.zeros(n, dtype=np.int32)
+    m = int(L.kf_parse_kf(text, len(text), V, n, rows.ctypes.data if rows is not None else None,
+                          feat.ctypes.data if feat is not None else None, off.ctypes.data, ln.ctypes.data))
+    if m != n:
+        raise KfError(m if m < 0 else -5, "kf_parse_kf")
+    labels = [text[int(o): int(o) + int(l)].decode() for o, l in zip(off, ln)]
+    return labels, rows, feat
 
 
 # ---- synthetic inputs --------------------------------------------------------------------------------------

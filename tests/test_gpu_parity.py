@@ -221,3 +221,56 @@ def test_fastq_edge_inputs_and_layout_check(eng):
     bad = b"@r\nACGTACGTAC\nACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIII\n@s\nACGTACGTAC\n+\nIIIIIIIIII\n"
     counts, freq, totals, status = eng.count_buffers([ok[0], bad], k=7)
     assert list(status) == [0, -6]
+
+
+# ---- chunked-genome mode (get_chunks, main.py:654-929; BASELINE.json configs[4]) -------------------------------
+def test_get_chunks_reproduces_reference_golden_rows(eng, toy_inputs, golden_dir, tmp_path):
+    """All 358 rows of the reference's committed toy_example/train_tree_chunks/*.kf, text-exact (sha256 of every
+    line); contig order is the input file's (the reference's is os.listdir order), order within a contig is checked."""
+    import hashlib
+    import json
+    from kf2vecfsw_b200 import get_chunks
+    gold = json.load(open(os.path.join(golden_dir, "chunks_golden.json")))
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir(); outd.mkdir()
+    for s in gold:
+        (ind / (s + ".fna")).write_bytes(toy_inputs[s])
+    (ind / "tiny.fna").write_bytes(b">c1\n" + b"ACGT" * 2500 + b"\n")       # 1 chunk < 5: excluded (main.py:845)
+    (ind / "short.fna").write_bytes(b">c1\n" + b"ACGT" * 100 + b"\n")       # no contig >= 10 kbp: excluded (main.py:761)
+    get_chunks(argparse.Namespace(input_dir=str(ind), output_dir=str(outd), k=7, p=4, pseudocount=False))
+    total = 0
+    for s, rows in gold.items():
+        lines = (outd / (s + ".kf")).read_bytes().splitlines(keepends=True)
+        assert len(lines) == len(rows)
+        gd = dict(rows)
+        for ln in lines:
+            label = ln.split(b",", 1)[0].decode()
+            assert hashlib.sha256(ln).hexdigest() == gd[label], label
+            total += 1
+        def contig_order(labels):
+            seen = {}
+            for l in labels:
+                seen.setdefault(l.split(".part_")[1], []).append(l)
+            return seen
+        ours, ref = contig_order([l.split(b",", 1)[0].decode() for l in lines]), contig_order([r[0] for r in rows])
+        assert ours == ref
+    assert total == 358
+    assert not (outd / "tiny.kf").exists() and not (outd / "short.kf").exists()
+    log = (outd / "get_chunks_in.log").read_text()
+    assert "Excluded tiny.fna. 1 chunks is too low. 5 is required." in log
+    assert "Excluded short.fna. No contigs above threshold length." in log
+    assert sorted(os.listdir(outd)) == sorted([s + ".kf" for s in gold] + ["get_chunks_in.log"])   # no tmp dirs left
+
+
+@pytest.mark.parametrize("k", [5, 7, 9])
+def test_count_windows_vs_oracle(eng, k):
+    rng = random.Random(k)
+    seq = "".join(rng.choice("ACGT" * 30 + "Nn" + "acgt" * 3 + "R") for _ in range(60000)).encode()
+    offs = [0, 1, 15, 16, 17, 511, 512, 513, 9999, 20000, 59000, 59990, 60000 - k, 0]
+    lens = [10000, 10000, 10000, 10000, 10000, 10000, 10000, 10000, 10000, 3, 1000, 10, k, 60000]
+    counts, freq, totals = eng.count_windows(np.frombuffer(seq, dtype=np.uint8), offs, lens, k=k)
+    for i, (a, n) in enumerate(zip(offs, lens)):
+        sym = o._CODE_LUT[np.frombuffer(seq[a:a + n], dtype=np.uint8)]
+        ref = o.fold_canonical(o.forward_counts(sym, k), k)
+        assert np.array_equal(counts[i], ref), i
+        assert int(totals[i]) == int(ref.sum())

@@ -114,3 +114,61 @@ def test_list_inputs_naming(tmp_path):
     assert set(files) == {"a.fna", "b.fa", "c.fasta", "d.fq", "e.fastq", "y.f.fna"}
     assert m["y.f.fna"] == "y.f" and m["c.fasta"] == "c" and m["e.fastq"] == "e"
     assert (files, samples) == tuple(map(list, zip(*o.list_inputs(str(tmp_path)))))
+
+
+def test_parse_kf_round_trips_golden_rows_and_matches_trainer_tensor(toy_golden_kf):
+    """The .kf reader (utils.py:436-437 and friends): values are exactly float(text) and the trainers' tensor
+    float32(value * 1e4) equals what pandas + numpy build (train_classifier_model.py:144-150)."""
+    import io
+    import pandas as pd
+    text = "".join(toy_golden_kf[s] for s in sorted(toy_golden_kf)).encode()
+    labels, rows, feat = engine.parse_kf(text, 8192, want_feat=True)
+    assert labels == sorted(toy_golden_kf)
+    for i, s in enumerate(labels):
+        exact = np.array([float(x) for x in toy_golden_kf[s].strip().split(",")[1:]])
+        assert np.array_equal(rows[i], exact)
+        assert engine.format_row(s, rows[i]) == toy_golden_kf[s]          # writer(reader(x)) == x
+    df = pd.read_csv(io.BytesIO(text), index_col=0, header=None, sep=",")   # the reference's reader
+    assert list(df.index) == labels
+    assert np.array_equal(feat, (df.values * 1e4).astype(np.float32))
+    assert np.allclose(rows, df.values, rtol=1e-14, atol=0)                  # pandas xstrtod is a few ulp off at times
+
+
+def test_parse_kf_formats_and_errors():
+    labels, rows, _ = engine.parse_kf(b"a,1,2,3\nb,1.0,0.0,nan\r\n\nc.part_x,5e-05,1e+16,0.5", 3)
+    assert labels == ["a", "b", "c.part_x"]
+    assert np.array_equal(rows[0], [1, 2, 3]) and np.isnan(rows[1][2]) and rows[2][0] == 5e-05 and rows[2][1] == 1e16
+    for bad in (b"a,1,2\n", b"a,1,2,3,4\n", b"a,1,x,3\n", b"a\n"):
+        with pytest.raises(engine.KfError):
+            engine.parse_kf(bad, 3)
+    assert engine.parse_kf(b"", 3)[0] == []
+
+
+def test_loader_and_chunk_readers(tmp_path, toy_golden_kf):
+    from kf2vecfsw_b200 import loader
+    for s, t in toy_golden_kf.items():
+        (tmp_path / (s + ".kf")).write_text(t)
+    (tmp_path / "chunks.kf").write_text("g.part_c.part_c_sliding__1-10000,16.0,0.0,300.0\ng.part_c.part_c_sliding__5-10004,1.0,255.0,256.0\n")
+    labels, rows = loader.read_kf(str(tmp_path / "G000830275sub.kf"))
+    assert labels == ["G000830275sub"] and rows.shape == (1, 8192)
+    names, feat = loader.load_kf_files([str(tmp_path / (s + ".kf")) for s in sorted(toy_golden_kf)])
+    assert names == sorted(toy_golden_kf) and tuple(feat.shape) == (7, 8192) and str(feat.dtype) == "torch.float32"
+    assert abs(float(feat[0].double().sum()) - 1e4) < 1e-2
+    lab, u16 = loader.read_chunk_kf(str(tmp_path / "chunks.kf"))
+    assert u16.dtype == np.uint16 and u16.tolist() == [[16, 0, 300], [1, 255, 256]]
+    lab, u8 = loader.read_chunk_kf(str(tmp_path / "chunks.kf"), cap_uint8=True)
+    assert u8.dtype == np.uint8 and u8.tolist() == [[16, 0, 255], [1, 255, 255]]       # utils.py:416-431
+
+
+def test_kmer_matrix_is_the_fsw_feature_layout():
+    """get_kmers (main.py:112-184): observed canonical k-mers as base codes A0 T1 C2 G3 + float32 normalised count."""
+    from kf2vecfsw_b200 import kmers
+    k = 3
+    counts = o.canonical_counts_bytes(b">a\nACGTTGCAAT\n", k)
+    m = kmers.kmer_matrix(counts, k)
+    assert m.dtype == np.float32 and m.shape == (int((counts > 0).sum()), k + 1)
+    code = {"A": 0.0, "T": 1.0, "C": 2.0, "G": 3.0}
+    words = [w for w, c in zip(o.vocab(k), counts) if c]
+    assert [[code[ch] for ch in w] for w in words] == m[:, :k].tolist()
+    c32 = counts[counts > 0].astype(np.float32)
+    assert np.array_equal(m[:, k], c32 / np.sum(c32))
