@@ -38,6 +38,9 @@ struct Ctx {
     uint8_t *d_formats = nullptr; size_t fmt_cap = 0;
     uint32_t *d_file_P = nullptr; size_t fP_cap = 0;
     uint32_t *d_width_counts = nullptr;
+    uint32_t *d_file_row = nullptr; size_t frow_cap = 0;          // first forward-count row of every file (+ total)
+    uint32_t *d_cta_first_rank = nullptr; size_t cfr_cap = 0;    // per line-kernel CTA: how many earlier CTAs hold a piece of its first file
+    uint32_t pc_rows = 0;
     unsigned long long *d_scratch = nullptr; size_t scratch_cap = 0;
     // FASTQ plan: 32 KiB tiles, their '\n' counts / line types, per-file tile ranges, layout-violation offsets
     Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
@@ -137,6 +140,31 @@ void build_plan(const uint64_t *offsets, const uint64_t *lens, const uint8_t *fo
     while (cta < grid) { cta++; cta_begin[(size_t)cta] = (int)tiles.size(); }
 }
 
+// Forward-count rows.  k <= 7: a FASTA file gets one row per line-kernel CTA that holds a piece of it (that CTA writes
+// its row with plain stores; the generic kernel adds into the first row), every other file one row.  The fold sums a
+// file's rows.  Line-kernel CTA b takes the tile ranges of the generic CTAs [b * stride, (b + 1) * stride).
+void build_rows(const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid, int stride, uint32_t f1,
+                bool per_cta_rows, std::vector<uint32_t> &file_row, std::vector<uint32_t> &cta_first_rank) {
+    std::vector<uint32_t> nrows((size_t)f1, 1u);
+    const int nlc = (grid + stride - 1) / stride;
+    cta_first_rank.assign((size_t)std::max(1, nlc), 0u);
+    if (per_cta_rows) {
+        std::vector<int> last_cta((size_t)f1, -1);
+        std::vector<uint32_t> cnt((size_t)f1, 0u);
+        for (int b = 0; b < nlc; b++) {
+            const int t0 = cta_begin[(size_t)(b * stride)], t1 = cta_begin[(size_t)std::min(grid, (b + 1) * stride)];
+            if (t0 < t1) cta_first_rank[(size_t)b] = cnt[tiles[(size_t)t0].file];
+            for (int t = t0; t < t1; t++) {
+                const uint32_t f = tiles[(size_t)t].file;
+                if (last_cta[f] != b) { cnt[f]++; last_cta[f] = b; }
+            }
+        }
+        for (uint32_t f = 0; f < f1; f++) nrows[f] = std::max(1u, cnt[f]);
+    }
+    file_row.assign((size_t)f1 + 1, 0u);
+    for (uint32_t f = 0; f < f1; f++) file_row[f + 1] = file_row[f] + nrows[f];
+}
+
 // FASTQ files [f0,f1): tiles of FQ_TILE_CHUNKS chunks in file order, contiguous tile-balanced CTA ranges, and the
 // tile range of every FASTQ file (for the per-file running newline count).
 constexpr uint32_t FQ_TILE_CHUNKS = 64;   // 32 KiB
@@ -168,8 +196,8 @@ int launch_fastq(const uint8_t *d_arena, int grid, uint32_t file_base, cudaStrea
         constexpr size_t smem = sizeof(uint32_t) << (2 * K);
         auto kern = count_fastq_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl,
-                                              (unsigned long long *)g.d_fwd - (size_t)file_base * ((size_t)1 << (2 * K)), g.d_fq_err);
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl, (unsigned long long *)g.d_fwd,
+                                              g.d_file_row, g.d_fq_err);
     } else {
         count_fastq_gmem_kernel<K, THREADS_GMEM><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl,
                                                                               (uint32_t *)g.d_fwd, file_base, g.d_fq_err);
@@ -198,13 +226,14 @@ int launch_fastq_k(int k, const uint8_t *d_arena, int grid, uint32_t file_base, 
 
 template <int LW>
 int launch_linegrid(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
-    using G = LineGrid<LW>;
+    using G = LineGeom<LW>;
     constexpr int NW = THREADS_LG / 32;
-    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * 2 * G::STAGE + 2 * NW * sizeof(uint64_t) + 2 * sizeof(unsigned long long) + 16;
-    auto kern = count_fasta_linegrid_kernel<LW, THREADS_LG>;
+    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    auto kern = count_fasta_lines_kernel<LW, THREADS_LG>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
-                                                             (unsigned long long *)g.d_fwd, g.d_scratch, CTAS_PER_SM, g.d_width_counts);
+                                                             (unsigned long long *)g.d_fwd, g.d_file_row, g.d_cta_first_rank, g.d_scratch,
+                                                             CTAS_PER_SM, g.d_width_counts);
     CK(cudaGetLastError());
     return KF_OK;
 }
@@ -216,11 +245,11 @@ int launch_smem(const uint8_t *d_arena, int grid, bool force_walker, cudaStream_
     if (force_walker) {
         auto kern = count_fasta_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM, true>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, g.d_file_P, g.d_width_counts);
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, g.d_file_row, g.d_file_P, g.d_width_counts);
     } else {
         auto kern = count_fasta_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM, false>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, g.d_file_P, g.d_width_counts);
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, g.d_file_row, g.d_file_P, g.d_width_counts);
     }
     CK(cudaGetLastError());
     return KF_OK;
@@ -266,8 +295,7 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     const int grid = smem_path ? g.sm_count * CTAS_PER_SM : g.sm_count * 4;
     int rc;
     if ((rc = ensure_canon(k)) != KF_OK) return rc;
-    const size_t fwd_bytes = (size_t)nf * NB * (smem_path ? sizeof(unsigned long long) : sizeof(uint32_t));
-    if ((rc = ensure(g.d_fwd, g.fwd_cap, fwd_bytes)) != KF_OK) return rc;
+    if (smem_path && f0 != 0) return KF_ERR_ARG;   // only the k >= 8 path is run in file batches
 
     // plan (cached on layout)
     bool hit = g.pc_k == k && g.pc_grid == grid && g.pc_f0 == f0 && g.pc_f1 == f1 &&
@@ -308,11 +336,23 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 CK(cudaMemcpy(g.d_fq_file_tile_begin, fq_ftb.data(), fq_ftb.size() * sizeof(int), cudaMemcpyHostToDevice));
             }
         }
+        if (smem_path) {
+            std::vector<uint32_t> file_row, cta_first_rank;
+            build_rows(tiles, cta_begin, grid, CTAS_PER_SM, f1, k == 7, file_row, cta_first_rank);
+            if ((rc = ensure(g.d_file_row, g.frow_cap, file_row.size() * sizeof(uint32_t))) != KF_OK) return rc;
+            if ((rc = ensure(g.d_cta_first_rank, g.cfr_cap, cta_first_rank.size() * sizeof(uint32_t))) != KF_OK) return rc;
+            CK(cudaMemcpy(g.d_file_row, file_row.data(), file_row.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(g.d_cta_first_rank, cta_first_rank.data(), cta_first_rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            g.pc_rows = file_row.back();
+        }
         g.pc_k = k; g.pc_grid = grid; g.pc_f0 = f0; g.pc_f1 = f1; g.pc_ntiles = (int)tiles.size();
         g.pc_offsets.assign(offsets + f0, offsets + f1);
         g.pc_lens.assign(lens + f0, lens + f1);
         g.pc_formats.assign(formats + f0, formats + f1);
     }
+    // forward-count workspace: u64 rows (see build_rows) for k <= 7, one u32 row per file for k >= 8
+    const size_t fwd_bytes = smem_path ? (size_t)g.pc_rows * NB * sizeof(unsigned long long) : (size_t)nf * NB * sizeof(uint32_t);
+    if ((rc = ensure(g.d_fwd, g.fwd_cap, fwd_bytes)) != KF_OK) return rc;
     CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));
     const bool force_walker = (flags & KF_FLAG_FORCE_WALKER) != 0;
     const bool use_lg = smem_path && k == 7 && !force_walker && !(flags & KF_FLAG_NO_LINEGRID);
@@ -320,7 +360,7 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         // line width per file (0 = generic kernel), then one line-grid launch per supported width
         CK(cudaMemsetAsync(g.d_width_counts, 0, 4 * sizeof(uint32_t), s));
-        probe_line_width_kernel<<<(f1 + 127) / 128, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, (int)f1,
+        probe_line_width_kernel<<<(f1 + 3) / 4, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, (int)f1,
                                                                 use_lg ? 0u : 1u, g.d_file_P, g.d_width_counts);
         CK(cudaGetLastError());
         g.last_launches++;
@@ -330,25 +370,14 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 if ((rc = ensure(g.d_scratch, g.scratch_cap, sc_bytes)) != KF_OK) return rc;
                 CK(cudaMemsetAsync(g.d_scratch, 0, g.scratch_cap, s));   // kept zero by the kernel afterwards
             }
-            void *saved = g.d_fwd;
-            g.d_fwd = (void *)((unsigned long long *)saved - (size_t)f0 * NB);
             rc = launch_linegrid<80>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<70>(d_arena, grid, s);
-            g.d_fwd = saved;
             if (rc != KF_OK) return rc;
             g.last_launches += 3;
         }
-        // file indices inside tiles are batch-global; forward rows are relative to f0
-        if (smem_path) {
-            // smem kernels index g_fwd by absolute file id: shift the base pointer
-            void *saved = g.d_fwd;
-            g.d_fwd = (void *)((unsigned long long *)saved - (size_t)f0 * NB);
-            rc = launch_count(k, d_arena, grid, force_walker, f0, s);
-            g.d_fwd = saved;
-        } else {
-            rc = launch_count(k, d_arena, grid, force_walker, f0, s);
-        }
+        // file indices inside tiles are batch-global; k >= 8 rows are relative to f0, k <= 7 rows come from d_file_row
+        rc = launch_count(k, d_arena, grid, force_walker, f0, s);
         if (rc != KF_OK) return rc;
         CK(cudaEventRecord(g.ev_k1, s));
         g.ev_valid = true;
@@ -368,10 +397,11 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     }
     if (smem_path)
         fold_normalize_kernel<unsigned long long><<<nf, 1024, 0, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
-                                                                       f0, d_counts, d_freq, d_feat, d_totals);
+                                                                       f0, (use_lg && g.pc_ntiles > 0) ? g.d_file_P : nullptr, g.d_file_row,
+                                                                       d_counts, d_freq, d_feat, d_totals);
     else
-        fold_normalize_kernel<uint32_t><<<nf, 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, d_counts,
-                                                             d_freq, d_feat, d_totals);
+        fold_normalize_kernel<uint32_t><<<nf, 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, nullptr, nullptr,
+                                                             d_counts, d_freq, d_feat, d_totals);
     CK(cudaGetLastError());
     g.last_launches++;
     return KF_OK;
@@ -446,7 +476,7 @@ int kf_shutdown(void) {
     cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
     cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals); cudaFree(g.d_seq); cudaFree(g.d_win_off); cudaFree(g.d_win_len);
     cudaFree(g.d_fq_tiles); cudaFree(g.d_fq_cta_begin); cudaFree(g.d_fq_tile_nl); cudaFree(g.d_fq_file_tile_begin); cudaFree(g.d_fq_err);
-    cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_scratch); cudaFree(g.d_width_counts);
+    cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_file_row); cudaFree(g.d_cta_first_rank); cudaFree(g.d_scratch); cudaFree(g.d_width_counts);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
     cudaEventDestroy(g.ev_k0); cudaEventDestroy(g.ev_k1);

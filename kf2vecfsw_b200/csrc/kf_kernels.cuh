@@ -336,7 +336,8 @@ template <int K, int THREADS, int MIN_CTAS, bool FORCE_WALKER, int PF = 3>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles,
                         const int *__restrict__ cta_begin, unsigned long long *__restrict__ g_fwd,
-                        const uint32_t *__restrict__ file_P, const uint32_t *__restrict__ width_counts) {
+                        const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ file_P,
+                        const uint32_t *__restrict__ width_counts) {
     KF_DYN_SMEM(uint32_t, hist);
     constexpr int NB = 1 << (2 * K);
     constexpr int NWARPS = THREADS / 32;
@@ -347,7 +348,7 @@ count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
     int cur_file = -1;
     auto flush = [&](int file) {
         __syncthreads();
-        unsigned long long *g = g_fwd + (size_t)file * NB;
+        unsigned long long *g = g_fwd + (size_t)file_row[file] * NB;   // the file's first row (rows are summed by the fold)
         for (int i = threadIdx.x; i < NB; i += THREADS) {
             const uint32_t v = hist[i];
             if (v) { atomicAdd(g + i, (unsigned long long)v); hist[i] = 0; }
@@ -395,7 +396,7 @@ count_fasta_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 }
 
 // ================================================================================================
-// Line-grid kernel (k = 7): fixed-width FASTA, one line per lane
+// Line kernel (k = 7): fixed-width FASTA, one line per lane -- shared pieces
 // ================================================================================================
 // Most FASTA is written with a fixed line width (NCBI 80, Ensembl 60, UCSC/others 70).  When a warp knows
 // the width LW it gives every lane one whole line: the '\n' sits at a compile-time byte, so nothing has to
@@ -405,12 +406,11 @@ count_fasta_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 // because their bank-conflict wavefronts are the first limiter of the generic kernel (profiles/r01_*).
 //
 //   staging  : per-warp buffer in shared memory filled by one TMA bulk copy (cp.async.bulk + mbarrier)
-//              of 32 lines; all lanes pull their line into registers, then the next copy is issued, so
-//              the copy of window i+1 overlaps the decode/count of window i.
+//              of 32 lines.
 //   histogram: 65,536 8-mer bins as 32,768 u32 words: word = v >> 1; the low half counts every pair of
 //              the word, the high half those with v & 1 (addend 1 or 0x10001).  A half can wrap, so at
 //              every flush the sum of the low halves is compared with the number of pairs issued; on a
-//              mismatch the CTA discards the histogram and recounts its tiles of that file with the
+//              mismatch the CTA discards the histogram and recounts its part of that file with the
 //              generic path into global memory (exact, slow, practically never taken).
 //   irregular: lines that break the grid (record ends, headers, other widths) and lanes with non-ACGT
 //              bytes go through the generic range processor / byte walker with a global-memory sink.
@@ -457,30 +457,20 @@ __device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32
 }
 #endif
 
-struct Gmem64Sink {   // rare paths of the line-grid kernel: a u64 row in global memory (+ "row is dirty" flag)
+struct Gmem64Sink {   // rare paths of the line kernel: a u64 row in global memory (+ "row is dirty" flag).  The row is in the
+                      // pair histogram's orientation (7-mer digits reversed: first base in bits 1:0), see the flush.
     unsigned long long *g;
     uint32_t *flag;
     __device__ __forceinline__ void operator()(uint32_t off) const {
-        atomicAdd(reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(g) + 2 * (size_t)off), 1ull);
+        const uint32_t r = __brev(off) >> 16;   // off = 4 * kmer, 14-bit kmer: bit-reverse, then swap the bits of each digit
+        const uint32_t idx = ((r & 0x2AAAu) >> 1) | ((r & 0x1555u) << 1);
+        atomicAdd(g + idx, 1ull);
         *flag = 1u;
 #ifdef KF_EMU_DEBUG
         extern std::atomic<long> g_dbg_emits;
         g_dbg_emits++;
 #endif
     }
-};
-
-template <int LW>
-struct LineGrid {
-    static_assert(LW % 2 == 0 && LW >= 32 && LW <= 120, "line width");
-    static constexpr int P = LW + 1;                 // bytes per line incl. '\n'
-    static constexpr int LA = 6;                     // look-ahead bases for the last pair
-    static constexpr int NBASES = LW + LA;
-    static constexpr int NWA = (P + LA + 3) / 4;     // aligned words a lane decodes
-    static constexpr int NPK = (NBASES + 15) / 16;   // packed registers
-    static constexpr int NPAIR = LW / 2;
-    static constexpr int NEED = 31 * P + 4 * NWA + 4;             // bytes a window must hold from its first line start
-    static constexpr int STAGE = ((NEED + 16 + 112 + 15) / 16) * 16;  // + alignment + slack to find the first line start
 };
 
 // First line start at or after byte q (a line start is file_begin or the byte after a '\n'); file_end if none.
@@ -516,77 +506,81 @@ __device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64
     fasta_process_range<K, false, 2>(src, c0, c1, file_c0, gs, lo, hi, true);
 }
 
-// Per-warp staging state: two buffers used strictly alternately (the window loop is unrolled by two, so which
-// buffer is "current" is a compile-time fact and nothing is shuffled between registers).
-struct StageBuf {
-    uint8_t *buf;
-    uint64_t *bar;
-};
+// ================================================================================================
+// The kernel.  Its first generation (static split of a file piece over the warps, double-buffered windows,
+// rare paths served from the staged window) was rebuilt around what its profile showed
+// (profiles/r01_*): 15 % of the warp samples sat in the per-file flush barrier (static split of a file piece
+// over the warps + rare-path detours of tens of microseconds), 10 % waited on global loads of those detours,
+// and the ALU pipe (LOP3/SHF/PRMT, 64 lanes/clk/SM) was the busiest unit while the FMA pipe idled.
+//   scheduling : a file piece is handed out to the warps in byte ranges ("units") from a shared cursor, large
+//                first and shrinking towards the end of the piece (guided self-scheduling); unit sizes are
+//                multiples of a window, anchored at the piece's first line start, so while the file stays on
+//                one grid phase every unit is a whole number of full windows.  The next unit is claimed, and the
+//                TMA copy of its first window started, before the current window is decoded.
+//   staging    : one buffer per warp; the lane's line is pulled into registers, then the buffer is re-armed for
+//                the next window at once (the copy overlaps the decode/count of this one).
+//   decode     : codes are packed LSB-first ((w & 0x06060606) * M: no shift), validity is checked with left
+//                shifts (IMAD, FMA pipe) and two LOP3 per word; k-mer indices are digit-reversed, undone at flush.
+//   rare paths : a line holding a non-ACGT byte (or whose 6 look-ahead bytes do) goes to the exact byte walker on
+//                global memory; a line that breaks the grid (short last line, header, other width) goes to the
+//                exact generic range processor up to the next sequence line, where the grid restarts.
 template <int LW>
-struct LgWarpStage {
-    StageBuf b0, b1;
-    uint32_t par0, par1;   // mbarrier phase parity to wait for next
+struct LineGeom {
+    static_assert(LW % 2 == 0 && LW >= 32 && LW <= 120, "line width");
+    static constexpr int P = LW + 1;                 // bytes per line incl. '\n'
+    static constexpr int LA = 6;                     // look-ahead bases (K - 1)
+    static constexpr int NBASES = LW + LA;
+    static constexpr int NWA = (P + LA + 3) / 4;     // aligned words a lane decodes
+    static constexpr int NPK = (NBASES + 15) / 16;   // packed registers
+    static constexpr int NPAIR = LW / 2;
+    static constexpr int WIN = 32 * P;               // bytes per full window
+    static constexpr int NEED = 31 * P + 4 * NWA + 4;                 // bytes a window must hold from its first line start
+    static constexpr int STAGE = ((NEED + 16 + 112 + 15) / 16) * 16;  // + alignment + slack to find a unit's first line start
 };
 
-// One window of 32 lines starting at line start B, staged in `cur` at byte offset woff.  On return B is the
-// next line start to process; if B < Xe its window is already on its way into `oth` (pend_oth) at offset woff.
+__device__ __forceinline__ uint32_t digit_rev7(uint32_t x) {   // reverse the seven 2-bit digits of a 14-bit value
+    const uint32_t r = __brev(x) >> 18;
+    return ((r & 0x2AAAu) >> 1) | ((r & 0x1555u) << 1);
+}
+
+// Decode the NWA aligned words of one line (+ look-ahead): returns non-zero iff a sequence byte is not A/C/G/T;
+// PK receives the 2-bit codes LSB-first (base j of the line at bits 2(j%16) of PK[j/16]; the '\n' is skipped).
 template <int LW>
-__device__ __forceinline__ void lg_window(const uint8_t *__restrict__ arena, uint64_t &B, uint32_t &woff, const uint64_t Xe,
-                                          const uint64_t F0, const uint64_t F1, const StageBuf cur, uint32_t &par_cur,
-                                          bool &pend_cur, const StageBuf oth, uint32_t &par_oth, bool &pend_oth,
-                                          uint32_t *hist16, Gmem64Sink gs, uint32_t &npairs, int &strikes) {
-    using G = LineGrid<LW>;
-    constexpr int K = 7;
-    const int lane = threadIdx.x & 31;
-    if (pend_cur) { stage_wait(cur.bar, par_cur); par_cur ^= 1u; pend_cur = false; }
-    // ---- pull my line (+ look-ahead) into registers, byte-aligned ----
-    const uint32_t o = woff + (uint32_t)lane * G::P;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(cur.buf) + (o >> 2);
-    const uint32_t ash = (o & 3u) * 8u;
-    uint32_t x[G::NWA + 1];
-#pragma unroll
-    for (int i = 0; i <= G::NWA; i++) x[i] = sw[i];
-    // next window into the other buffer while this one is decoded (all lanes finished with `oth` one window ago)
-    const uint64_t Bn = B + 32ull * G::P;
-    if (Bn < Xe) {
-        KF_SYNCWARP();
-        if (lane == 0) stage_issue(oth.buf, arena + (Bn & ~15ull), G::STAGE, oth.bar);
-        pend_oth = true;
-    }
-#pragma unroll
-    for (int i = 0; i < G::NWA; i++) x[i] = __funnelshift_r(x[i], x[i + 1], ash);
-    // ---- decode ----
-    uint32_t anyV = 0;
+__device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::NWA + 1], uint32_t (&PK)[LineGeom<LW>::NPK + 1]) {
+    using G = LineGeom<LW>;
+    constexpr uint32_t MPACK = (1u << 23) + (1u << 17) + (1u << 11) + (1u << 5);   // byte3 = c0 | c1<<2 | c2<<4 | c3<<6
+    uint32_t acc4 = 0, accC = 0;
     uint32_t pk[G::NWA];
 #pragma unroll
     for (int i = 0; i < G::NWA; i++) {
-        uint32_t V;
-        decode_word(x[i], pk[i], V);
-        // bytes of this word that are sequence: line bases [0,LW) and look-ahead bytes (LW, LW+LA]
-        uint32_t m = 0;
+        const uint32_t w = x[i];
+        pk[i] = (w & 0x06060606u) * MPACK;
+        // at bit 4 of every byte: bit4 == (bit2 & ~bit1)  [T is the only base with bit 4]  and  bit0 != bit4
+        const uint32_t b = w * 4u, c = w * 8u, d = w * 16u;
+        const uint32_t X = w ^ (b & ~c);
+        const uint32_t Y = X | ~(w ^ d);
+        const uint32_t Z = w ^ 0x40404040u;   // bits 7,6,3 must read 0,1,0
+        uint32_t m = 0;                       // bytes of this word that are sequence: [0,LW) and (LW, LW+LA]
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int byte = 4 * i + b;
-            if (byte < LW || (byte > LW && byte <= LW + G::LA)) m |= 0xFFu << (8 * b);
+        for (int bb = 0; bb < 4; bb++) {
+            const int byte = 4 * i + bb;
+            if (byte < LW || (byte > LW && byte <= LW + G::LA)) m |= 0xFFu << (8 * bb);
         }
-        if (m == 0xFFFFFFFFu) anyV |= V;
-        else if (m != 0) anyV |= V & m;
+        if (m == 0xFFFFFFFFu) { acc4 |= Y; accC |= Z; }
+        else if (m != 0) { acc4 |= Y & m; accC |= Z & m; }
     }
-    const bool nl_ok = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au;
-    // ---- pack: base stream = line bases then look-ahead bases (the '\n' byte is skipped statically) ----
-    uint32_t PK[G::NPK + 1];
     constexpr int NFULL = (LW / 4) / 4;   // groups of four full words -> one register, three byte permutes
 #pragma unroll
     for (int gq = 0; gq < NFULL; gq++) {
-        const uint32_t r1 = __byte_perm(pk[4 * gq + 3], pk[4 * gq + 2], 0x0073);
-        const uint32_t r2 = __byte_perm(pk[4 * gq + 1], pk[4 * gq], 0x0073);
+        const uint32_t r1 = __byte_perm(pk[4 * gq], pk[4 * gq + 1], 0x0073);       // [.., .., p1.b3, p0.b3]
+        const uint32_t r2 = __byte_perm(pk[4 * gq + 2], pk[4 * gq + 3], 0x0073);   // [.., .., p3.b3, p2.b3]
         PK[gq] = __byte_perm(r1, r2, 0x5410);
     }
 #pragma unroll
     for (int i = NFULL; i <= G::NPK; i++) PK[i] = 0;
 #pragma unroll
     for (int i = 4 * NFULL; i < G::NWA; i++) {
-        const uint32_t g8 = pk[i] >> 24;   // 4 codes, first in bits 7:6
+        const uint32_t g8 = pk[i] >> 24;   // 4 codes, byte 0's in bits 1:0
 #pragma unroll
         for (int seg = 0; seg < 2; seg++) {
             int b0 = (seg == 0) ? 0 : LW + 1 - 4 * i;                  // line bases | look-ahead bases
@@ -597,130 +591,217 @@ __device__ __forceinline__ void lg_window(const uint8_t *__restrict__ arena, uin
                 const int n = b1 - b0;
                 const int byte = 4 * i + b0;
                 const int pos = byte < LW ? byte : byte - 1;          // sequence bytes before this one
-                const uint32_t val = (g8 >> (8 - 2 * b1)) & ((1u << (2 * n)) - 1u);
-                const int sh = 32 - 2 * (pos & 15) - 2 * n;
-                if (sh >= 0) PK[pos >> 4] |= val << sh;
-                else { PK[pos >> 4] |= val >> (-sh); PK[(pos >> 4) + 1] |= val << (32 + sh); }
+                const uint32_t val = (g8 >> (2 * b0)) & ((1u << (2 * n)) - 1u);
+                const int sh = 2 * (pos & 15);
+                PK[pos >> 4] |= val << sh;
+                if (sh + 2 * n > 32) PK[(pos >> 4) + 1] |= val >> (32 - sh);
             }
         }
     }
-    // ---- who is on the grid: lines that start before Xe ----
-    const uint64_t rem = Xe - B;                                  // > 0
-    const uint32_t nact = rem >= 32ull * G::P ? 32u : (uint32_t)((rem + G::P - 1) / G::P);
-    const bool active = (uint32_t)lane < nact;
-    const unsigned bad = __ballot_sync(FULL, active && !nl_ok);
-    const uint32_t f = bad ? (uint32_t)(__ffs((int)bad) - 1) : nact;
-    const uint64_t wbase = B - woff;
-    if ((uint32_t)lane < f) {
-        if (anyV == 0) {
-            const uint32_t hbase = smem_addr(hist16);
+    return (acc4 & 0x10101010u) | (accC & 0xC8C8C8C8u);
+}
+
+// Count the NPAIR 8-mers ("pairs" of 7-mers) of one decoded line into the pair histogram.
+template <int LW>
+__device__ __forceinline__ void ln_count_pairs(const uint32_t (&PK)[LineGeom<LW>::NPK + 1], uint32_t *hist16, uint32_t hbase) {
+    using G = LineGeom<LW>;
 #pragma unroll
-            for (int i = 0; i < G::NPAIR; i++) {
-                const int r = (4 * i) & 31, q = (4 * i) >> 5;
-                const int sh = 47 - r;   // 8-mer v lands on bits 16:1
-                const uint32_t sv = (sh >= 32) ? (PK[q] >> (sh - 32)) : __funnelshift_r(PK[q + 1], PK[q], sh);
-                red_shared_add(hist16, hbase, sv & 0x1FFFCu, (sv & 2u) * 0x8000u + 1u);
-            }
-            npairs += G::NPAIR;
-        } else {
-            const WindowSrc wsrc{arena, cur.buf, wbase, (uint32_t)G::STAGE};
-            const uint64_t sl = B + (uint64_t)lane * G::P;
-            auto emit = [&](uint32_t xk) { gs(xk << 2); };
-            fasta_walk_lane<K>(wsrc, sl, sl + G::P, false, true, emit);
-        }
-    }
-    if (f == nact) {
-        B += (uint64_t)nact * G::P;   // == Bn when the window was full; >= Xe otherwise
-        woff = (uint32_t)(B & 15u);
-        strikes = 0;
-    } else {
-        // the line at sf breaks the grid: handle it and any header lines that follow from the staged window
-        const WindowSrc wsrc{arena, cur.buf, wbase, (uint32_t)G::STAGE};
-        const uint64_t sf = B + (uint64_t)f * G::P;
-        uint64_t q = fasta_line_start_at_or_after(wsrc, sf + 1, F0, F1, lane);
-        while (q < Xe && wsrc.byte(q) == (uint32_t)'>') q = fasta_line_start_at_or_after(wsrc, q + 1, F0, F1, lane);
-        lg_generic_region<K>(wsrc, sf, q, (uint32_t)(F0 / CHUNK), gs);
-        strikes = (f == 0) ? strikes + 1 : 0;
-        // the prefetch (if any) went to the wrong place: drain it and fetch the window of q instead
-        if (pend_oth) { stage_wait(oth.bar, par_oth); par_oth ^= 1u; pend_oth = false; }
-        B = q;
-        woff = (uint32_t)(q & 15u);
-        if (q < Xe && strikes < 4) {
-            KF_SYNCWARP();
-            if (lane == 0) stage_issue(oth.buf, arena + (q & ~15ull), G::STAGE, oth.bar);
-            pend_oth = true;
-        }
+    for (int i = 0; i < G::NPAIR; i++) {
+        const int r = (4 * i) & 31, q = (4 * i) >> 5;
+        uint32_t sv;   // the 8-mer v = bases 2i..2i+7 on bits 16:1
+        if (r == 0) sv = (q == 0) ? (PK[0] << 1) : __funnelshift_r(PK[q - 1], PK[q], 31);
+        else if (r - 1 + 17 <= 32) sv = PK[q] >> (r - 1);
+        else sv = __funnelshift_r(PK[q], PK[q + 1], r - 1);
+        red_shared_add(hist16, hbase, sv & 0x1FFFCu, (sv & 2u) * 0x8000u + 1u);
     }
 }
 
-// One warp over the lines that start in [X0, X1) of a file [F0, F1).
+struct LnUnit {      // a claimed byte range of the current file piece
+    uint64_t Us, Ue;   // lines that start in [Us, Ue) are this warp's
+};
+
+// One warp: claim units of the piece [A, Xe) of file [F0, F1) until none is left.  A is a line start.
+// s_cursor: shared byte cursor relative to A.  Returns the number of pairs issued through npairs.
 template <int LW>
-__device__ __forceinline__ void lg_process_range(const uint8_t *__restrict__ arena, uint64_t X0, uint64_t X1, uint64_t F0,
-                                                 uint64_t F1, LgWarpStage<LW> &S, uint32_t *hist16, Gmem64Sink gs,
-                                                 uint32_t &npairs) {
-    using G = LineGrid<LW>;
+__device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ arena, const uint64_t A, const uint64_t Xe,
+                                                 const uint64_t F0, const uint64_t F1, uint8_t *buf, uint64_t *bar,
+                                                 uint32_t &par, uint32_t *s_cursor, const uint32_t nwarps, uint32_t *hist16,
+                                                 Gmem64Sink gs, uint32_t &npairs) {
+    using G = LineGeom<LW>;
     constexpr int K = 7;
     const int lane = threadIdx.x & 31;
-    const uint64_t Xe = X1 < F1 ? X1 : F1;
-    if (X0 >= Xe) return;
-    bool pend0 = false, pend1 = false;
-    // ---- first line start at or after X0, found in the first staged window when possible ----
-    uint64_t B;
-    uint32_t woff;
-    {
-        const uint64_t base = (X0 <= F0) ? (F0 & ~15ull) : ((X0 - 1) & ~15ull);
+    const uint32_t hbase = smem_addr(hist16);
+    const GlobalSrc gsrc{arena};
+    auto emit = [&](uint32_t xk) { gs(xk << 2); };
+    if (A >= Xe) return;
+    const uint64_t plen = Xe - A;
+    // guided self-scheduling: a 1/(2 * nwarps) share of what is left, in whole windows, between 2 and 64 windows.
+    // The piece's last TAIL bytes are handed out FIRST (cursor range [0, TAIL)): the end of a file -- short last line,
+    // missing newline -- takes the slow exact path, which must not be what the other warps wait for at the barrier.
+    const uint64_t TAIL = plen > 4ull * G::WIN ? 2ull * G::WIN : 0ull;
+    const uint64_t body = plen - TAIL;   // cursor range [TAIL, TAIL + body) is the piece's [0, body)
+    auto claim = [&](LnUnit &U) -> bool {
+        uint32_t old = 0, sz = 0;
+        if (lane == 0) {
+            const uint64_t seen = *reinterpret_cast<volatile uint32_t *>(s_cursor);
+            if (TAIL && seen == 0) sz = (uint32_t)TAIL;
+            else {
+                const uint64_t left = seen < plen ? plen - seen : 0;
+                uint64_t nwin = left / ((uint64_t)G::WIN * 2u * nwarps);
+                nwin = nwin < 2 ? 2 : (nwin > 64 ? 64 : nwin);
+                sz = (uint32_t)(nwin * G::WIN);
+            }
+            old = atomicAdd(s_cursor, sz);
+        }
+        old = __shfl_sync(FULL, old, 0);
+        sz = __shfl_sync(FULL, sz, 0);
+        if ((uint64_t)old >= plen) return false;
+        if ((uint64_t)old < TAIL) {   // only the very first claim (old == 0, made while the cursor read 0, so sz == TAIL)
+            U.Us = A + body;
+            U.Ue = A + plen;
+            return true;
+        }
+        U.Us = A + (old - TAIL);
+        U.Ue = U.Us + sz;
+        if (U.Ue > A + body) U.Ue = A + body;
+        return true;
+    };
+    LnUnit U;
+    bool have = claim(U);
+    // window state: B = first line start of the window (unknown while `search`), woff = B - staged base
+    uint64_t B = 0, base = 0;
+    uint32_t woff = 0;
+    bool search = false;
+    int strikes = 0;
+    auto start_unit = [&](const LnUnit &u) {
+        search = u.Us > A;          // A itself is a line start; later units are found from the staged bytes
+        base = search ? ((u.Us - 1) & ~15ull) : (u.Us & ~15ull);
+        B = u.Us;
+        woff = (uint32_t)(B - base);
+        strikes = 0;
         KF_SYNCWARP();
-        if (lane == 0) stage_issue(S.b0.buf, arena + base, G::STAGE, S.b0.bar);
-        pend0 = true;
-        if (X0 <= F0) {
-            B = F0;
-        } else {
-            stage_wait(S.b0.bar, S.par0); S.par0 ^= 1u; pend0 = false;
-            const uint32_t o0 = (uint32_t)((X0 - 1) - base);
+        if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
+    };
+    auto refetch = [&](uint64_t at) {   // window whose first line starts at `at`
+        base = at & ~15ull;
+        B = at;
+        woff = (uint32_t)(at & 15u);
+        search = false;
+        KF_SYNCWARP();
+        if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
+    };
+    if (have) start_unit(U);
+    while (have) {
+        stage_wait(bar, par);
+        par ^= 1u;
+        if (search) {
+            // first line start at or after Us: the byte after the first '\n' in [Us-1, Us+95)
+            const uint32_t o0 = (uint32_t)((U.Us - 1) - base);
             int first = 3;
 #pragma unroll
             for (int j = 2; j >= 0; j--)
-                if (S.b0.buf[o0 + 3 * lane + j] == 0x0Au) first = j;
+                if (buf[o0 + 3 * lane + j] == 0x0Au) first = j;
             const unsigned Bm = __ballot_sync(FULL, first < 3);
             if (Bm) {
                 const int jl = __ffs((int)Bm) - 1;
                 const int fj = __shfl_sync(FULL, first, jl);
-                B = (X0 - 1) + 3ull * jl + (uint64_t)fj + 1;
-                if (B > F1) B = F1;
+                B = (U.Us - 1) + 3ull * jl + (uint64_t)fj + 1;
             } else {
-                B = fasta_line_start_at_or_after(GlobalSrc{arena}, X0 + 95, F0, F1, lane);
+                B = fasta_line_start_at_or_after(gsrc, U.Us + 95, F0, F1, lane);
+            }
+            if (B > F1) B = F1;
+            search = false;
+            if (B >= U.Ue) {   // no line starts inside this unit
+                have = claim(U);
+                if (have) start_unit(U);
+                continue;
+            }
+            woff = (uint32_t)(B - base);
+            if ((uint64_t)(B - base) + G::NEED > (uint64_t)G::STAGE) { refetch(B); continue; }
+        }
+        // ---- pull my line (+ look-ahead) into registers, byte-aligned ----
+        const uint32_t o = woff + (uint32_t)lane * G::P;
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(buf) + (o >> 2);
+        const uint32_t ash = (o & 3u) * 8u;
+        uint32_t x[G::NWA + 1];
+#pragma unroll
+        for (int i = 0; i <= G::NWA; i++) x[i] = sw[i];
+#pragma unroll
+        for (int i = 0; i < G::NWA; i++) x[i] = __funnelshift_r(x[i], x[i + 1], ash);
+        const bool nl_ok = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au;
+        // ---- who is on the grid: lines that start before the unit's end ----
+        const uint64_t rem = U.Ue - B;                                  // > 0
+        const uint32_t nact = rem >= (uint64_t)G::WIN ? 32u : (uint32_t)((rem + G::P - 1) / G::P);
+        const bool active = (uint32_t)lane < nact;
+        const unsigned bad = __ballot_sync(FULL, active && !nl_ok);
+        const uint32_t f = bad ? (uint32_t)(__ffs((int)bad) - 1) : nact;
+        // ---- where the next window is; get its copy going before the decode ----
+        const uint64_t sf = B + (uint64_t)f * G::P;     // first byte not covered by lanes [0, f)
+        uint64_t q = sf;                                // next line start to process on the grid
+        if (f < nact) {
+            // the line at sf breaks the grid: skip it and any header lines that follow (found in the staged window
+            // when they lie inside it); [sf, q) goes to the exact generic path below
+            const WindowSrc wsrc{arena, buf, base, (uint32_t)G::STAGE};
+            q = fasta_line_start_at_or_after(wsrc, sf + 1, F0, F1, lane);
+            while (q < U.Ue && wsrc.byte(q) == (uint32_t)'>') q = fasta_line_start_at_or_after(wsrc, q + 1, F0, F1, lane);
+            strikes = (f == 0) ? strikes + 1 : 0;
+        } else {
+            strikes = 0;
+        }
+        const uint64_t curB = B;
+        uint64_t gen_lo = sf, gen_hi = q;               // exact generic region (empty when the window was clean)
+        LnUnit Un = U;
+        bool have_n = true;
+        if (q < U.Ue && strikes >= 4) {
+            // this stretch is not on the grid (another width, blank lines ...): finish the unit generically
+            gen_hi = fasta_line_start_at_or_after(gsrc, U.Ue, F0, F1, lane);
+            q = U.Ue;
+        }
+        if (q < U.Ue) refetch(q);
+        else {
+            have_n = claim(Un);
+            if (have_n) start_unit(Un);
+        }
+        // ---- decode + count the lanes on the grid ----
+        if ((uint32_t)lane < f) {
+            uint32_t PK[G::NPK + 1];
+            const uint32_t anyV = ln_decode<LW>(x, PK);
+            if (anyV == 0) {
+                ln_count_pairs<LW>(PK, hist16, hbase);
+                npairs += G::NPAIR;
+            } else {
+                const uint64_t sl = curB + (uint64_t)lane * G::P;
+                fasta_walk_lane<K>(gsrc, sl, sl + G::P, false, true, emit);
             }
         }
-        woff = (uint32_t)(B - base);
-        if (B < Xe && (uint64_t)woff + G::NEED > (uint64_t)G::STAGE) {   // line start beyond the slack: fetch its own window
-            KF_SYNCWARP();
-            if (lane == 0) stage_issue(S.b0.buf, arena + (B & ~15ull), G::STAGE, S.b0.bar);
-            pend0 = true;
-            woff = (uint32_t)(B & 15u);
-        }
-    }
-    int strikes = 0;
-    while (B < Xe && strikes < 4) {
-        lg_window<LW>(arena, B, woff, Xe, F0, F1, S.b0, S.par0, pend0, S.b1, S.par1, pend1, hist16, gs, npairs, strikes);
-        if (!(B < Xe && strikes < 4)) break;
-        lg_window<LW>(arena, B, woff, Xe, F0, F1, S.b1, S.par1, pend1, S.b0, S.par0, pend0, hist16, gs, npairs, strikes);
-    }
-    if (pend0) { stage_wait(S.b0.bar, S.par0); S.par0 ^= 1u; }
-    if (pend1) { stage_wait(S.b1.bar, S.par1); S.par1 ^= 1u; }
-    if (B < Xe) {   // this stretch is not on the grid: finish the range generically
-        const uint64_t E = fasta_line_start_at_or_after(GlobalSrc{arena}, X1, F0, F1, lane);
-        lg_generic_region<K>(GlobalSrc{arena}, B, E, (uint32_t)(F0 / CHUNK), gs);
+        if (gen_lo < gen_hi) lg_generic_region<K>(gsrc, gen_lo, gen_hi, (uint32_t)(F0 / CHUNK), gs);
+        U = Un;
+        have = have_n;
     }
 }
 
+#ifdef KF_PIECE_TIMING
+// developer instrumentation (tools/ubench only): SM-clock sums over all warps / CTAs
+// [0] warp cycles claiming+processing units  [1] warp cycles waiting at the end-of-piece barrier  [2] CTA cycles in the flush
+// [3] pieces  [4] CTA cycles total  [5] CTA cycles anchor search + cursor reset  [6] warp cycles in the fold loop
+// ([1] = arrival at the flush until the checksum is known: barrier wait + low-half sums; [2] = zeroing + last barrier)
+__device__ unsigned long long g_piece_timing[8];
+#define KF_T(var) const long long var = clock64()
+#define KF_TADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_piece_timing[i], (unsigned long long)(v)); } while (0)
+#else
+#define KF_T(var)
+#define KF_TADD(i, v)
+#endif
+
 template <int LW, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-count_fasta_linegrid_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
-                            const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
-                            const uint64_t *__restrict__ file_len, unsigned long long *__restrict__ g_fwd,
-                            unsigned long long *__restrict__ g_scratch, int cta_stride,
-                            const uint32_t *__restrict__ width_counts) {
-    using G = LineGrid<LW>;
+count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
+                         const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
+                         const uint64_t *__restrict__ file_len, unsigned long long *__restrict__ g_fwd,
+                         const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ cta_first_rank,
+                         unsigned long long *__restrict__ g_scratch, int cta_stride,
+                         const uint32_t *__restrict__ width_counts) {
+    using G = LineGeom<LW>;
     if (width_counts[(LW - 50) / 10] == 0) return;   // no file of this width in the batch (uniform exit)
     constexpr int NWARPS = THREADS / 32;
     constexpr int NWORDS = 32768;
@@ -728,95 +809,118 @@ count_fasta_linegrid_kernel(const uint8_t *__restrict__ arena, const Tile *__res
     KF_DYN_SMEM(uint32_t, smem);
     uint32_t *hist16 = smem;
     uint8_t *stage_base = reinterpret_cast<uint8_t *>(smem + NWORDS);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_base + (size_t)NWARPS * 2 * G::STAGE);
-    unsigned long long *s_acc = reinterpret_cast<unsigned long long *>(bars + 2 * NWARPS);   // [0] pairs issued, [1] low-half sum
-    uint32_t *s_flag = reinterpret_cast<uint32_t *>(s_acc + 2);                              // rare-path row is non-zero
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stage_base + (size_t)NWARPS * G::STAGE);
+    uint32_t *s_part = reinterpret_cast<uint32_t *>(bars + NWARPS);   // [0..NWARPS) pairs issued, [NWARPS..2 NWARPS) low-half sums
+    uint32_t *s_flag = s_part + 2 * NWARPS;                           // [0] rare-path row is non-zero, [1] sink of the recount
+    uint32_t *s_cursor = s_flag + 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NWORDS; i += THREADS) hist16[i] = 0;
-    if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
-    if (threadIdx.x == 0) *s_flag = 0;
-    LgWarpStage<LW> S;
-    S.b0 = StageBuf{stage_base + (size_t)(2 * warp) * G::STAGE, bars + 2 * warp};
-    S.b1 = StageBuf{stage_base + (size_t)(2 * warp + 1) * G::STAGE, bars + 2 * warp + 1};
-    S.par0 = S.par1 = 0u;
-    if (lane == 0) { stage_bar_init(S.b0.bar); stage_bar_init(S.b1.bar); }
+    if (threadIdx.x == 0) { s_flag[0] = 0; *s_cursor = 0; }
+    uint8_t *buf = stage_base + (size_t)warp * G::STAGE;
+    uint64_t *bar = bars + warp;
+    uint32_t par = 0;
+    if (lane == 0) stage_bar_init(bar);
     __syncthreads();
     // rare-path k-mers (walker, off-grid lines) go to this CTA's private u64 row so that a failed checksum can
     // discard them together with the pair histogram
     unsigned long long *scratch = g_scratch + (size_t)blockIdx.x * NB7;
     uint32_t npairs = 0;
-    int cur_file = -1, first_tile = 0;
+    int cur_file = -1;
+    uint64_t file_lo = 0, file_hi = 0;   // byte range of cur_file this CTA has processed (for the exact recount)
+    const int tb0 = cta_begin[blockIdx.x * cta_stride], tb1 = cta_begin[(blockIdx.x + 1) * cta_stride];
+    const int first_file = tb0 < tb1 ? (int)tiles[tb0].file : -1;
 
-    auto warp_range = [&](uint32_t first_chunk, uint32_t n_chunks, uint64_t &X0, uint64_t &X1) {
-        const uint32_t cpw = (n_chunks + NWARPS - 1) / NWARPS;
-        const uint32_t c0 = first_chunk + (uint32_t)warp * cpw;
-        const uint32_t cend = first_chunk + n_chunks;
-        const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-        X0 = (uint64_t)c0 * CHUNK;
-        X1 = (uint64_t)c1 * CHUNK;
-        return c0 < c1;
-    };
-    auto flush = [&](int file, int t_first, int t_last) {
-        atomicAdd(s_acc, (unsigned long long)npairs);
+    auto flush = [&](int file) {
+        // checksum: pairs issued vs the sum of the low halves, through per-warp partial sums (no contended atomics)
+        uint32_t np = npairs;
         npairs = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync(FULL, np, o);
+        if (lane == 0) s_part[warp] = np;
+        KF_T(tw0);
         __syncthreads();
-        unsigned long long low = 0;
+        uint32_t low = 0;
         for (int i = threadIdx.x; i < NWORDS; i += THREADS) low += hist16[i] & 0xFFFFu;
-        atomicAdd(s_acc + 1, low);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) low += __shfl_xor_sync(FULL, low, o);
+        if (lane == 0) s_part[NWARPS + warp] = low;
         __syncthreads();
-        const bool ok = s_acc[0] == s_acc[1];
-        const bool rare = *s_flag != 0;
-        unsigned long long *g = g_fwd + (size_t)file * NB7;
+        unsigned long long tp = 0, tl = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; }
+        const bool ok = tp == tl;
+        const bool rare = s_flag[0] != 0;
+        // every CTA that holds a piece of the file owns one row of it (file_row[file] + its rank among those CTAs; the
+        // fold kernel sums the rows), so the row is WRITTEN, every bin, with plain 16-byte stores: no global atomics.
+        // Only the first file of a CTA's tile range can have begun in an earlier CTA: its rank comes from the host.
+        const uint32_t rank = (file == first_file) ? cta_first_rank[blockIdx.x] : 0u;
+        unsigned long long *g = g_fwd + ((size_t)file_row[file] + rank) * NB7;
+#ifdef KF_PIECE_TIMING
+        long long tw1 = clock64();
+        if (tp == 0xFFFFFFFFFFFFull) tw1 = 0;   // depends on the shared reads above: taken after the barrier released
+        KF_TADD(1, tw1 - tw0);
+#endif
         if (rare) __threadfence();
-        if (ok) {
-            // 7-mer x = prefix of the 8-mers 4x..4x+3 (words 2x, 2x+1: sum of the low halves) and suffix of the
-            // 8-mers a*16384 + x (word a*8192 + (x >> 1); odd x in the high half, even x = low - high)
+        // xk: 7-mer with its digits reversed (first base in bits 1:0) -- the orientation of the pair histogram, of the
+        // rare-path row and of this file's rows in g_fwd (the fold kernel undoes it).  xk is the first 7-mer of the
+        // 8-mers xk + a*16384 (word a*8192 + (xk >> 1); odd xk in the high half, even xk = low - high) and the second
+        // 7-mer of the 8-mers 4xk .. 4xk+3 (words 2xk, 2xk+1: sum of the low halves).  One thread: xk = 2j, 2j+1.
 #pragma unroll 4
-            for (int xk = threadIdx.x; xk < NB7; xk += THREADS) {
-                const uint2 pw = *reinterpret_cast<const uint2 *>(hist16 + 2 * xk);
-                unsigned long long c = (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu);
+        for (int j = threadIdx.x; j < NB7 / 2; j += THREADS) {
+            unsigned long long c0 = 0, c1 = 0;
+            if (ok) {
+                const uint4 pw = *reinterpret_cast<const uint4 *>(hist16 + 4 * j);
+                c0 = (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu);
+                c1 = (pw.z & 0xFFFFu) + (pw.w & 0xFFFFu);
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
-                    const uint32_t w = hist16[a * 8192 + (xk >> 1)];
-                    c += (xk & 1) ? (w >> 16) : ((w & 0xFFFFu) - (w >> 16));
+                    const uint32_t w = hist16[a * 8192 + j];
+                    c0 += (w & 0xFFFFu) - (w >> 16);
+                    c1 += w >> 16;
                 }
-                if (rare) c += KF_LDCG(scratch + xk);
-                if (c) atomicAdd(g + xk, c);
             }
+            if (rare) {
+                const ulonglong2 v = KF_LDCG(reinterpret_cast<const ulonglong2 *>(scratch) + j);
+                if (v.x | v.y) reinterpret_cast<ulonglong2 *>(scratch)[j] = make_ulonglong2(0ull, 0ull);
+                if (ok) { c0 += v.x; c1 += v.y; }
+            }
+            reinterpret_cast<ulonglong2 *>(g)[j] = make_ulonglong2(c0, c1);
         }
-        if (rare)
-            for (int xk = threadIdx.x; xk < NB7; xk += THREADS) scratch[xk] = 0;
+#ifdef KF_PIECE_TIMING
+        const long long tw2 = clock64();
+        KF_TADD(6, tw2 - tw1);
+#endif
         __syncthreads();
         uint4 *h4 = reinterpret_cast<uint4 *>(hist16);
         for (int i = threadIdx.x; i < NWORDS / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x < 2) s_acc[threadIdx.x] = 0;
-        if (threadIdx.x == 0) *s_flag = 0;
+        if (threadIdx.x == 0) s_flag[0] = 0;
         __syncthreads();
+#ifdef KF_PIECE_TIMING
+        { long long tw3 = clock64(); if (s_flag[0] == 12345u) tw3 = 0; KF_TADD(2, tw3 - tw2); if (threadIdx.x == 0) atomicAdd(&g_piece_timing[3], 1ull); }
+#endif
         if (!ok) {
-            // a 16-bit half wrapped: recount this CTA's tiles of the file exactly, straight into global memory
+            // a 16-bit half wrapped: recount this CTA's part of the file exactly, straight into its (zeroed) row
+            __threadfence();
             Gmem64Sink gs;
             gs.g = g;
             gs.flag = s_flag + 1;   // nobody reads this one
             const uint64_t F0 = file_off[file], F1 = F0 + file_len[file];
             const GlobalSrc src{arena};
-            for (int t = t_first; t <= t_last; ++t) {
-                const Tile T = tiles[t];
-                if ((int)T.file != file) continue;
-                uint64_t X0, X1;
-                if (!warp_range(T.first_chunk, T.n_chunks, X0, X1)) continue;
-                const uint64_t lo = fasta_line_start_at_or_after(src, X0, F0, F1, lane);
-                const uint64_t hi = fasta_line_start_at_or_after(src, X1, F0, F1, lane);
-                lg_generic_region<7>(src, lo, hi, T.file_chunk0, gs);
+            const uint64_t lo_b = file_lo > F0 ? file_lo : F0, hi_b = file_hi < F1 ? file_hi : F1;
+            const uint64_t span = (hi_b - lo_b + NWARPS - 1) / NWARPS;
+            const uint64_t a0 = lo_b + (uint64_t)warp * span, a1 = (a0 + span < hi_b) ? a0 + span : hi_b;
+            if (a0 < hi_b) {
+                const uint64_t lo = fasta_line_start_at_or_after(src, a0, F0, F1, lane);
+                const uint64_t hi = (a1 >= hi_b && hi_b >= F1) ? F1 : fasta_line_start_at_or_after(src, a1, F0, F1, lane);
+                lg_generic_region<7>(src, lo, hi, (uint32_t)(F0 / CHUNK), gs);
             }
         }
     };
 
     // the tile plan is cut for the generic kernel's grid; this CTA takes cta_stride consecutive shares of it.
-    // Consecutive tiles of one file are contiguous in the arena: they are processed as ONE range split over
-    // the warps, so the per-range costs (first line start, first un-prefetched window, ragged last window)
-    // are paid once per file piece instead of once per 512 KiB tile.
+    // Consecutive tiles of one file are contiguous in the arena: they are processed as ONE piece.
     const int t1 = cta_begin[(blockIdx.x + 1) * cta_stride];
-    int last_tile = -1;
+    KF_T(tk0);
     for (int t = cta_begin[blockIdx.x * cta_stride]; t < t1;) {
         const Tile T = tiles[t];
         if (file_P[T.file] != (uint32_t)G::P) { ++t; continue; }
@@ -826,57 +930,95 @@ count_fasta_linegrid_kernel(const uint8_t *__restrict__ arena, const Tile *__res
             n_chunks += tiles[te].n_chunks;
             ++te;
         }
+        const uint64_t X0 = (uint64_t)T.first_chunk * CHUNK, X1 = X0 + (uint64_t)n_chunks * CHUNK;
         if ((int)T.file != cur_file) {
-            if (cur_file >= 0) flush(cur_file, first_tile, last_tile);
+            if (cur_file >= 0) flush(cur_file);
             cur_file = (int)T.file;
-            first_tile = t;
+            file_lo = X0;
+        } else {
+            __syncthreads();   // every warp is done with the previous piece (the cursor is about to be reset)
         }
-        last_tile = te - 1;
-        uint64_t X0, X1;
-        if (warp_range(T.first_chunk, n_chunks, X0, X1)) {
-            Gmem64Sink gs;
-            gs.g = scratch;
-            gs.flag = s_flag;
-            const uint64_t F0 = file_off[T.file];
-            lg_process_range<LW>(arena, X0, X1, F0, F0 + file_len[T.file], S, hist16, gs, npairs);
-        }
+        file_hi = X1;
+        const uint64_t F0 = file_off[T.file], F1 = F0 + file_len[T.file];
+        const uint64_t Xe = X1 < F1 ? X1 : F1;
+        KF_T(ta0);
+        if (threadIdx.x == 0) *s_cursor = 0;
+        // every warp finds the piece's anchor (its first line start) by itself: same loads, served by L1 after the first
+        const uint64_t A = fasta_line_start_at_or_after(GlobalSrc{arena}, X0, F0, F1, lane);
+        __syncthreads();
+        KF_T(ta1);
+        if (threadIdx.x == 0) KF_TADD(5, ta1 - ta0);
+        Gmem64Sink gs;
+        gs.g = scratch;
+        gs.flag = s_flag;
+        ln_process_piece<LW>(arena, A, Xe, F0, F1, buf, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
+        KF_T(ta2);
+        KF_TADD(0, ta2 - ta1);
         t = te;
     }
-    if (cur_file >= 0) flush(cur_file, first_tile, last_tile);
+    if (cur_file >= 0) flush(cur_file);
+#ifdef KF_PIECE_TIMING
+    if (threadIdx.x == 0) atomicAdd(&g_piece_timing[4], (unsigned long long)(clock64() - tk0));
+#endif
+}
+
+// byte-mask helpers (also used by the FASTQ kernels below)
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every byte of v that is non-zero
+    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t movemask4(uint32_t f) {       // f has 0x80 flags; -> 4-bit mask, byte 0 in bit 0
+    return ((f >> 7) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t newline_mask16(const uint4 w) {
+    const uint32_t n0 = ~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n1 = ~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n2 = ~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n3 = ~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u;
+    return movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12);
 }
 
 // Line width of each FASTA file, judged from its first lines: P = LW + 1 if the three lines after the
-// header are LW bases wide (LW one of 60/70/80), else 0 (generic kernel).  One thread per file.
-__global__ void probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
-                                        const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
-                                        uint32_t force_generic, uint32_t *__restrict__ file_P,
-                                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80 */) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// header are LW bases wide (LW one of 60/70/80), else 0 (generic kernel).  One warp per file: 512-byte chunks,
+// newline masks per lane, the first four '\n' positions picked out of the ballots.
+__global__ void __launch_bounds__(128)
+probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
+                        const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
+                        uint32_t force_generic, uint32_t *__restrict__ file_P,
+                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80 */) {
+    const int lane = threadIdx.x & 31;
+    const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (f >= n) return;
     uint32_t P = 0;
     if (!force_generic && formats[f] == (uint8_t)'>') {
-        const uint8_t *d = arena + file_off[f];
-        const uint64_t L = file_len[f];
-        uint64_t p = 0;
-        const uint64_t cap = L < 65536 ? L : 65536;
-        while (p < cap && d[p] != 0x0Au) p++;
-        if (p < cap) {
-            p++;
-            uint32_t w0 = 0;
-            bool ok = true;
-            for (int line = 0; line < 3 && ok; line++) {
-                uint32_t w = 0;
-                while (p + w < L && w <= 128 && d[p + w] != 0x0Au) w++;
-                if (p + w >= L || w > 128) { ok = false; break; }
-                if (line == 0) w0 = w;
-                else if (w != w0) ok = false;
-                p += w + 1;
+        const uint64_t F0 = file_off[f], L = file_len[f];
+        const uint64_t nchunks = (L + CHUNK - 1) / CHUNK < 128 ? (L + CHUNK - 1) / CHUNK : 128;   // look at most 64 KiB in
+        uint64_t nlpos[4];
+        int found = 0;
+        for (uint64_t c = 0; c < nchunks && found < 4; c++) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(arena + F0) + c * 32 + lane);
+            const uint64_t pb = c * CHUNK + (uint64_t)lane * 16;   // offset in the file
+            uint32_t m = newline_mask16(w);
+            if (pb + 16 > L) m &= pb >= L ? 0u : ((1u << (uint32_t)(L - pb)) - 1u);
+            unsigned Bm = __ballot_sync(FULL, m != 0);
+            while (Bm && found < 4) {
+                const int j = __ffs((int)Bm) - 1;
+                Bm &= Bm - 1;
+                uint32_t mj = __shfl_sync(FULL, m, j);
+                while (mj && found < 4) {
+                    nlpos[found++] = c * CHUNK + (uint64_t)j * 16 + (uint32_t)(__ffs((int)mj) - 1);
+                    mj &= mj - 1;
+                }
             }
-            if (ok && (w0 == 60 || w0 == 70 || w0 == 80)) P = w0 + 1;
+        }
+        if (found == 4) {
+            const uint64_t w0 = nlpos[1] - nlpos[0] - 1, w1 = nlpos[2] - nlpos[1] - 1, w2 = nlpos[3] - nlpos[2] - 1;
+            if (w0 == w1 && w1 == w2 && (w0 == 60 || w0 == 70 || w0 == 80)) P = (uint32_t)w0 + 1;
         }
     }
-    file_P[f] = P;
-    atomicAdd(width_counts + (P ? (P - 51) / 10 : 0), 1u);
+    if (lane == 0) {
+        file_P[f] = P;
+        atomicAdd(width_counts + (P ? (P - 51) / 10 : 0), 1u);
+    }
 }
 
 // ================================================================================================
@@ -896,20 +1038,6 @@ __global__ void probe_line_width_kernel(const uint8_t *__restrict__ arena, const
 // from the base stream and every lane takes the same branch-free path.
 // The layout is checked as a side effect: the line after every sequence line must begin with '+'; the lowest
 // offending byte offset per file lands in fq_err (the host maps it to KF_ERR_FASTQ).
-
-__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every byte of v that is non-zero
-    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t movemask4(uint32_t f) {       // f has 0x80 flags; -> 4-bit mask, byte 0 in bit 0
-    return ((f >> 7) * 0x01020408u) >> 24;
-}
-__device__ __forceinline__ uint32_t newline_mask16(const uint4 w) {
-    const uint32_t n0 = ~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u;
-    const uint32_t n1 = ~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u;
-    const uint32_t n2 = ~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u;
-    const uint32_t n3 = ~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u;
-    return movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12);
-}
 
 struct FqLane {
     uint32_t bits;    // 16 bases, 2 bits each, first base in bits 31:30 (garbage where the byte is not a base)
@@ -1078,7 +1206,7 @@ template <int K, int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
                         const uint32_t *__restrict__ tile_type, unsigned long long *__restrict__ g_fwd,
-                        unsigned long long *__restrict__ fq_err) {
+                        const uint32_t *__restrict__ file_row, unsigned long long *__restrict__ fq_err) {
     KF_DYN_SMEM(uint32_t, hist);
     constexpr int NB = 1 << (2 * K);
     constexpr int NWARPS = THREADS / 32;
@@ -1096,7 +1224,7 @@ count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
             fastq_process_range<K, 3>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[tt], emit, fq_err + file);
         }
         __syncthreads();
-        unsigned long long *g = g_fwd + (size_t)file * NB;
+        unsigned long long *g = g_fwd + (size_t)file_row[file] * NB;
         for (int i = threadIdx.x; i < NB; i += THREADS) {
             const uint32_t v = hist[i];
             if (v) { atomicAdd(g + i, (unsigned long long)v); hist[i] = 0; }
@@ -1155,20 +1283,34 @@ __device__ __forceinline__ uint32_t std_to_gray(uint32_t x) { return x ^ ((x >> 
 template <typename FwdT>
 __global__ void __launch_bounds__(1024)
 fold_normalize_kernel(const FwdT *__restrict__ g_fwd, const uint32_t *__restrict__ canon, int k, long long V,
-                      uint32_t flags, uint32_t file_base, unsigned long long *__restrict__ counts,
+                      uint32_t flags, uint32_t file_base, const uint32_t *__restrict__ file_P,
+                      const uint32_t *__restrict__ file_row, unsigned long long *__restrict__ counts,
                       double *__restrict__ freq, float *__restrict__ feat,
                       unsigned long long *__restrict__ totals) {
     const size_t NB = (size_t)1 << (2 * k);
     const uint32_t file = blockIdx.x;
-    const FwdT *g = g_fwd + (size_t)file * NB;
+    // rows of this file: one, or (k = 7 line kernel) one per CTA that held a piece of it
+    const uint32_t row0 = file_row ? file_row[file + file_base] : file;
+    const uint32_t nrows = file_row ? file_row[file + file_base + 1] - row0 : 1u;
+    const FwdT *g = g_fwd + (size_t)row0 * NB;
     const size_t orow = (size_t)(file + file_base) * (size_t)V;
     __shared__ unsigned long long red[32];
     __shared__ unsigned long long s_total;
+    // rows written by the line kernel (k = 7, file_P != 0) hold the 7-mers with their digits reversed
+    const bool rev = file_P != nullptr && file_P[file + file_base] != 0;
+    auto row_index = [&](uint32_t m) -> uint32_t {
+        const uint32_t gcode = std_to_gray(m);
+        return rev ? digit_rev7(gcode) : gcode;
+    };
     auto canon_count = [&](long long i) -> unsigned long long {
         const uint32_t m = canon[i];
         const uint32_t r = revcomp_std(m, k);
-        unsigned long long c = (unsigned long long)g[std_to_gray(m)];
-        if (r != m) c += (unsigned long long)g[std_to_gray(r)];
+        const uint32_t i0 = row_index(m), i1 = row_index(r);
+        unsigned long long c = 0;
+        for (uint32_t rr = 0; rr < nrows; rr++) {
+            c += (unsigned long long)g[(size_t)rr * NB + i0];
+            if (r != m) c += (unsigned long long)g[(size_t)rr * NB + i1];
+        }
         return c;
     };
     unsigned long long local = 0;

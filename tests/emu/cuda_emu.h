@@ -5,6 +5,7 @@
 // It is never part of the product: libkfcount.so is built by nvcc from the same header without KF_EMU.
 #pragma once
 #include <pthread.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <string.h>
 #include <atomic>
@@ -22,6 +23,8 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };
+struct ulonglong2 { unsigned long long x, y; };
+inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{a, b}; }
 inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 struct dim3 { unsigned x = 1, y = 1, z = 1; };
 

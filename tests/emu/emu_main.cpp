@@ -37,21 +37,21 @@ using namespace kf;
 
 template <int K, int THREADS>
 static void run(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
-                bool fw, unsigned long long *fwd, const uint32_t *file_P, const uint32_t *wc) {
+                bool fw, unsigned long long *fwd, const uint32_t *file_row, const uint32_t *file_P, const uint32_t *wc) {
     size_t smem = sizeof(uint32_t) << (2 * K);
-    if (fw) emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, true>(arena, tiles.data(), cta_begin.data(), fwd, file_P, wc); });
-    else    emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, false>(arena, tiles.data(), cta_begin.data(), fwd, file_P, wc); });
+    if (fw) emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, true>(arena, tiles.data(), cta_begin.data(), fwd, file_row, file_P, wc); });
+    else    emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, false>(arena, tiles.data(), cta_begin.data(), fwd, file_row, file_P, wc); });
 }
 
 template <int LW, int THREADS>
 static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
                    const uint32_t *file_P, const uint64_t *off, const uint64_t *len, unsigned long long *fwd,
-                   unsigned long long *scratch, const uint32_t *wc) {
-    using G = LineGrid<LW>;
+                   const uint32_t *file_row, const uint32_t *file_first_cta, unsigned long long *scratch, const uint32_t *wc) {
+    using G = LineGeom<LW>;
     constexpr int NW = THREADS / 32;
-    size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * 2 * G::STAGE + 2 * NW * sizeof(uint64_t) + 2 * sizeof(unsigned long long) + 16;
+    size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
     emu::launch(grid, THREADS, smem, [&]() {
-        count_fasta_linegrid_kernel<LW, THREADS>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, scratch, 1, wc);
+        count_fasta_lines_kernel<LW, THREADS>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, scratch, 1, wc);
     });
 }
 
@@ -96,30 +96,44 @@ int main(int argc, char **argv) {
     }
     while (cta < grid) { cta++; cta_begin[cta] = (int)tiles.size(); }
     size_t NB = (size_t)1 << (2 * k);
-    std::vector<unsigned long long> fwd((size_t)n * NB, 0);
+    // rows: same rule as kf_api.cu:build_rows with stride 1 (every emulated CTA is a line-kernel CTA)
+    std::vector<uint32_t> file_row(n + 1, 0), file_first_cta(grid, 0);   // (second one: rank of each CTA for its first file)
+    {
+        std::vector<uint32_t> cnt(n, 0); std::vector<int> last(n, -1);
+        if (k == 7)
+            for (int b = 0; b < grid; b++) {
+                if (cta_begin[b] < cta_begin[b + 1]) file_first_cta[b] = cnt[tiles[cta_begin[b]].file];
+                for (int t = cta_begin[b]; t < cta_begin[b + 1]; t++) {
+                    uint32_t f = tiles[t].file;
+                    if (last[f] != b) { cnt[f]++; last[f] = b; }
+                }
+            }
+        for (int f = 0; f < n; f++) file_row[f + 1] = file_row[f] + std::max(1u, cnt[f]);
+    }
+    std::vector<unsigned long long> fwd((size_t)file_row[n] * NB, 0);
     // same launch sequence as kf_api.cu:run_files -- probe, one line-grid launch per width, generic kernel
     std::vector<uint8_t> formats(n);
     for (int i = 0; i < n; i++) formats[i] = len[i] ? arena[off[i]] : 0;
     std::vector<uint32_t> file_P(n, 0);
     std::vector<uint32_t> wc(4, 0);
     const bool lg = use_lg && k == 7 && !fw;
-    emu::launch((n + 31) / 32, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data()); });
+    emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data()); });
     if (lg) {
         std::vector<unsigned long long> scratch((size_t)grid * 16384, 0);
         if (threads == 64) {
-            run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
-            run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
-            run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+            run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
+            run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
+            run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
         } else {
-            run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
-            run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
-            run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), scratch.data(), wc.data());
+            run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
+            run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
+            run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
         }
         for (auto v : scratch) if (v) { fprintf(stderr, "scratch not zero after run\n"); return 3; }
         int nlg = 0; for (auto P : file_P) nlg += P != 0;
         fprintf(stderr, "linegrid files: %d of %d\n", nlg, n);
     }
-#define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_P.data(), wc.data()); break;
+#define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); break;
     switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }
     // FASTQ files: same sequence as kf_api.cu (tile newline counts -> tile line types -> counting kernel)
     {
@@ -140,8 +154,8 @@ int main(int argc, char **argv) {
             emu::launch(2, 64, 0, [&]() { fastq_tile_newlines_kernel(arena.data(), fq.data(), (int)fq.size(), nl.data()); });
             emu::launch((unsigned)ftb.size() - 1, 64, 0, [&]() { fastq_tile_types_kernel(nl.data(), ftb.data()); });
             size_t smem = sizeof(uint32_t) << (2 * k);
-#define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), err.data()); }); \
-                          else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), err.data()); }); break;
+#define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), file_row.data(), err.data()); }); \
+                          else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), file_row.data(), err.data()); }); break;
             switch (k) { RUNQ(3) RUNQ(4) RUNQ(5) RUNQ(7) default: return 2; }
             for (int f = 0; f < n; f++)
                 if (err[f] != ~0ull && err[f] - off[f] < len[f]) fprintf(stderr, "fastq layout violation file %d at %llu\n", f, err[f] - off[f]);
@@ -151,7 +165,7 @@ int main(int argc, char **argv) {
     long long V = (long long)canon.size();
     std::vector<unsigned long long> counts((size_t)n * V), totals(n);
     std::vector<double> freq((size_t)n * V);
-    emu::launch(n, 64, 0, [&]() { fold_normalize_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, 0u, counts.data(), freq.data(), (float *)nullptr, totals.data()); });
+    emu::launch(n, 64, 0, [&]() { fold_normalize_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data()); });
     for (int f = 0; f < n; f++) {
         printf("%llu", totals[f]);
         for (long long i = 0; i < V; i++) printf(" %llu", counts[(size_t)f * V + i]);

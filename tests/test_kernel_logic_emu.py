@@ -120,3 +120,17 @@ def test_emulated_fastq_fuzz(tmp_path):
         for f, (tot, counts, _) in zip(files, res):
             ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
             assert np.array_equal(counts, ref), (s, k, grid, thr, tile, f)
+
+
+def test_emulated_more_ctas_than_chunks(toy_inputs, tmp_path):
+    """A 14 KB file cut over 40 CTAs: most CTAs hold nothing, the others one 512-byte piece each -- every piece owns a
+    row of the file (rank among the CTAs that hold the file, with gaps between them), the fold sums the rows."""
+    files = []
+    for s in ("G000830275sub", "G000402355sub"):
+        p = str(tmp_path / (s + ".fna"))
+        open(p, "wb").write(toy_inputs[s][:20000] if s != "G000830275sub" else toy_inputs[s])
+        files.append(p)
+    for grid in (40, 97):
+        res = run_emu(7, 32, grid, False, 1, files)
+        for f, (tot, counts, _) in zip(files, res):
+            assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), 7)), (grid, f)

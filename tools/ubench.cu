@@ -4,6 +4,7 @@
 //
 // Every variant streams the same synthetic 80-column FASTA arena (one record) and reports GB/s of file
 // bytes, bases per SM-clock (SM clock measured with clock64 inside the kernel) and ms.
+#define KF_PIECE_TIMING 1
 #include "kf_kernels.cuh"
 
 #include <cstdio>
@@ -157,10 +158,10 @@ void run(const char *name, const uint8_t *arena, size_t bytes, int sms, unsigned
 // line-grid kernel on the same arena (one file, tiles of 1024 chunks, one CTA per SM)
 template <int THREADS>
 void run_lg(const uint8_t *arena, size_t bytes, int sms) {
-    using G = LineGrid<80>;
+    using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
-    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * 2 * G::STAGE + 2 * NW * sizeof(uint64_t) + 2 * sizeof(unsigned long long) + 16;
-    auto kern = count_fasta_linegrid_kernel<80, THREADS>;
+    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    auto kern = count_fasta_lines_kernel<80, THREADS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t n_chunks = (uint32_t)(bytes / CHUNK);
     std::vector<Tile> tiles; std::vector<int> cta_begin(sms + 1, 0);
@@ -178,25 +179,127 @@ void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     CK(cudaMalloc(&d_off, 8)); CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_len, 8)); CK(cudaMemcpy(d_len, &len, 8, cudaMemcpyHostToDevice));
     uint32_t *d_wc; uint32_t wc[4] = {1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 16)); CK(cudaMemcpy(d_wc, wc, 16, cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&d_fwd, 16384 * 8)); CK(cudaMemset(d_fwd, 0, 16384 * 8));
+    CK(cudaMalloc(&d_fwd, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_fwd, 0, (size_t)sms * 16384 * 8));
     CK(cudaMalloc(&d_scr, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_scr, 0, (size_t)sms * 16384 * 8));
+    uint32_t *d_row, *d_fc; uint32_t rows[2] = {0u, (uint32_t)sms};
+    std::vector<uint32_t> ranks(sms); for (int b = 0; b < sms; b++) ranks[b] = b;
+    CK(cudaMalloc(&d_row, 8)); CK(cudaMemcpy(d_row, rows, 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_fc, 4 * sms)); CK(cudaMemcpy(d_fc, ranks.data(), 4 * sms, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int it = 0; it < 5; it++) {
-        CK(cudaMemset(d_fwd, 0, 16384 * 8));
+        CK(cudaMemset(d_fwd, 0, (size_t)sms * 16384 * 8));
         CK(cudaEventRecord(e0));
-        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_scr, 1, d_wc);
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, d_scr, 1, d_wc);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (it >= 1 && ms < best) best = ms;
     }
-    std::vector<unsigned long long> h(16384);
-    CK(cudaMemcpy(h.data(), d_fwd, 16384 * 8, cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> h((size_t)sms * 16384);
+    CK(cudaMemcpy(h.data(), d_fwd, (size_t)sms * 16384 * 8, cudaMemcpyDeviceToHost));
     unsigned long long tot = 0; for (auto v : h) tot += v;
     const double bases = (double)bytes * 80.0 / 81.0, gbs = (double)bytes / best / 1e6;
     printf("%-34s      thr=%4d ctas/SM=1  %8.3f ms  %8.1f GB/s  %6.3f Tbases/s  %6.2f bases/clk/SM@1.965GHz  total 7-mers %llu  (%.1f%% of 6550)\n",
-           "line-grid kernel LW=80 pair16", THREADS, best, gbs, bases / best / 1e9, bases / (best * 1e-3 * 1.965e9 * sms), tot, 100.0 * gbs * 1.02 / 6550.0);
+           "line kernel LW=80 pair16", THREADS, best, gbs, bases / best / 1e9, bases / (best * 1e-3 * 1.965e9 * sms), tot, 100.0 * gbs * 1.02 / 6550.0);
     cudaFree(d_tiles); cudaFree(d_cb); cudaFree(d_P); cudaFree(d_off); cudaFree(d_len); cudaFree(d_fwd); cudaFree(d_scr);
+}
+
+// many equal files (16-byte header, 80-column lines, short last line) through the line kernel, with the per-piece
+// cycle breakdown of KF_PIECE_TIMING
+__global__ void gen_fasta_files(uint8_t *arena, size_t file_bytes, size_t slot, int nfiles) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = slot * (size_t)nfiles, stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const size_t o = i % slot;
+        uint8_t c = 0;
+        if (o < file_bytes) {
+            if (o < 16) c = (o == 0) ? '>' : (o == 15 ? '\n' : 'x');
+            else if ((o - 16) % 81 == 80 || o == file_bytes - 1) c = '\n';
+            else {
+                uint64_t z = i * 0x9E3779B97F4A7C15ull;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                c = "ACGT"[z & 3];
+            }
+        }
+        arena[i] = c;
+    }
+}
+
+template <int THREADS>
+void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms) {
+    using G = LineGeom<80>;
+    constexpr int NW = THREADS / 32;
+    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    auto kern = count_fasta_lines_kernel<80, THREADS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t slot = (arena_bytes / nfiles) / CHUNK * CHUNK;
+    const size_t file_bytes = slot - 100;
+    gen_fasta_files<<<sms * 8, 256>>>(arena, file_bytes, slot, nfiles);
+    CK(cudaDeviceSynchronize());
+    const uint64_t total_chunks = (uint64_t)nfiles * (slot / CHUNK);
+    std::vector<Tile> tiles; std::vector<int> cta_begin(sms + 1, 0);
+    std::vector<uint64_t> off(nfiles), len(nfiles); std::vector<uint32_t> P(nfiles, 81);
+    for (int f = 0; f < nfiles; f++) { off[f] = (uint64_t)f * slot; len[f] = file_bytes; }
+    {
+        uint64_t done = 0; int cta = 0;
+        auto hi = [&](int b) { return total_chunks * (uint64_t)(b + 1) / (uint64_t)sms; };
+        for (int f = 0; f < nfiles; f++) {
+            uint64_t fc0 = off[f] / CHUNK, nch = slot / CHUNK, pos = 0;
+            while (pos < nch) {
+                while (cta < sms - 1 && done >= hi(cta)) { cta++; cta_begin[cta] = (int)tiles.size(); }
+                uint64_t room = (cta == sms - 1) ? total_chunks - done : hi(cta) - done;
+                uint64_t take = std::min<uint64_t>(std::min<uint64_t>(nch - pos, room), 1024);
+                if (!take) take = 1;
+                tiles.push_back(Tile{(uint32_t)(fc0 + pos), (uint32_t)take, (uint32_t)f, (uint32_t)fc0});
+                pos += take; done += take;
+            }
+        }
+        while (cta < sms) { cta++; cta_begin[cta] = (int)tiles.size(); }
+    }
+    Tile *d_tiles; int *d_cb; uint32_t *d_P; uint64_t *d_off, *d_len; unsigned long long *d_fwd, *d_scr;
+    CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(Tile))); CK(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_cb, cta_begin.size() * sizeof(int))); CK(cudaMemcpy(d_cb, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_P, 4 * nfiles)); CK(cudaMemcpy(d_P, P.data(), 4 * nfiles, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_off, 8 * nfiles)); CK(cudaMemcpy(d_off, off.data(), 8 * nfiles, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_len, 8 * nfiles)); CK(cudaMemcpy(d_len, len.data(), 8 * nfiles, cudaMemcpyHostToDevice));
+    uint32_t *d_wc; uint32_t wc[4] = {1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 16)); CK(cudaMemcpy(d_wc, wc, 16, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> frow(nfiles + 1, 0), ffc(sms, 0);
+    {
+        std::vector<uint32_t> cnt(nfiles, 0); std::vector<int> last(nfiles, -1);
+        for (int b = 0; b < sms; b++) {
+            if (cta_begin[b] < cta_begin[b + 1]) ffc[b] = cnt[tiles[cta_begin[b]].file];
+            for (int t = cta_begin[b]; t < cta_begin[b + 1]; t++) {
+                uint32_t f = tiles[t].file;
+                if (last[f] != b) { cnt[f]++; last[f] = b; }
+            }
+        }
+        for (int f = 0; f < nfiles; f++) frow[f + 1] = frow[f] + std::max(1u, cnt[f]);
+    }
+    const size_t nrows = frow[nfiles];
+    uint32_t *d_row, *d_fc;
+    CK(cudaMalloc(&d_row, 4 * (nfiles + 1))); CK(cudaMemcpy(d_row, frow.data(), 4 * (nfiles + 1), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_fc, 4 * sms)); CK(cudaMemcpy(d_fc, ffc.data(), 4 * sms, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_fwd, nrows * 16384 * 8));
+    CK(cudaMalloc(&d_scr, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_scr, 0, (size_t)sms * 16384 * 8));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    unsigned long long tm[8] = {0}, zero[8] = {0};
+    for (int it = 0; it < 4; it++) {
+        CK(cudaMemset(d_fwd, 0, nrows * 16384 * 8));
+        CK(cudaMemcpyToSymbol(g_piece_timing, zero, sizeof zero));
+        CK(cudaEventRecord(e0));
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, d_scr, 1, d_wc);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 1 && ms < best) { best = ms; CK(cudaMemcpyFromSymbol(tm, g_piece_timing, sizeof tm)); }
+    }
+    const double bytes = (double)nfiles * file_bytes, pieces = (double)tm[3];
+    printf("files=%5d x %8zu B  %7.3f ms  %7.1f GB/s | per CTA: total %.0f kclk, pieces %.1f | per piece: units %.1f kclk/warp, wait+checksum %.1f kclk/warp, "
+           "fold %.1f kclk/warp, zero %.1f kclk/warp, anchor %.1f kclk\n", nfiles, file_bytes, best, bytes / best / 1e6, tm[4] / (double)sms / 1e3, pieces / sms,
+           tm[0] / pieces / NW / 1e3, tm[1] / pieces / NW / 1e3, tm[6] / pieces / NW / 1e3, tm[2] / pieces / NW / 1e3, tm[5] / pieces / 1e3);
+    cudaFree(d_tiles); cudaFree(d_cb); cudaFree(d_P); cudaFree(d_off); cudaFree(d_len); cudaFree(d_fwd); cudaFree(d_scr); cudaFree(d_wc);
 }
 
 int main(int argc, char **argv) {
@@ -219,19 +322,11 @@ int main(int argc, char **argv) {
     run<XOR_SINK, 7, 512, 2>("load+decode+extract (xor sink)", arena, bytes, sms, g_out, d_clk);
     run<ATOMS_ONLY, 7, 512, 2>("atomics only u32 16384 bins", arena, bytes, sms, g_out, d_clk);
     run<SIMPLE_U32, 7, 512, 2>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 512, 2, 2>("production range processor", arena, bytes, sms, g_out, d_clk);
     run<FULL_PROD, 7, 512, 2, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 512, 2, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 1024, 1, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 256, 3, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 256, 3, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 256, 3, 6>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 384, 2, 4>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 7, 384, 2, 6>("production range processor", arena, bytes, sms, g_out, d_clk);
-    run<FULL_PROD, 5, 512, 2, 3>("production range processor k=5", arena, bytes, sms, g_out, d_clk);
     run_lg<512>(arena, bytes, sms);
+    run_lg<640>(arena, bytes, sms);
     run_lg<768>(arena, bytes, sms);
-    run_lg<1024>(arena, bytes, sms);
+    for (int nf : {148, 1000, 4000}) run_lg_files<512>(arena, bytes, nf, sms);
     printf("done\n");
     return 0;
 }
