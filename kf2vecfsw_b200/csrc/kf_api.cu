@@ -41,7 +41,6 @@ struct Ctx {
     uint32_t *d_file_row = nullptr; size_t frow_cap = 0;          // first forward-count row of every file (+ total)
     uint32_t *d_cta_first_rank = nullptr; size_t cfr_cap = 0;    // per line-kernel CTA: how many earlier CTAs hold a piece of its first file
     uint32_t pc_rows = 0;
-    unsigned long long *d_scratch = nullptr; size_t scratch_cap = 0;
     // FASTQ plan: 32 KiB tiles, their '\n' counts / line types, per-file tile ranges, layout-violation offsets
     Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
     int *d_fq_cta_begin = nullptr; size_t fq_cta_cap = 0;
@@ -228,12 +227,12 @@ template <int LW>
 int launch_linegrid(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
     using G = LineGeom<LW>;
     constexpr int NW = THREADS_LG / 32;
-    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
     auto kern = count_fasta_lines_kernel<LW, THREADS_LG>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
-                                                             (unsigned long long *)g.d_fwd, g.d_file_row, g.d_cta_first_rank, g.d_scratch,
-                                                             CTAS_PER_SM, g.d_width_counts);
+                                                             (unsigned long long *)g.d_fwd, g.d_file_row, g.d_cta_first_rank, CTAS_PER_SM,
+                                                             g.d_width_counts);
     CK(cudaGetLastError());
     return KF_OK;
 }
@@ -365,11 +364,6 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         CK(cudaGetLastError());
         g.last_launches++;
         if (use_lg) {
-            const size_t sc_bytes = (size_t)(grid / CTAS_PER_SM) * 16384 * sizeof(unsigned long long);
-            if (sc_bytes > g.scratch_cap) {
-                if ((rc = ensure(g.d_scratch, g.scratch_cap, sc_bytes)) != KF_OK) return rc;
-                CK(cudaMemsetAsync(g.d_scratch, 0, g.scratch_cap, s));   // kept zero by the kernel afterwards
-            }
             rc = launch_linegrid<80>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<70>(d_arena, grid, s);
@@ -476,7 +470,7 @@ int kf_shutdown(void) {
     cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
     cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals); cudaFree(g.d_seq); cudaFree(g.d_win_off); cudaFree(g.d_win_len);
     cudaFree(g.d_fq_tiles); cudaFree(g.d_fq_cta_begin); cudaFree(g.d_fq_tile_nl); cudaFree(g.d_fq_file_tile_begin); cudaFree(g.d_fq_err);
-    cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_file_row); cudaFree(g.d_cta_first_rank); cudaFree(g.d_scratch); cudaFree(g.d_width_counts);
+    cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_file_row); cudaFree(g.d_cta_first_rank); cudaFree(g.d_width_counts);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
     cudaEventDestroy(g.ev_k0); cudaEventDestroy(g.ev_k1);

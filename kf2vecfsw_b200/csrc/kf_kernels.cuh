@@ -457,20 +457,29 @@ __device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32
 }
 #endif
 
-struct Gmem64Sink {   // rare paths of the line kernel: a u64 row in global memory (+ "row is dirty" flag).  The row is in the
-                      // pair histogram's orientation (7-mer digits reversed: first base in bits 1:0), see the flush.
-    unsigned long long *g;
-    uint32_t *flag;
+// Sinks of the line kernel's rare paths (byte walker, off-grid lines).  Both take off = 4 * kmer with the first base
+// most significant and store it in the pair histogram's orientation (7-mer digits reversed: first base in bits 1:0).
+__device__ __forceinline__ uint32_t rev7_of_off(uint32_t off) {   // off = 4 * kmer, 14-bit kmer
+    const uint32_t r = __brev(off) >> 16;                          // bit-reverse, then swap the two bits of each digit
+    return ((r & 0x2AAAu) >> 1) | ((r & 0x1555u) << 1);
+}
+struct SingleSink {   // "singles" histogram in shared memory: 16,384 7-mer bins as 8,192 words of two u16 halves
+                      // (word = xk >> 1, half = xk & 1) plus the number of k-mers issued, for the overflow checksum
+    uint32_t *h;
+    uint32_t *n;
     __device__ __forceinline__ void operator()(uint32_t off) const {
-        const uint32_t r = __brev(off) >> 16;   // off = 4 * kmer, 14-bit kmer: bit-reverse, then swap the bits of each digit
-        const uint32_t idx = ((r & 0x2AAAu) >> 1) | ((r & 0x1555u) << 1);
-        atomicAdd(g + idx, 1ull);
-        *flag = 1u;
+        const uint32_t idx = rev7_of_off(off);
+        atomicAdd(h + (idx >> 1), (idx & 1u) ? 0x10000u : 1u);
+        atomicAdd(n, 1u);
 #ifdef KF_EMU_DEBUG
         extern std::atomic<long> g_dbg_emits;
         g_dbg_emits++;
 #endif
     }
+};
+struct Gmem64Sink {   // exact recount after a wrapped 16-bit half: straight into the CTA's u64 row in global memory
+    unsigned long long *g;
+    __device__ __forceinline__ void operator()(uint32_t off) const { atomicAdd(g + rev7_of_off(off), 1ull); }
 };
 
 // First line start at or after byte q (a line start is file_begin or the byte after a '\n'); file_end if none.
@@ -499,8 +508,8 @@ __device__ KF_NOINLINE uint64_t fasta_line_start_at_or_after(const Src src, uint
 }
 
 // Exact but slow: the generic range processor over the lines starting in [lo, hi), global sink.
-template <int K, class Src>
-__device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64_t hi, uint32_t file_c0, Gmem64Sink gs) {
+template <int K, class Src, class Sink>
+__device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64_t hi, uint32_t file_c0, Sink gs) {
     if (lo >= hi) return;
     const uint32_t c0 = (uint32_t)(lo / CHUNK), c1 = (uint32_t)((hi + CHUNK - 1) / CHUNK);
     fasta_process_range<K, false, 2>(src, c0, c1, file_c0, gs, lo, hi, true);
@@ -616,6 +625,44 @@ __device__ __forceinline__ void ln_count_pairs(const uint32_t (&PK)[LineGeom<LW>
     }
 }
 
+// All 32 lanes: count the K-mers that start at stream positions [0, npos) of ONE line whose bytes sit in shared memory.
+// Stream position p is byte p for p < skip and byte p + 1 from there on (skip = index of the one '\n' that is not part
+// of the stream; pass a large value when there is none); nstream positions exist.  A K-mer counts iff its K bytes are
+// all A/C/G/T, i.e. every other byte is taken as a window break -- the callers make sure no '\n' is among them.
+template <int K, class Sink>
+__device__ __forceinline__ void ln_coop_line(const uint8_t *bytes, int npos, int nstream, int skip, Sink sink) {
+    const int lane = threadIdx.x & 31;
+    for (int pos = lane; pos < npos; pos += 32) {
+        bool valid = pos + K <= nstream;
+        uint32_t kmer = 0;
+        if (valid) {
+#pragma unroll
+            for (int t = 0; t < K; t++) {
+                const int sp = pos + t;
+                const uint32_t c = bytes[sp < skip ? sp : sp + 1];
+                valid = valid && is_base(c);
+                kmer = (kmer << 2) | ((c >> 1) & 3u);
+            }
+        }
+        if (valid) sink(kmer << 2);
+    }
+}
+
+#ifdef KF_PIECE_TIMING
+// developer instrumentation (tools/ubench only): SM-clock sums over all warps / CTAs
+// [0] warp cycles claiming+processing units  [1] warp cycles waiting at the end-of-piece barrier  [2] CTA cycles in the flush
+// [3] pieces  [4] CTA cycles total  [5] CTA cycles anchor search + cursor reset  [6] warp cycles in the fold loop
+// ([1] = arrival at the flush until the checksum is known: barrier wait + low-half sums; [2] = zeroing + last barrier)
+__device__ unsigned long long g_piece_timing[16];
+// [8] clean windows  [9] their warp cycles (decode + count)  [10] windows with a dirty lane  [11] their warp cycles
+// [12] grid breaks  [13] warp cycles in the exact generic region  [14] warp cycles finding the next line start at a break
+#define KF_T(var) const long long var = clock64()
+#define KF_TADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_piece_timing[i], (unsigned long long)(v)); } while (0)
+#else
+#define KF_T(var)
+#define KF_TADD(i, v)
+#endif
+
 struct LnUnit {      // a claimed byte range of the current file piece
     uint64_t Us, Ue;   // lines that start in [Us, Ue) are this warp's
 };
@@ -624,9 +671,9 @@ struct LnUnit {      // a claimed byte range of the current file piece
 // s_cursor: shared byte cursor relative to A.  Returns the number of pairs issued through npairs.
 template <int LW>
 __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ arena, const uint64_t A, const uint64_t Xe,
-                                                 const uint64_t F0, const uint64_t F1, uint8_t *buf, uint64_t *bar,
-                                                 uint32_t &par, uint32_t *s_cursor, const uint32_t nwarps, uint32_t *hist16,
-                                                 Gmem64Sink gs, uint32_t &npairs) {
+                                                 const uint64_t F0, const uint64_t F1, uint8_t *buf, uint32_t *wscr,
+                                                 uint64_t *bar, uint32_t &par, uint32_t *s_cursor, const uint32_t nwarps, uint32_t *hist16,
+                                                 SingleSink gs, uint32_t &npairs) {
     using G = LineGeom<LW>;
     constexpr int K = 7;
     const int lane = threadIdx.x & 31;
@@ -634,6 +681,12 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
     const GlobalSrc gsrc{arena};
     auto emit = [&](uint32_t xk) { gs(xk << 2); };
     if (A >= Xe) return;
+#ifdef KF_PIECE_TIMING
+    unsigned long long tacc[7] = {0, 0, 0, 0, 0, 0, 0};   // slots 8..14 of g_piece_timing, added once per piece
+#define KF_LADD(i, v) tacc[(i) - 8] += (unsigned long long)(v)
+#else
+#define KF_LADD(i, v)
+#endif
     const uint64_t plen = Xe - A;
     // guided self-scheduling: a 1/(2 * nwarps) share of what is left, in whole windows, between 2 and 64 windows.
     // The piece's last TAIL bytes are handed out FIRST (cursor range [0, TAIL)): the end of a file -- short last line,
@@ -738,18 +791,43 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         // ---- where the next window is; get its copy going before the decode ----
         const uint64_t sf = B + (uint64_t)f * G::P;     // first byte not covered by lanes [0, f)
         uint64_t q = sf;                                // next line start to process on the grid
+        bool fast_break = false;
         if (f < nact) {
-            // the line at sf breaks the grid: skip it and any header lines that follow (found in the staged window
-            // when they lie inside it); [sf, q) goes to the exact generic path below
+            // the line at sf breaks the grid.  Usual case: the short last line of a record, followed by a header line or
+            // the end of the file -- then its k-mers end with it and all lanes count them together straight from the
+            // staged window.  Anything else ([sf, q) holds another kind of line) goes to the exact generic path below.
+            // q = the next line start that is not a header: where the grid restarts.
+            KF_T(tq0);
+            const uint8_t *lb = buf + woff + f * G::P;
+            int nlp = G::P + 1;   // index of the line's '\n' (none within LW + 1 bytes: the line is longer than the grid's)
+#pragma unroll
+            for (int i = 0; i < (G::P + 31) / 32; i++) {
+                const int bi = lane + 32 * i;
+                const unsigned m = __ballot_sync(FULL, bi < G::P && lb[bi] == 0x0Au);
+                if (m && nlp > G::P) nlp = 32 * i + __ffs((int)m) - 1;
+            }
             const WindowSrc wsrc{arena, buf, base, (uint32_t)G::STAGE};
-            q = fasta_line_start_at_or_after(wsrc, sf + 1, F0, F1, lane);
+            const bool is_hdr = lb[0] == (uint8_t)'>';   // sf is a line start: a '>' here opens a header line
+            if (nlp <= G::P && is_hdr) {
+                fast_break = true;                        // a header line that ends inside the slot: nothing to count
+                q = sf + (uint64_t)nlp + 1 < F1 ? sf + (uint64_t)nlp + 1 : F1;
+            } else if (nlp < LW && !is_hdr) {
+                const uint64_t after = sf + (uint64_t)nlp + 1;
+                fast_break = after >= F1 || lb[nlp + 1] == (uint8_t)'>';
+                q = after < F1 ? after : F1;
+                if (fast_break) ln_coop_line<K>(lb, nlp, nlp, 1 << 20, gs);
+            } else {
+                q = fasta_line_start_at_or_after(wsrc, sf + 1, F0, F1, lane);
+            }
             while (q < U.Ue && wsrc.byte(q) == (uint32_t)'>') q = fasta_line_start_at_or_after(wsrc, q + 1, F0, F1, lane);
-            strikes = (f == 0) ? strikes + 1 : 0;
+            strikes = (f == 0 && !fast_break) ? strikes + 1 : 0;
+            KF_T(tq1);
+            KF_LADD(14, tq1 - tq0);
         } else {
             strikes = 0;
         }
         const uint64_t curB = B;
-        uint64_t gen_lo = sf, gen_hi = q;               // exact generic region (empty when the window was clean)
+        uint64_t gen_lo = sf, gen_hi = fast_break ? sf : q;   // exact generic region (empty when the window was clean)
         LnUnit Un = U;
         bool have_n = true;
         if (q < U.Ue && strikes >= 4) {
@@ -763,6 +841,11 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             if (have_n) start_unit(Un);
         }
         // ---- decode + count the lanes on the grid ----
+        KF_T(td0);
+#ifdef KF_PIECE_TIMING
+        bool any_dirty = false;
+#endif
+        bool dirty = false;
         if ((uint32_t)lane < f) {
             uint32_t PK[G::NPK + 1];
             const uint32_t anyV = ln_decode<LW>(x, PK);
@@ -770,36 +853,66 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
                 ln_count_pairs<LW>(PK, hist16, hbase);
                 npairs += G::NPAIR;
             } else {
-                const uint64_t sl = curB + (uint64_t)lane * G::P;
-                fasta_walk_lane<K>(gsrc, sl, sl + G::P, false, true, emit);
+                dirty = true;
             }
         }
+        // lines that hold a non-ACGT byte (or whose look-ahead does): the window buffer is already being refilled, so the
+        // line is fetched again from global memory (L2) into the warp's scratch, one word per lane, and all lanes count
+        // its k-mers together.  A '\n' among its bytes (a line shorter than the grid's inside the slot, or a next line
+        // shorter than the look-ahead) is not a window break: such a line goes to the exact byte walker.
+        unsigned D = __ballot_sync(FULL, dirty);
+#ifdef KF_PIECE_TIMING
+        any_dirty = D != 0;
+#endif
+        while (D) {
+            const int j = __ffs((int)D) - 1;
+            D &= D - 1;
+            const uint64_t sl = curB + (uint64_t)j * G::P;
+            const uint64_t wb = sl & ~3ull;
+            KF_SYNCWARP();
+            if (lane < 24) wscr[lane] = __ldg(reinterpret_cast<const uint32_t *>(arena + wb) + lane);
+            KF_SYNCWARP();
+            const uint8_t *lb = reinterpret_cast<const uint8_t *>(wscr) + (uint32_t)(sl & 3u);
+            bool has_nl = false;
+#pragma unroll
+            for (int i = 0; i < (G::P + G::LA + 31) / 32; i++) {
+                const int bi = lane + 32 * i;
+                has_nl = has_nl || (bi < G::P + G::LA && bi != LW && lb[bi] == 0x0Au);
+            }
+            if (__ballot_sync(FULL, has_nl) != 0) {
+                if (lane == j) fasta_walk_lane<K>(gsrc, sl, sl + G::P, false, true, emit);
+            } else if (lb[0] != (uint8_t)'>') {   // (a header line exactly as long as a sequence line holds no k-mers)
+                ln_coop_line<K>(lb, LW, LW + G::LA, LW, gs);
+            }
+        }
+#ifdef KF_PIECE_TIMING
+        {
+            const bool wd = any_dirty;
+            const long long td1 = clock64();
+            KF_LADD(wd ? 10 : 8, 1);
+            KF_LADD(wd ? 11 : 9, td1 - td0);
+        }
+#endif
+        KF_T(tg0);
         if (gen_lo < gen_hi) lg_generic_region<K>(gsrc, gen_lo, gen_hi, (uint32_t)(F0 / CHUNK), gs);
+#ifdef KF_PIECE_TIMING
+        if (gen_lo < gen_hi) { const long long tg1 = clock64(); KF_LADD(12, 1); KF_LADD(13, tg1 - tg0); }
+#endif
         U = Un;
         have = have_n;
     }
+#ifdef KF_PIECE_TIMING
+    for (int i = 0; i < 7; i++) if (tacc[i]) KF_TADD(8 + i, tacc[i]);
+#endif
 }
 
-#ifdef KF_PIECE_TIMING
-// developer instrumentation (tools/ubench only): SM-clock sums over all warps / CTAs
-// [0] warp cycles claiming+processing units  [1] warp cycles waiting at the end-of-piece barrier  [2] CTA cycles in the flush
-// [3] pieces  [4] CTA cycles total  [5] CTA cycles anchor search + cursor reset  [6] warp cycles in the fold loop
-// ([1] = arrival at the flush until the checksum is known: barrier wait + low-half sums; [2] = zeroing + last barrier)
-__device__ unsigned long long g_piece_timing[8];
-#define KF_T(var) const long long var = clock64()
-#define KF_TADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_piece_timing[i], (unsigned long long)(v)); } while (0)
-#else
-#define KF_T(var)
-#define KF_TADD(i, v)
-#endif
 
 template <int LW, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
                          const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
                          const uint64_t *__restrict__ file_len, unsigned long long *__restrict__ g_fwd,
-                         const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ cta_first_rank,
-                         unsigned long long *__restrict__ g_scratch, int cta_stride,
+                         const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ cta_first_rank, int cta_stride,
                          const uint32_t *__restrict__ width_counts) {
     using G = LineGeom<LW>;
     if (width_counts[(LW - 50) / 10] == 0) return;   // no file of this width in the batch (uniform exit)
@@ -807,23 +920,23 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     constexpr int NWORDS = 32768;
     constexpr int NB7 = 16384;
     KF_DYN_SMEM(uint32_t, smem);
-    uint32_t *hist16 = smem;
-    uint8_t *stage_base = reinterpret_cast<uint8_t *>(smem + NWORDS);
+    constexpr int NSWORDS = NB7 / 2;
+    uint32_t *hist16 = smem;               // pairs: 65,536 8-mer bins, two u16 halves per word
+    uint32_t *single16 = smem + NWORDS;    // rare paths: 16,384 7-mer bins, two u16 halves per word
+    uint8_t *stage_base = reinterpret_cast<uint8_t *>(single16 + NSWORDS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage_base + (size_t)NWARPS * G::STAGE);
-    uint32_t *s_part = reinterpret_cast<uint32_t *>(bars + NWARPS);   // [0..NWARPS) pairs issued, [NWARPS..2 NWARPS) low-half sums
-    uint32_t *s_flag = s_part + 2 * NWARPS;                           // [0] rare-path row is non-zero, [1] sink of the recount
-    uint32_t *s_cursor = s_flag + 2;
+    uint32_t *s_wscr = reinterpret_cast<uint32_t *>(bars + NWARPS);   // per warp: 24 words, one dirty line re-fetched from global
+    uint32_t *s_part = s_wscr + 24 * NWARPS;                          // per warp: pairs issued | pair low-half sums | singles half sums
+    uint32_t *s_nsingle = s_part + 3 * NWARPS;                        // singles issued
+    uint32_t *s_cursor = s_nsingle + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < NWORDS; i += THREADS) hist16[i] = 0;
-    if (threadIdx.x == 0) { s_flag[0] = 0; *s_cursor = 0; }
+    for (int i = threadIdx.x; i < NWORDS + NSWORDS; i += THREADS) smem[i] = 0;
+    if (threadIdx.x == 0) { *s_nsingle = 0; *s_cursor = 0; }
     uint8_t *buf = stage_base + (size_t)warp * G::STAGE;
     uint64_t *bar = bars + warp;
     uint32_t par = 0;
     if (lane == 0) stage_bar_init(bar);
     __syncthreads();
-    // rare-path k-mers (walker, off-grid lines) go to this CTA's private u64 row so that a failed checksum can
-    // discard them together with the pair histogram
-    unsigned long long *scratch = g_scratch + (size_t)blockIdx.x * NB7;
     uint32_t npairs = 0;
     int cur_file = -1;
     uint64_t file_lo = 0, file_hi = 0;   // byte range of cur_file this CTA has processed (for the exact recount)
@@ -831,7 +944,8 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     const int first_file = tb0 < tb1 ? (int)tiles[tb0].file : -1;
 
     auto flush = [&](int file) {
-        // checksum: pairs issued vs the sum of the low halves, through per-warp partial sums (no contended atomics)
+        // checksums (a u16 half may have wrapped): pairs issued vs the sum of the pair histogram's low halves, singles
+        // issued vs the sum of all halves of the singles histogram -- through per-warp partial sums
         uint32_t np = npairs;
         npairs = 0;
 #pragma unroll
@@ -839,17 +953,17 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         if (lane == 0) s_part[warp] = np;
         KF_T(tw0);
         __syncthreads();
-        uint32_t low = 0;
+        uint32_t low = 0, sing = 0;
         for (int i = threadIdx.x; i < NWORDS; i += THREADS) low += hist16[i] & 0xFFFFu;
+        for (int i = threadIdx.x; i < NSWORDS; i += THREADS) { const uint32_t v = single16[i]; sing += (v & 0xFFFFu) + (v >> 16); }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) low += __shfl_xor_sync(FULL, low, o);
-        if (lane == 0) s_part[NWARPS + warp] = low;
+        for (int o = 16; o > 0; o >>= 1) { low += __shfl_xor_sync(FULL, low, o); sing += __shfl_xor_sync(FULL, sing, o); }
+        if (lane == 0) { s_part[NWARPS + warp] = low; s_part[2 * NWARPS + warp] = sing; }
         __syncthreads();
-        unsigned long long tp = 0, tl = 0;
+        unsigned long long tp = 0, tl = 0, ts = 0;
 #pragma unroll
-        for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; }
-        const bool ok = tp == tl;
-        const bool rare = s_flag[0] != 0;
+        for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; ts += s_part[2 * NWARPS + w]; }
+        const bool ok = tp == tl && ts == (unsigned long long)*s_nsingle;
         // every CTA that holds a piece of the file owns one row of it (file_row[file] + its rank among those CTAs; the
         // fold kernel sums the rows), so the row is WRITTEN, every bin, with plain 16-byte stores: no global atomics.
         // Only the first file of a CTA's tile range can have begun in an earlier CTA: its rank comes from the host.
@@ -860,29 +974,24 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         if (tp == 0xFFFFFFFFFFFFull) tw1 = 0;   // depends on the shared reads above: taken after the barrier released
         KF_TADD(1, tw1 - tw0);
 #endif
-        if (rare) __threadfence();
-        // xk: 7-mer with its digits reversed (first base in bits 1:0) -- the orientation of the pair histogram, of the
-        // rare-path row and of this file's rows in g_fwd (the fold kernel undoes it).  xk is the first 7-mer of the
-        // 8-mers xk + a*16384 (word a*8192 + (xk >> 1); odd xk in the high half, even xk = low - high) and the second
-        // 7-mer of the 8-mers 4xk .. 4xk+3 (words 2xk, 2xk+1: sum of the low halves).  One thread: xk = 2j, 2j+1.
+        // xk: 7-mer with its digits reversed (first base in bits 1:0) -- the orientation of both histograms and of this
+        // file's rows in g_fwd (the fold kernel undoes it).  xk is the first 7-mer of the 8-mers xk + a*16384 (word
+        // a*8192 + (xk >> 1); odd xk in the high half, even xk = low - high) and the second 7-mer of the 8-mers
+        // 4xk .. 4xk+3 (words 2xk, 2xk+1: sum of the low halves).  One thread: xk = 2j and 2j+1.
 #pragma unroll 4
         for (int j = threadIdx.x; j < NB7 / 2; j += THREADS) {
             unsigned long long c0 = 0, c1 = 0;
             if (ok) {
                 const uint4 pw = *reinterpret_cast<const uint4 *>(hist16 + 4 * j);
-                c0 = (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu);
-                c1 = (pw.z & 0xFFFFu) + (pw.w & 0xFFFFu);
+                const uint32_t sw = single16[j];
+                c0 = (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu) + (sw & 0xFFFFu);
+                c1 = (pw.z & 0xFFFFu) + (pw.w & 0xFFFFu) + (sw >> 16);
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
                     const uint32_t w = hist16[a * 8192 + j];
                     c0 += (w & 0xFFFFu) - (w >> 16);
                     c1 += w >> 16;
                 }
-            }
-            if (rare) {
-                const ulonglong2 v = KF_LDCG(reinterpret_cast<const ulonglong2 *>(scratch) + j);
-                if (v.x | v.y) reinterpret_cast<ulonglong2 *>(scratch)[j] = make_ulonglong2(0ull, 0ull);
-                if (ok) { c0 += v.x; c1 += v.y; }
             }
             reinterpret_cast<ulonglong2 *>(g)[j] = make_ulonglong2(c0, c1);
         }
@@ -891,19 +1000,18 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         KF_TADD(6, tw2 - tw1);
 #endif
         __syncthreads();
-        uint4 *h4 = reinterpret_cast<uint4 *>(hist16);
-        for (int i = threadIdx.x; i < NWORDS / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) s_flag[0] = 0;
+        uint4 *h4 = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < (NWORDS + NSWORDS) / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) *s_nsingle = 0;
         __syncthreads();
 #ifdef KF_PIECE_TIMING
-        { long long tw3 = clock64(); if (s_flag[0] == 12345u) tw3 = 0; KF_TADD(2, tw3 - tw2); if (threadIdx.x == 0) atomicAdd(&g_piece_timing[3], 1ull); }
+        { long long tw3 = clock64(); if (*s_nsingle == 12345u) tw3 = 0; KF_TADD(2, tw3 - tw2); if (threadIdx.x == 0) atomicAdd(&g_piece_timing[3], 1ull); }
 #endif
         if (!ok) {
             // a 16-bit half wrapped: recount this CTA's part of the file exactly, straight into its (zeroed) row
             __threadfence();
             Gmem64Sink gs;
             gs.g = g;
-            gs.flag = s_flag + 1;   // nobody reads this one
             const uint64_t F0 = file_off[file], F1 = F0 + file_len[file];
             const GlobalSrc src{arena};
             const uint64_t lo_b = file_lo > F0 ? file_lo : F0, hi_b = file_hi < F1 ? file_hi : F1;
@@ -948,10 +1056,10 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         __syncthreads();
         KF_T(ta1);
         if (threadIdx.x == 0) KF_TADD(5, ta1 - ta0);
-        Gmem64Sink gs;
-        gs.g = scratch;
-        gs.flag = s_flag;
-        ln_process_piece<LW>(arena, A, Xe, F0, F1, buf, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
+        SingleSink gs;
+        gs.h = single16;
+        gs.n = s_nsingle;
+        ln_process_piece<LW>(arena, A, Xe, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
         KF_T(ta2);
         KF_TADD(0, ta2 - ta1);
         t = te;

@@ -46,12 +46,12 @@ static void run(const uint8_t *arena, const std::vector<Tile> &tiles, const std:
 template <int LW, int THREADS>
 static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
                    const uint32_t *file_P, const uint64_t *off, const uint64_t *len, unsigned long long *fwd,
-                   const uint32_t *file_row, const uint32_t *file_first_cta, unsigned long long *scratch, const uint32_t *wc) {
+                   const uint32_t *file_row, const uint32_t *file_first_cta, const uint32_t *wc) {
     using G = LineGeom<LW>;
     constexpr int NW = THREADS / 32;
-    size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
     emu::launch(grid, THREADS, smem, [&]() {
-        count_fasta_lines_kernel<LW, THREADS>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, scratch, 1, wc);
+        count_fasta_lines_kernel<LW, THREADS>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
     });
 }
 
@@ -119,17 +119,15 @@ int main(int argc, char **argv) {
     const bool lg = use_lg && k == 7 && !fw;
     emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data()); });
     if (lg) {
-        std::vector<unsigned long long> scratch((size_t)grid * 16384, 0);
         if (threads == 64) {
-            run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
-            run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
-            run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
+            run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         } else {
-            run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
-            run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
-            run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), scratch.data(), wc.data());
+            run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         }
-        for (auto v : scratch) if (v) { fprintf(stderr, "scratch not zero after run\n"); return 3; }
         int nlg = 0; for (auto P : file_P) nlg += P != 0;
         fprintf(stderr, "linegrid files: %d of %d\n", nlg, n);
     }

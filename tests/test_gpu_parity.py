@@ -180,6 +180,11 @@ def test_linegrid_u16_overflow_recount(eng):
     ref = c_oracle.count_buffer(data, 7)
     assert status[0] == 0 and np.array_equal(counts[0], ref)
     assert int(ref.max()) > 40_000_000
+    # same for the rare-path ("singles") histogram: every line holds an N, so all of it goes through the byte walker
+    data = b">polyA_with_N\n" + (b"A" * 40 + b"N" + b"A" * 39 + b"\n") * 400_000
+    counts, freq, totals, status = eng.count_buffers([data], k=7)
+    ref = c_oracle.count_buffer(data, 7)
+    assert status[0] == 0 and np.array_equal(counts[0], ref)
 
 
 # ---- FASTQ (BASELINE.json configs[3]: process_query_data preprocessing path) -----------------------------------

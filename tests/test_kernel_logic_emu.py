@@ -99,6 +99,14 @@ def test_emulated_linegrid_u16_overflow_is_detected_and_recounted(tmp_path):
     for grid, thr in ((1, 64), (3, 32)):
         tot, counts, _ = run_emu(7, thr, grid, False, 64, [p], linegrid=True)[0]
         assert np.array_equal(counts, ref)
+    # the rare-path ("singles") histogram has 16-bit halves too: 2,500 lines that each hold an N send > 65,535
+    # identical 7-mers through the byte walker
+    data = (">polyA_with_N\n" + ("A" * 40 + "N" + "A" * 39 + "\n") * 2500).encode()
+    open(p, "wb").write(data)
+    ref = o.canonical_counts_bytes(data, 7)
+    assert int(ref.max()) > 2 * 65535
+    tot, counts, _ = run_emu(7, 64, 1, False, 64, [p], linegrid=True)[0]
+    assert np.array_equal(counts, ref)
 
 
 def test_emulated_fastq_fuzz(tmp_path):

@@ -6,6 +6,8 @@
 // bytes, bases per SM-clock (SM clock measured with clock64 inside the kernel) and ms.
 #define KF_PIECE_TIMING 1
 #include "kf_kernels.cuh"
+#include "kfcount.h"
+#include <thread>
 
 #include <cstdio>
 #include <cstdlib>
@@ -160,7 +162,7 @@ template <int THREADS>
 void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
-    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
     auto kern = count_fasta_lines_kernel<80, THREADS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t n_chunks = (uint32_t)(bytes / CHUNK);
@@ -190,7 +192,7 @@ void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     for (int it = 0; it < 5; it++) {
         CK(cudaMemset(d_fwd, 0, (size_t)sms * 16384 * 8));
         CK(cudaEventRecord(e0));
-        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, d_scr, 1, d_wc);
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, 1, d_wc);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (it >= 1 && ms < best) best = ms;
@@ -228,20 +230,36 @@ __global__ void gen_fasta_files(uint8_t *arena, size_t file_bytes, size_t slot, 
 }
 
 template <int THREADS>
-void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms) {
+void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms, int max_contigs = 0, int n_runs = 0, long long bases = 0) {
     using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
-    const size_t smem = 32768 * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (2 * NW + 4) * sizeof(uint32_t);
+    const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
     auto kern = count_fasta_lines_kernel<80, THREADS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const size_t slot = (arena_bytes / nfiles) / CHUNK * CHUNK;
-    const size_t file_bytes = slot - 100;
-    gen_fasta_files<<<sms * 8, 256>>>(arena, file_bytes, slot, nfiles);
+    size_t slot = (arena_bytes / nfiles) / CHUNK * CHUNK;
+    size_t file_bytes = slot - 100;
+    std::vector<uint64_t> flen;
+    if (max_contigs > 0) {
+        // realistic files from the library's generator (contigs, N runs); every file in a slot of the largest size
+        flen.resize(nfiles);
+        size_t mx = 0;
+        for (int f = 0; f < nfiles; f++) { flen[f] = (uint64_t)kf_synth_fasta_ex(1, f, bases, 80, max_contigs, n_runs, nullptr, 0); mx = std::max<size_t>(mx, flen[f]); }
+        slot = (mx + CHUNK - 1) / CHUNK * CHUNK;
+        if ((size_t)nfiles * slot > arena_bytes) { printf("arena too small for synthetic mode\n"); return; }
+        std::vector<uint8_t> host((size_t)nfiles * slot, 0);
+        std::vector<std::thread> th;
+        for (int w = 0; w < 16; w++) th.emplace_back([&, w]() { for (int f = w; f < nfiles; f += 16) kf_synth_fasta_ex(1, f, bases, 80, max_contigs, n_runs, host.data() + (size_t)f * slot, flen[f]); });
+        for (auto &t : th) t.join();
+        CK(cudaMemcpy(arena, host.data(), host.size(), cudaMemcpyHostToDevice));
+        file_bytes = mx;
+    } else {
+        gen_fasta_files<<<sms * 8, 256>>>(arena, file_bytes, slot, nfiles);
+    }
     CK(cudaDeviceSynchronize());
     const uint64_t total_chunks = (uint64_t)nfiles * (slot / CHUNK);
     std::vector<Tile> tiles; std::vector<int> cta_begin(sms + 1, 0);
     std::vector<uint64_t> off(nfiles), len(nfiles); std::vector<uint32_t> P(nfiles, 81);
-    for (int f = 0; f < nfiles; f++) { off[f] = (uint64_t)f * slot; len[f] = file_bytes; }
+    for (int f = 0; f < nfiles; f++) { off[f] = (uint64_t)f * slot; len[f] = flen.empty() ? file_bytes : flen[f]; }
     {
         uint64_t done = 0; int cta = 0;
         auto hi = [&](int b) { return total_chunks * (uint64_t)(b + 1) / (uint64_t)sms; };
@@ -285,12 +303,12 @@ void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms) {
     CK(cudaMalloc(&d_scr, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_scr, 0, (size_t)sms * 16384 * 8));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best = 1e30f;
-    unsigned long long tm[8] = {0}, zero[8] = {0};
+    unsigned long long tm[16] = {0}, zero[16] = {0};
     for (int it = 0; it < 4; it++) {
         CK(cudaMemset(d_fwd, 0, nrows * 16384 * 8));
         CK(cudaMemcpyToSymbol(g_piece_timing, zero, sizeof zero));
         CK(cudaEventRecord(e0));
-        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, d_scr, 1, d_wc);
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, 1, d_wc);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (it >= 1 && ms < best) { best = ms; CK(cudaMemcpyFromSymbol(tm, g_piece_timing, sizeof tm)); }
@@ -299,6 +317,9 @@ void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms) {
     printf("files=%5d x %8zu B  %7.3f ms  %7.1f GB/s | per CTA: total %.0f kclk, pieces %.1f | per piece: units %.1f kclk/warp, wait+checksum %.1f kclk/warp, "
            "fold %.1f kclk/warp, zero %.1f kclk/warp, anchor %.1f kclk\n", nfiles, file_bytes, best, bytes / best / 1e6, tm[4] / (double)sms / 1e3, pieces / sms,
            tm[0] / pieces / NW / 1e3, tm[1] / pieces / NW / 1e3, tm[6] / pieces / NW / 1e3, tm[2] / pieces / NW / 1e3, tm[5] / pieces / 1e3);
+    printf("      windows: clean %llu x %.2f kclk | with a dirty lane %llu x %.2f kclk | grid breaks %llu: generic region %.2f kclk + next-line search %.2f kclk each\n",
+           tm[8], tm[8] ? tm[9] / (double)tm[8] / 1e3 : 0.0, tm[10], tm[10] ? tm[11] / (double)tm[10] / 1e3 : 0.0, tm[12],
+           tm[12] ? tm[13] / (double)tm[12] / 1e3 : 0.0, tm[12] ? tm[14] / (double)tm[12] / 1e3 : 0.0);
     cudaFree(d_tiles); cudaFree(d_cb); cudaFree(d_P); cudaFree(d_off); cudaFree(d_len); cudaFree(d_fwd); cudaFree(d_scr); cudaFree(d_wc);
 }
 
@@ -327,6 +348,10 @@ int main(int argc, char **argv) {
     run_lg<640>(arena, bytes, sms);
     run_lg<768>(arena, bytes, sms);
     for (int nf : {148, 1000, 4000}) run_lg_files<512>(arena, bytes, nf, sms);
+    run_lg_files<512>(arena, bytes, 296, sms, 1, 0, 5000000);
+    run_lg_files<512>(arena, bytes, 296, sms, 50, 0, 5000000);
+    run_lg_files<512>(arena, bytes, 296, sms, 1, 10, 5000000);
+    run_lg_files<512>(arena, bytes, 296, sms, 50, 10, 5000000);
     printf("done\n");
     return 0;
 }
