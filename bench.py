@@ -69,7 +69,7 @@ def generate_genomes(engine, ids, n_bases, threads, pinned=True):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled every 10 ms over the timed region through NVML (the same
+    """SM clock and throttle reasons sampled every 2 ms over the timed region through NVML (the same
     counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; B200_PROFILING.md recipe)."""
 
     def __init__(self, device):
@@ -108,7 +108,7 @@ class ClockSampler:
                     except Exception as e:  # pragma: no cover
                         self.err = repr(e)
                         return
-                    time.sleep(0.01)
+                    time.sleep(0.002)
 
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
@@ -149,6 +149,11 @@ def cpu_reference_run(engine, n_bases, k, steps, warmup, budget_s_per_step=2.0):
     return gbases, dt / steps * 1e3, threads, S
 
 
+def workload_name(genomes, bases, k, world):
+    return ("%d synthetic bacterial-size genomes per GPU x %d bases (80-col FASTA, 1-50 contigs, 10 N-runs), k=%d; "
+            "BASELINE.json configs[%d]" % (genomes, bases, k, 1 if world == 1 else 2))
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -165,9 +170,11 @@ def main():
             "impl": "reference", "metric": METRIC, "value": gb, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 counts / f64 frequencies", "data": "synthetic",
-            "config": {"workload": "synthetic bacterial-size genomes (%d bases, 80-col FASTA), k=%d, CPU restatement "
-                                   "of jellyfish count -C + dump + normalise (Jellyfish binary absent from the image)"
-                                   % (args.bases, args.k)},
+            "config": {"workload": workload_name(args.genomes, args.bases, args.k, args.gpus),
+                       "genomes_per_gpu": args.genomes, "bases_per_genome": args.bases, "k": args.k,
+                       "reference_arm": "CPU restatement of jellyfish count -C + dump -c + vocabulary merge + normalise "
+                                        "(oracle/kf_oracle.c; the Jellyfish binary is not in the image), all host threads, "
+                                        "each step a bounded sample of the workload: " + sample},
             "cpu_baseline": {"value": gb, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": gb, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -276,19 +283,28 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         alg_bytes = file_bytes + G * V * 4 + G * V * 8          # BASELINE.md section 3, per rank
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this
+        # command (tools/ncu_summary.py writes the file); only quoted when it was taken on the same workload
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath))
+            if t.get("genomes") == G and t.get("bases") == NB and t.get("k") == k:
+                traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
         achieved = alg_bytes / (float(kms.item()) * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 shared-memory counts -> u64 counts, f64 frequencies", "data": "synthetic",
-            "config": {"workload": "%d synthetic bacterial-size genomes per GPU x %d bases (80-col FASTA, 1-50 contigs, "
-                                   "10 N-runs), k=%d; BASELINE.json configs[%d]" % (G, NB, k, 1 if world == 1 else 2),
+            "config": {"workload": workload_name(G, NB, k, world),
                        "genomes_per_gpu": G, "bases_per_genome": NB, "k": k, "file_bytes_per_gpu": int(file_bytes),
                        "l2_policy": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed" % (file_bytes / 1e9),
                        "parallelism": "genome-sharded, one process per GPU, no collective on the counting path"
                                       + ("; NCCL all-gather of the [N,8192] fp32 matrix inside the step" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "count_fasta_smem_kernel", "kernel_ms": float(kms.item()),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "count_fasta_lines_kernel<80,512> (+ width probe; the 60/70-column and generic launches "
+                                   "exit at once on this input)", "kernel_ms": float(kms.item()),
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,

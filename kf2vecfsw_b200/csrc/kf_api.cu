@@ -352,17 +352,23 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     // forward-count workspace: u64 rows (see build_rows) for k <= 7, one u32 row per file for k >= 8
     const size_t fwd_bytes = smem_path ? (size_t)g.pc_rows * NB * sizeof(unsigned long long) : (size_t)nf * NB * sizeof(uint32_t);
     if ((rc = ensure(g.d_fwd, g.fwd_cap, fwd_bytes)) != KF_OK) return rc;
-    CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));
+    if (!smem_path) CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));   // (k <= 7: the probe kernel zeroes what needs it)
     const bool force_walker = (flags & KF_FLAG_FORCE_WALKER) != 0;
     const bool use_lg = smem_path && k == 7 && !force_walker && !(flags & KF_FLAG_NO_LINEGRID);
-    if (g.pc_ntiles > 0) {
+    if (smem_path) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
-        // line width per file (0 = generic kernel), then one line-grid launch per supported width
+        // line width per file (0 = generic kernel) + zeroing of the rows the line kernel will not write
         CK(cudaMemsetAsync(g.d_width_counts, 0, 4 * sizeof(uint32_t), s));
         probe_line_width_kernel<<<(f1 + 3) / 4, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, (int)f1,
-                                                                use_lg ? 0u : 1u, g.d_file_P, g.d_width_counts);
+                                                                use_lg ? 0u : 1u, g.d_file_P, g.d_width_counts,
+                                                                (unsigned long long *)g.d_fwd, g.d_file_row, (uint32_t)NB);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(g.ev_k1, s));
+        g.ev_valid = true;
         g.last_launches++;
+    }
+    if (g.pc_ntiles > 0) {
+        if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         if (use_lg) {
             rc = launch_linegrid<80>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
@@ -389,11 +395,12 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         g.last_launches += 3;
         g.fq_err_n = (int)f1;
     }
-    if (smem_path)
-        fold_normalize_kernel<unsigned long long><<<nf, 1024, 0, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
-                                                                       f0, (use_lg && g.pc_ntiles > 0) ? g.d_file_P : nullptr, g.d_file_row,
-                                                                       d_counts, d_freq, d_feat, d_totals);
-    else
+    if (smem_path) {
+        const size_t fsm = NB * sizeof(unsigned long long);
+        CK(cudaFuncSetAttribute(fold_normalize_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        fold_normalize_smem_kernel<<<nf, 1024, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
+                                                          use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
+    } else
         fold_normalize_kernel<uint32_t><<<nf, 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, nullptr, nullptr,
                                                              d_counts, d_freq, d_feat, d_totals);
     CK(cudaGetLastError());

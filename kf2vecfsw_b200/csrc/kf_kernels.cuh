@@ -1092,7 +1092,8 @@ __global__ void __launch_bounds__(128)
 probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
                         const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
                         uint32_t force_generic, uint32_t *__restrict__ file_P,
-                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80 */) {
+                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80 */,
+                        unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row, uint32_t row_bins) {
     const int lane = threadIdx.x & 31;
     const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (f >= n) return;
@@ -1126,6 +1127,14 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
     if (lane == 0) {
         file_P[f] = P;
         atomicAdd(width_counts + (P ? (P - 51) / 10 : 0), 1u);
+    }
+    // Forward rows: the line kernel WRITES every bin of the rows of the files it takes; every other file's rows are
+    // added to with atomics (generic / FASTQ kernels) or never touched (unsupported input), so they are zeroed here --
+    // this replaces a memset of the whole workspace.
+    if (P == 0 && g_fwd != nullptr) {
+        ulonglong2 *row = reinterpret_cast<ulonglong2 *>(g_fwd + (size_t)file_row[f] * row_bins);
+        const size_t n16 = (size_t)(file_row[f + 1] - file_row[f]) * row_bins / 2;
+        for (size_t i = lane; i < n16; i += 32) row[i] = make_ulonglong2(0ull, 0ull);
     }
 }
 
@@ -1196,16 +1205,28 @@ __device__ __forceinline__ void fastq_process_range(const uint8_t *__restrict__ 
                 const FqLane nxt = fq_decode16(wnxt);
                 // ---- line type at this lane's first byte: carry + '\n' in the lanes before ----
                 const uint32_t nlc = (uint32_t)__popc(cur.nl);
-                uint32_t incl = nlc;
-                if (__ballot_sync(FULL, nlc != 0)) {
+                uint32_t excl, total_nl;
+                {
+                    // a 16-byte lane rarely holds more than two '\n' ("\n+\n"): three ballots give the prefix sum, a
+                    // shuffle scan covers the rest (reads shorter than a handful of bases)
+                    const unsigned b1 = __ballot_sync(FULL, nlc >= 1), b2 = __ballot_sync(FULL, nlc >= 2), b3 = __ballot_sync(FULL, nlc >= 3);
+                    if (__ballot_sync(FULL, nlc >= 4) == 0) {
+                        const unsigned lt = (1u << lane) - 1u;
+                        excl = (uint32_t)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt));
+                        total_nl = (uint32_t)(__popc(b1) + __popc(b2) + __popc(b3));
+                    } else {
+                        uint32_t incl = nlc;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t v = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += v;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        excl = incl - nlc;
+                        total_nl = __shfl_sync(FULL, incl, 31);
                     }
                 }
-                const uint32_t t0 = (carry + incl - nlc) & 3u;
-                carry = (carry + __shfl_sync(FULL, incl, 31)) & 3u;
+                const uint32_t t0 = (carry + excl) & 3u;
+                carry = (carry + total_nl) & 3u;
                 // ---- what the next lane starts with: first byte (for the '+' check), bases, bad bits ----
                 const uint32_t myfirst = wcur.x & 0xFFu, nxfirst = wnxt.x & 0xFFu;
                 const uint32_t nb_first = __shfl_sync(FULL, lane == 0 ? nxfirst : myfirst, (lane + 1) & 31);
@@ -1317,21 +1338,27 @@ count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
                         const uint32_t *__restrict__ file_row, unsigned long long *__restrict__ fq_err) {
     KF_DYN_SMEM(uint32_t, hist);
     constexpr int NB = 1 << (2 * K);
-    constexpr int NWARPS = THREADS / 32;
+    __shared__ uint32_t s_next;
     for (int i = threadIdx.x; i < NB; i += THREADS) hist[i] = 0;
+    if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
     const SmemSink emit = make_smem_sink(hist);
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1;) {
         const uint32_t file = tiles[t].file;
         int te = t + 1;
         while (te < t1 && tiles[te].file == file) ++te;
-        for (int tt = t + warp; tt < te; tt += NWARPS) {
+        // the warps take the segment's tiles from a shared counter (tiles differ in how much sequence they hold)
+        for (;;) {
+            int tt = 0;
+            if ((threadIdx.x & 31) == 0) tt = t + (int)atomicAdd(&s_next, 1u);
+            tt = __shfl_sync(FULL, tt, 0);
+            if (tt >= te) break;
             const Tile T = tiles[tt];
-            fastq_process_range<K, 3>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[tt], emit, fq_err + file);
+            fastq_process_range<K, 4>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[tt], emit, fq_err + file);
         }
         __syncthreads();
+        if (threadIdx.x == 0) s_next = 0;
         unsigned long long *g = g_fwd + (size_t)file_row[file] * NB;
         for (int i = threadIdx.x; i < NB; i += THREADS) {
             const uint32_t v = hist[i];
@@ -1387,6 +1414,72 @@ __device__ __forceinline__ uint32_t revcomp_std(uint32_t x, int k) {
     return y >> (32 - 2 * k);
 }
 __device__ __forceinline__ uint32_t std_to_gray(uint32_t x) { return x ^ ((x >> 1) & 0x55555555u); }
+
+// k <= 7: the file's rows are summed with coalesced loads into shared memory (4^k u64, 128 KB at k = 7), then the
+// canonical gather, the total and the normalisation read from there.
+__global__ void __launch_bounds__(1024)
+fold_normalize_smem_kernel(const unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ canon, int k, long long V,
+                           uint32_t flags, const uint32_t *__restrict__ file_P, const uint32_t *__restrict__ file_row,
+                           unsigned long long *__restrict__ counts, double *__restrict__ freq, float *__restrict__ feat,
+                           unsigned long long *__restrict__ totals) {
+    KF_DYN_SMEM(unsigned long long, row);
+    const uint32_t NB = 1u << (2 * k);
+    const uint32_t file = blockIdx.x;
+    const uint32_t row0 = file_row[file], nrows = file_row[file + 1] - row0;
+    const unsigned long long *g = g_fwd + (size_t)row0 * NB;
+    const size_t orow = (size_t)file * (size_t)V;
+    __shared__ unsigned long long red[32];
+    __shared__ unsigned long long s_total;
+    if (NB >= 2) {
+        for (uint32_t i = threadIdx.x; i < NB / 2; i += blockDim.x) {
+            ulonglong2 a = make_ulonglong2(0ull, 0ull);
+            for (uint32_t r = 0; r < nrows; r++) {
+                const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(g + (size_t)r * NB)[i];
+                a.x += v.x;
+                a.y += v.y;
+            }
+            row[2 * i] = a.x;
+            row[2 * i + 1] = a.y;
+        }
+    }
+    __syncthreads();
+    // rows written by the line kernel (k = 7, file_P != 0) hold the 7-mers with their digits reversed
+    const bool rev = file_P != nullptr && file_P[file] != 0;
+    auto canon_count = [&](long long i) -> unsigned long long {
+        const uint32_t m = canon[i];
+        const uint32_t r = revcomp_std(m, k);
+        const uint32_t g0 = std_to_gray(m), g1 = std_to_gray(r);
+        unsigned long long c = row[rev ? digit_rev7(g0) : g0];
+        if (r != m) c += row[rev ? digit_rev7(g1) : g1];
+        return c;
+    };
+    unsigned long long local = 0;
+    for (long long i = threadIdx.x; i < V; i += blockDim.x) {
+        const unsigned long long c = canon_count(i);
+        if (counts) counts[orow + i] = c;
+        local += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (threadIdx.x == 0) { s_total = v; if (totals) totals[file] = v; }
+    }
+    __syncthreads();
+    if (!freq && !feat) return;
+    const bool pc = flags & 1u, raw = flags & 2u;
+    const double denom = (double)s_total + (pc ? 0.5 * (double)V : 0.0);
+    for (long long i = threadIdx.x; i < V; i += blockDim.x) {
+        double v = (double)canon_count(i) + (pc ? 0.5 : 0.0);
+        if (!raw) v = v / denom;   // IEEE fp64 division: correctly rounded, bit-exact with numpy
+        if (freq) freq[orow + i] = v;
+        if (feat) feat[orow + i] = (float)(v * 1e4);   // train_classifier_model.py:149,323
+    }
+}
 
 template <typename FwdT>
 __global__ void __launch_bounds__(1024)

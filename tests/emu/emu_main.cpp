@@ -110,14 +110,14 @@ int main(int argc, char **argv) {
             }
         for (int f = 0; f < n; f++) file_row[f + 1] = file_row[f] + std::max(1u, cnt[f]);
     }
-    std::vector<unsigned long long> fwd((size_t)file_row[n] * NB, 0);
+    std::vector<unsigned long long> fwd((size_t)file_row[n] * NB, 0xDEADBEEFCAFEull);   // garbage: every row must be written or zeroed by the kernels
     // same launch sequence as kf_api.cu:run_files -- probe, one line-grid launch per width, generic kernel
     std::vector<uint8_t> formats(n);
     for (int i = 0; i < n; i++) formats[i] = len[i] ? arena[off[i]] : 0;
     std::vector<uint32_t> file_P(n, 0);
     std::vector<uint32_t> wc(4, 0);
     const bool lg = use_lg && k == 7 && !fw;
-    emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data()); });
+    emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data(), fwd.data(), file_row.data(), (uint32_t)NB); });
     if (lg) {
         if (threads == 64) {
             run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
@@ -163,7 +163,7 @@ int main(int argc, char **argv) {
     long long V = (long long)canon.size();
     std::vector<unsigned long long> counts((size_t)n * V), totals(n);
     std::vector<double> freq((size_t)n * V);
-    emu::launch(n, 64, 0, [&]() { fold_normalize_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data()); });
+    emu::launch(n, 64, NB * sizeof(unsigned long long), [&]() { fold_normalize_smem_kernel(fwd.data(), canon.data(), k, V, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data()); });
     for (int f = 0; f < n; f++) {
         printf("%llu", totals[f]);
         for (long long i = 0; i < V; i++) printf(" %llu", counts[(size_t)f * V + i]);

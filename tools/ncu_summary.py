@@ -26,3 +26,21 @@ for r in rows[2:]:
     for k, v in sorted(st, key=lambda x: -x[1])[:10]:
         print("     %-40s %6.1f %%" % (k.replace("smsp__pcsamp_warps_issue_stalled_", ""), 100 * v / tot))
     ops = [(k, float(d[k])) for k in hdr if k.startswith("sass__inst_executed_per_opcode") or k.startswith("smsp__sass_inst_executed_op_")]
+
+if len(sys.argv) >= 6 and sys.argv[2] == "--traffic-json":
+    # python tools/ncu_summary.py rep --traffic-json GENOMES BASES K  -> profiles/traffic.json for bench.py's roofline.traffic
+    import json, os
+    G, NB, K = int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    best = None
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        if "count_fasta_lines_kernel<80" in d["Kernel Name"]:
+            units = dict(zip(hdr, rows[1]))
+            def to_bytes(key):
+                v, u = float(d[key]), units[key]
+                return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+            best = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+    out = {"genomes": G, "bases": NB, "k": K, "dram_bytes_per_launch": best,
+           "source": "ncu --set full --clock-control none, count_fasta_lines_kernel<80,512>, dram__bytes_read.sum + dram__bytes_write.sum (%s)" % os.path.basename(rep)}
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json"), "w"), indent=1)
+    print(out)
