@@ -41,11 +41,9 @@ struct Ctx {
     uint32_t *d_file_row = nullptr; size_t frow_cap = 0;          // first forward-count row of every file (+ total)
     uint32_t *d_cta_first_rank = nullptr; size_t cfr_cap = 0;    // per line-kernel CTA: how many earlier CTAs hold a piece of its first file
     uint32_t pc_rows = 0;
-    // FASTQ plan: 32 KiB tiles, their '\n' counts / line types, per-file tile ranges, layout-violation offsets
+    // FASTQ plan: 128 KiB tiles (32 lane ranges), layout-violation offsets
     Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
     int *d_fq_cta_begin = nullptr; size_t fq_cta_cap = 0;
-    uint32_t *d_fq_tile_nl = nullptr; size_t fq_nl_cap = 0;
-    int *d_fq_file_tile_begin = nullptr; size_t fq_ftb_cap = 0;
     unsigned long long *d_fq_err = nullptr; size_t fq_err_cap = 0;
     int pc_fq_ntiles = 0, pc_fq_nfiles = 0;
     std::vector<unsigned long long> h_fq_err;     // copied back by fetch_status
@@ -164,9 +162,9 @@ void build_rows(const std::vector<Tile> &tiles, const std::vector<int> &cta_begi
     for (uint32_t f = 0; f < f1; f++) file_row[f + 1] = file_row[f] + nrows[f];
 }
 
-// FASTQ files [f0,f1): tiles of FQ_TILE_CHUNKS chunks in file order, contiguous tile-balanced CTA ranges, and the
-// tile range of every FASTQ file (for the per-file running newline count).
-constexpr uint32_t FQ_TILE_CHUNKS = 64;   // 32 KiB
+// FASTQ files [f0,f1): tiles of FQ_TILE_CHUNKS chunks in file order, contiguous tile-balanced CTA ranges (and the tile
+// range of every FASTQ file).
+constexpr uint32_t FQ_TILE_CHUNKS = 32 * FQ_LANE_BYTES / CHUNK;   // 128 KiB: one lane range per lane
 void build_fastq_plan(const uint64_t *offsets, const uint64_t *lens, const uint8_t *formats, uint32_t f0, uint32_t f1,
                       int grid, std::vector<Tile> &tiles, std::vector<int> &cta_begin, std::vector<int> &file_tile_begin) {
     tiles.clear();
@@ -195,10 +193,10 @@ int launch_fastq(const uint8_t *d_arena, int grid, uint32_t file_base, cudaStrea
         constexpr size_t smem = sizeof(uint32_t) << (2 * K);
         auto kern = count_fastq_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl, (unsigned long long *)g.d_fwd,
-                                              g.d_file_row, g.d_fq_err);
+        kern<<<grid, THREADS_SMEM, smem, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_file_off, g.d_file_len,
+                                              (unsigned long long *)g.d_fwd, g.d_file_row, g.d_fq_err);
     } else {
-        count_fastq_gmem_kernel<K, THREADS_GMEM><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_tile_nl,
+        count_fastq_gmem_kernel<K, THREADS_GMEM><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, g.d_file_off, g.d_file_len,
                                                                               (uint32_t *)g.d_fwd, file_base, g.d_fq_err);
     }
     CK(cudaGetLastError());
@@ -328,11 +326,8 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             if (g.pc_fq_ntiles > 0) {
                 if ((rc = ensure(g.d_fq_tiles, g.fq_tiles_cap, fq_tiles.size() * sizeof(Tile))) != KF_OK) return rc;
                 if ((rc = ensure(g.d_fq_cta_begin, g.fq_cta_cap, fq_cta_begin.size() * sizeof(int))) != KF_OK) return rc;
-                if ((rc = ensure(g.d_fq_tile_nl, g.fq_nl_cap, fq_tiles.size() * sizeof(uint32_t))) != KF_OK) return rc;
-                if ((rc = ensure(g.d_fq_file_tile_begin, g.fq_ftb_cap, fq_ftb.size() * sizeof(int))) != KF_OK) return rc;
                 CK(cudaMemcpy(g.d_fq_tiles, fq_tiles.data(), fq_tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
                 CK(cudaMemcpy(g.d_fq_cta_begin, fq_cta_begin.data(), fq_cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-                CK(cudaMemcpy(g.d_fq_file_tile_begin, fq_ftb.data(), fq_ftb.size() * sizeof(int), cudaMemcpyHostToDevice));
             }
         }
         if (smem_path) {
@@ -385,14 +380,10 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     }
     if (g.pc_fq_ntiles > 0) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
-        fastq_tile_newlines_kernel<<<g.sm_count * 8, 256, 0, s>>>(d_arena, g.d_fq_tiles, g.pc_fq_ntiles, g.d_fq_tile_nl);
-        CK(cudaGetLastError());
-        fastq_tile_types_kernel<<<g.pc_fq_nfiles, 1024, 0, s>>>(g.d_fq_tile_nl, g.d_fq_file_tile_begin);
-        CK(cudaGetLastError());
         if ((rc = launch_fastq_k(k, d_arena, grid, f0, s)) != KF_OK) return rc;
         CK(cudaEventRecord(g.ev_k1, s));
         g.ev_valid = true;
-        g.last_launches += 3;
+        g.last_launches += 1;
         g.fq_err_n = (int)f1;
     }
     if (smem_path) {
@@ -476,7 +467,7 @@ int kf_shutdown(void) {
     cudaDeviceSynchronize();
     cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
     cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals); cudaFree(g.d_seq); cudaFree(g.d_win_off); cudaFree(g.d_win_len);
-    cudaFree(g.d_fq_tiles); cudaFree(g.d_fq_cta_begin); cudaFree(g.d_fq_tile_nl); cudaFree(g.d_fq_file_tile_begin); cudaFree(g.d_fq_err);
+    cudaFree(g.d_fq_tiles); cudaFree(g.d_fq_cta_begin); cudaFree(g.d_fq_err);
     cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_file_row); cudaFree(g.d_cta_first_rank); cudaFree(g.d_width_counts);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);

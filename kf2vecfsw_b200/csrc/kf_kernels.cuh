@@ -1139,29 +1139,33 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
 }
 
 // ================================================================================================
-// FASTQ (4-line records): line type from newline parity, mask-based k-mer validity, no byte walker
+// FASTQ (4-line records): every lane chases its own records
 // ================================================================================================
-// A 4-line FASTQ file is a sequence of lines of type 0 '@header', 1 sequence, 2 '+...', 3 qualities, so the
-// type of a byte is (number of '\n' before it) mod 4.  Header and quality lines may hold ANY byte but '\n'
-// (qualities legitimately contain A/C/G/T and may begin with '@' or '+'), so nothing about the record
-// structure can be read off the bytes themselves: the newline count is the only sound source.  It is made
-// available in two steps: fastq_tile_newlines_kernel counts the '\n' of every 32 KiB tile, fastq_tile_types_kernel
-// turns the per-file running sum into the line type at each tile's first byte, and the counting kernel carries
-// the count from there (warp prefix sum per 512-byte chunk).
-//
-// Per 16-byte lane: bad16 has a bit for every byte that is not "A/C/G/T inside a sequence line"; the k-mer that
-// starts at byte j is counted iff bad[j .. j+K-1] is clear (the K-1 look-ahead bits and bases come from the
-// next lane by shuffle).  In 4-line FASTQ a '\n' ends the sequence, so unlike FASTA nothing is ever deleted
-// from the base stream and every lane takes the same branch-free path.
-// The layout is checked as a side effect: the line after every sequence line must begin with '+'; the lowest
-// offending byte offset per file lands in fq_err (the host maps it to KF_ERR_FASTQ).
+// Header and quality lines may hold ANY byte but '\n' (qualities legitimately contain A/C/G/T and may begin with '@'
+// or '+'), so a record's structure cannot be read off isolated bytes.  What 4-line FASTQ does guarantee -- and what
+// Jellyfish relies on as well -- is that the quality line is exactly as long as the sequence line.  So a lane that
+// stands on a record start can walk the file alone: header line up to its '\n', sequence line (counted), '+' line up to
+// its '\n', then JUMP over the quality line by length.  More than half of the file (qualities) is never even loaded.
+//   work split : a tile = 32 lane ranges of FQ_LANE_BYTES; a lane owns the records whose header starts in its range and
+//                finishes the last one beyond the range end.
+//   sync       : a range start is put on a record boundary with a rule that is exact for 4-line FASTQ: the first line
+//                start s with byte '@' whose second-next line starts with '+'.  (A quality line that begins with '@' is
+//                followed by a header and then a SEQUENCE line, which never begins with '+'.)
+//   inner loop : one 16-byte piece per iteration, the same code for every lane whatever its state (header / sequence /
+//                plus line), so the lanes of a warp stay converged although they sit in different records: decode 16
+//                bytes + 8 look-ahead bytes, byte masks for "not A/C/G/T" and '\n', a few state transitions, then the
+//                k-mer that starts at byte j counts iff bad[j .. j+K) is clear.
+//   layout     : the line after a sequence line must begin with '+', the byte after the skipped quality line must be
+//                '\n' followed by '@' (or the end of the file); the lowest offending offset per file lands in fq_err and
+//                the host maps it to KF_ERR_FASTQ.
+constexpr uint32_t FQ_LANE_BYTES = 4096;
 
-struct FqLane {
-    uint32_t bits;    // 16 bases, 2 bits each, first base in bits 31:30 (garbage where the byte is not a base)
-    uint32_t inv;     // 16-bit: byte is not A/C/G/T
-    uint32_t nl;      // 16-bit: byte is '\n' (subset of inv)
+struct FqPiece {
+    uint32_t bits;   // 16 bases, 2 bits each, first base in bits 31:30 (garbage where the byte is not a base)
+    uint32_t inv;    // 16-bit: byte is not A/C/G/T
+    uint32_t nl;     // 16-bit: byte is '\n' (subset of inv)
 };
-__device__ __forceinline__ FqLane fq_decode16(const uint4 w) {
+__device__ __forceinline__ FqPiece fq_decode16(const uint4 w) {
     uint32_t p0, p1, p2, p3, V0, V1, V2, V3;
     decode_word(w.x, p0, V0);
     decode_word(w.y, p1, V1);
@@ -1169,7 +1173,7 @@ __device__ __forceinline__ FqLane fq_decode16(const uint4 w) {
     decode_word(w.w, p3, V3);
     const uint32_t r1 = __byte_perm(p3, p2, 0x0073);
     const uint32_t r2 = __byte_perm(p1, p0, 0x0073);
-    FqLane L;
+    FqPiece L;
     L.bits = __byte_perm(r1, r2, 0x5410);
     L.inv = 0;
     L.nl = 0;
@@ -1181,181 +1185,188 @@ __device__ __forceinline__ FqLane fq_decode16(const uint4 w) {
     return L;
 }
 
-// One warp over the chunks [c0, c1) of a FASTQ file; type0 = line type at the first byte of chunk c0.
-// fq_err: lowest byte offset (arena coordinates) where the 4-line layout is violated.
-template <int K, int PF, class Sink>
-__device__ __forceinline__ void fastq_process_range(const uint8_t *__restrict__ arena, uint32_t c0, uint32_t c1, uint32_t type0,
-                                                    Sink sink, unsigned long long *fq_err) {
-    static_assert(PF >= 2 && PF <= 6, "prefetch depth");
-    const int lane = threadIdx.x & 31;
-    const GlobalSrc src{arena};
-    const uint32_t cmax = c1 + 1;   // the arena's NUL tail keeps chunk c1+1 in bounds
-    uint4 slot[PF];
-#pragma unroll
-    for (int i = 0; i < PF; i++) slot[i] = src.load16(min(c0 + i, cmax), lane);
-    FqLane cur = fq_decode16(slot[0]);
-    uint32_t carry = type0;   // line type at the first byte of the current chunk
-    for (uint32_t cg = c0; cg < c1; cg += PF) {
-#pragma unroll
-        for (int u = 0; u < PF; u++) {
-            const uint32_t c = cg + u;
-            if (c < c1) {
-                const uint4 wcur = slot[u];
-                const uint4 wnxt = slot[(u + 1) % PF];
-                const FqLane nxt = fq_decode16(wnxt);
-                // ---- line type at this lane's first byte: carry + '\n' in the lanes before ----
-                const uint32_t nlc = (uint32_t)__popc(cur.nl);
-                uint32_t excl, total_nl;
-                {
-                    // a 16-byte lane rarely holds more than two '\n' ("\n+\n"): three ballots give the prefix sum, a
-                    // shuffle scan covers the rest (reads shorter than a handful of bases)
-                    const unsigned b1 = __ballot_sync(FULL, nlc >= 1), b2 = __ballot_sync(FULL, nlc >= 2), b3 = __ballot_sync(FULL, nlc >= 3);
-                    if (__ballot_sync(FULL, nlc >= 4) == 0) {
-                        const unsigned lt = (1u << lane) - 1u;
-                        excl = (uint32_t)(__popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt));
-                        total_nl = (uint32_t)(__popc(b1) + __popc(b2) + __popc(b3));
-                    } else {
-                        uint32_t incl = nlc;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t v = __shfl_up_sync(FULL, incl, o);
-                            if (lane >= o) incl += v;
-                        }
-                        excl = incl - nlc;
-                        total_nl = __shfl_sync(FULL, incl, 31);
-                    }
-                }
-                const uint32_t t0 = (carry + excl) & 3u;
-                carry = (carry + total_nl) & 3u;
-                // ---- what the next lane starts with: first byte (for the '+' check), bases, bad bits ----
-                const uint32_t myfirst = wcur.x & 0xFFu, nxfirst = wnxt.x & 0xFFu;
-                const uint32_t nb_first = __shfl_sync(FULL, lane == 0 ? nxfirst : myfirst, (lane + 1) & 31);
-                // ---- bytes of this lane that belong to a sequence line ----
-                uint32_t seq = 0;
-                {
-                    uint32_t t = t0, start = 0, m = cur.nl;
-                    for (;;) {
-                        const uint32_t pos = m ? (uint32_t)(__ffs((int)m) - 1) : 16u;
-                        if (t == 1u) seq |= ((1u << pos) - 1u) & ~((1u << start) - 1u);
-                        if (!m) break;
-                        m &= m - 1u;
-                        start = pos + 1u;
-                        t = (t + 1u) & 3u;
-                        if (t == 2u) {   // a sequence line just ended: the next line must be the '+' line
-                            const uint32_t b = start < 16u ? byte_of(wcur, (int)start) : nb_first;
-                            if (b != (uint32_t)'+') atomicMin(fq_err, (unsigned long long)c * CHUNK + (unsigned long long)lane * 16 + start);
-                        }
-                    }
-                }
-                const uint32_t bad = (cur.inv | ~seq) & 0xFFFFu;
-                // the next lane's bad bits need ITS line types; only its bytes before its first '\n' matter here and
-                // they continue this lane's last line, so: type after my last byte == 1 and the byte is a base
-                const uint32_t t_end = (t0 + nlc) & 3u;
-                // next lane (or lane 0 of the next chunk): invalid-or-after-newline bits of its first bytes
-                const uint32_t my_lead = cur.inv | (cur.nl ? (0xFFFFu & ~((1u << (__ffs((int)cur.nl) - 1)) - 1u)) : 0u);
-                const uint32_t nx_lead = nxt.inv | (nxt.nl ? (0xFFFFu & ~((1u << (__ffs((int)nxt.nl) - 1)) - 1u)) : 0u);
-                const uint32_t nb_lead = __shfl_sync(FULL, lane == 0 ? nx_lead : my_lead, (lane + 1) & 31);
-                const uint32_t nb_bits = __shfl_sync(FULL, lane == 0 ? nxt.bits : cur.bits, (lane + 1) & 31);
-                // look-ahead bytes count only while the sequence line goes on: they do iff this lane ends inside one
-                const uint32_t ahead_bad = (t_end == 1u) ? nb_lead : 0xFFFFu;
-                uint32_t o = bad | (ahead_bad << 16);
-                {   // o[j] |= o[j+1 .. j+K-1]
-                    int cover = 1;
-#pragma unroll
-                    for (int it = 0; it < 4; it++) {
-                        if (cover < K) {
-                            const int s = (cover < K - cover) ? cover : K - cover;
-                            o |= o >> s;
-                            cover += s;
-                        }
-                    }
-                }
-                const uint32_t ok = ~o & 0xFFFFu;
-                if (ok) {
-                    const uint32_t hi = cur.bits, lo = nb_bits;
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if ((ok >> j) & 1u) sink(kmer_off_at<K>(hi, lo, j));
-                }
-                cur = nxt;
-                slot[u] = src.load16(min(c + PF, cmax), lane);
+// position of the first '\n' at or after p (p < end), or end.  16-byte pieces of the arena.
+__device__ __forceinline__ uint64_t fq_next_newline(const uint8_t *__restrict__ arena, uint64_t p, uint64_t end) {
+    while (p < end) {
+        const uint64_t a = p & ~15ull;
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
+        uint32_t m = newline_mask16(w) & ~((1u << (uint32_t)(p - a)) - 1u);
+        if (m) {
+            const uint64_t q = a + (uint32_t)(__ffs((int)m) - 1);
+            return q < end ? q : end;
+        }
+        p = a + 16;
+    }
+    return end;
+}
+
+// One lane: count the k-mers of every record whose header line starts in [X0, X1) of the file [F0, F1).
+template <int K, class Sink>
+__device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ arena, uint64_t F0, uint64_t F1, uint64_t X0,
+                                                   uint64_t X1, Sink sink, unsigned long long *fq_err) {
+    if (X0 >= F1) X0 = X1 = F1;
+    if (X1 > F1) X1 = F1;
+    // ---- put the range start on a record boundary ----
+    uint64_t pos = X0;          // a record (header line) start, once synchronised
+    bool run = X0 < X1;
+    if (run && X0 > F0) {
+        // line starts after X0 - 1: s1, s2, s3 ...; the first s_i that holds '@' while s_(i+2) holds '+'
+        uint64_t n = fq_next_newline(arena, X0 - 1, F1);
+        uint64_t s0 = n + 1;
+        uint64_t s1 = s0 < F1 ? fq_next_newline(arena, s0, F1) + 1 : F1 + 1;
+        run = false;
+        for (int it = 0; it < 8; it++) {
+            if (s0 >= X1 || s0 >= F1) break;
+            const uint64_t s2 = s1 < F1 ? fq_next_newline(arena, s1, F1) + 1 : F1 + 1;
+            // near the end of the file the second-next line may not exist: then s0 is a header iff the line after it
+            // (if any) is a sequence line, i.e. does not begin with '@'
+            const bool hdr = arena[s0] == (uint8_t)'@' &&
+                             (s2 < F1 ? arena[s2] == (uint8_t)'+' : (s1 >= F1 || arena[s1] != (uint8_t)'@'));
+            if (hdr) { pos = s0; run = true; break; }
+            s0 = s1;
+            s1 = s2;
+        }
+    }
+    // ---- the chain: one 16-byte piece per iteration ----
+    enum { HDR = 0, SEQ = 1, PLUS = 2 };
+    uint32_t st = HDR;
+    uint64_t seq_start = 0;     // first byte of the current sequence line
+    uint32_t seqlen = 0;        // its length in bytes once it has ended
+    bool fresh = true;          // pos is the first byte of a line whose first byte has to be checked
+    while (run) {
+        if (pos >= F1) break;
+        const uint64_t a = pos & ~15ull;
+        const uint32_t off = (uint32_t)(pos - a);
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
+        const uint4 wl = __ldg(reinterpret_cast<const uint4 *>(arena + a + 16));
+        FqPiece P = fq_decode16(w);
+        // look-ahead: the next 12 bytes are enough for K <= 12 (K - 1 <= 11)
+        uint32_t lbits, linv, lnl;
+        {
+            uint32_t q0, q1, q2, W0, W1, W2;
+            decode_word(wl.x, q0, W0);
+            decode_word(wl.y, q1, W1);
+            decode_word(wl.z, q2, W2);
+            const uint32_t r2 = __byte_perm(q1, q0, 0x0073);
+            lbits = __byte_perm(q2 >> 24, r2, 0x5400) & 0xFFFFFF00u;   // [q0.b3, q1.b3, q2.b3, 0]
+            linv = 0;
+            lnl = 0;
+            if (W0 | W1 | W2) {
+                linv = movemask4(nonzero_bytes(W0)) | (movemask4(nonzero_bytes(W1)) << 4) | (movemask4(nonzero_bytes(W2)) << 8);
+                lnl = (movemask4(~nonzero_bytes(wl.x ^ 0x0A0A0A0Au) & 0x80808080u)) | (movemask4(~nonzero_bytes(wl.y ^ 0x0A0A0A0Au) & 0x80808080u) << 4) |
+                      (movemask4(~nonzero_bytes(wl.z ^ 0x0A0A0A0Au) & 0x80808080u) << 8);
             }
         }
-    }
-}
-
-// '\n' count of every FASTQ tile (one warp per tile).
-__global__ void __launch_bounds__(256)
-fastq_tile_newlines_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, int n_tiles,
-                           uint32_t *__restrict__ tile_nl) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < n_tiles; t += gridDim.x * wpb) {
-        const Tile T = tiles[t];
-        const uint4 *p = reinterpret_cast<const uint4 *>(arena) + (size_t)T.first_chunk * 32 + lane;
-        uint32_t n = 0;
-#pragma unroll 4
-        for (uint32_t c = 0; c < T.n_chunks; c++) {
-            const uint4 w = __ldg(p + (size_t)c * 32);
-            n += (uint32_t)__popc(~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u) + (uint32_t)__popc(~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u) +
-                 (uint32_t)__popc(~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u) + (uint32_t)__popc(~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u);
+        // bytes at or beyond the end of the file behave like a '\n' followed by garbage
+        if (a + 16 > F1) { const uint32_t v = (uint32_t)(F1 - a); P.inv |= 0xFFFFu & ~((1u << v) - 1u); P.nl |= 1u << v; }
+        if (a + 28 > F1) {
+            const uint32_t v = F1 > a + 16 ? (uint32_t)(F1 - a - 16) : 0u;
+            linv |= 0xFFFu & ~((1u << v) - 1u);
+            lnl |= 1u << v;
         }
+        // ---- state transitions inside this piece; seqm = its bytes that belong to a sequence line ----
+        uint32_t cur = off, seqm = 0;
+        bool seq_runs_on = false;   // the sequence line continues into the next piece
+        bool jumped = false;
+        for (;;) {
+            if (fresh && cur < 16u) {
+                // first byte of a header / plus line
+                const uint32_t c = byte_of(w, (int)cur);
+                const uint64_t at = a + cur;
+                if (at < F1 && ((st == HDR && c != (uint32_t)'@') || (st == PLUS && c != (uint32_t)'+'))) {
+                    atomicMin(fq_err, at);
+                    run = false;
+                    break;
+                }
+                fresh = false;
+            }
+            if (cur >= 16u) break;
+            const uint32_t m = P.nl & ~((1u << cur) - 1u);
+            const uint32_t e = m ? (uint32_t)(__ffs((int)m) - 1) : 16u;   // this line's '\n' in the piece, or 16
+            if (st == SEQ) seqm |= ((1u << e) - 1u) & ~((1u << cur) - 1u);
+            if (e == 16u) { seq_runs_on = st == SEQ; break; }
+            cur = e + 1u;
+            if (st == HDR) {
+                if (a + e + 1 > F1) { run = false; break; }
+                st = SEQ;
+                seq_start = a + e + 1;
+            } else if (st == SEQ) {
+                seqlen = (uint32_t)(a + e - seq_start);
+                st = PLUS;
+                fresh = true;
+            } else {
+                // end of the plus line: jump over the quality line; the next record's header must follow
+                const uint64_t qstart = a + e + 1;
+                const uint64_t nxt = qstart + seqlen + 1;
+                if (nxt - 1 < F1 && arena[nxt - 1] != 0x0Au) { atomicMin(fq_err, nxt - 1); run = false; break; }
+                pos = nxt;
+                st = HDR;
+                fresh = true;
+                jumped = true;
+                if (pos >= X1) run = false;   // that record belongs to the next range
+                break;
+            }
+        }
+        // ---- count: k-mer at byte j iff bad[j .. j+K) clear; look-ahead bytes count only while the line runs on ----
+        if (seqm) {
+            const uint32_t bad = (P.inv | ~seqm) & 0xFFFFu;
+            uint32_t lbad = 0xFFFu;
+            if (seq_runs_on) lbad = linv | (lnl ? (0xFFFu & ~((1u << (__ffs((int)lnl) - 1)) - 1u)) : 0u);
+            uint32_t o = bad | (lbad << 16) | 0xF0000000u;
+            {
+                int cover = 1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
-        if (lane == 0) tile_nl[t] = n;
+                for (int it = 0; it < 4; it++) {
+                    if (cover < K) {
+                        const int sft = (cover < K - cover) ? cover : K - cover;
+                        o |= o >> sft;
+                        cover += sft;
+                    }
+                }
+            }
+            const uint32_t ok = ~o & 0xFFFFu;
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if ((ok >> j) & 1u) sink(kmer_off_at<K>(P.bits, lbits, j));
+            }
+        }
+        if (!jumped) pos = a + 16;
     }
 }
 
-// Line type at the first byte of every tile: running '\n' count of the file, mod 4.  One CTA per FASTQ file;
-// file_tile_begin[f] .. file_tile_begin[f+1] are its tiles (in file order).  In place: tile_nl -> type.
-__global__ void __launch_bounds__(1024)
-fastq_tile_types_kernel(uint32_t *__restrict__ tile_nl, const int *__restrict__ file_tile_begin) {
-    __shared__ uint32_t part[1024];
-    const int t0 = file_tile_begin[blockIdx.x], t1 = file_tile_begin[blockIdx.x + 1];
-    const int n = t1 - t0;
-    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int a = t0 + (int)threadIdx.x * per;
-    const int b = (a + per < t1) ? a + per : t1;
-    uint32_t s = 0;
-    for (int t = a; t < b; t++) s += tile_nl[t];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < (int)blockDim.x; i++) { const uint32_t v = part[i]; part[i] = run; run += v; }
-    }
-    __syncthreads();
-    uint32_t run = part[threadIdx.x];
-    for (int t = a; t < b; t++) { const uint32_t v = tile_nl[t]; tile_nl[t] = run & 3u; run += v; }
-}
-
-// FASTQ counting, k <= 7: per-CTA shared-memory histogram; CTA b owns tiles [cta_begin[b], cta_begin[b+1]),
-// its warps take them round-robin, the histogram is flushed when the CTA moves to another file.
+// FASTQ counting, k <= 7: per-CTA shared-memory histogram; CTA b owns tiles [cta_begin[b], cta_begin[b+1]), its warps take
+// them from a shared counter, the histogram is flushed when the CTA moves to another file.
 template <int K, int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
-                        const uint32_t *__restrict__ tile_type, unsigned long long *__restrict__ g_fwd,
-                        const uint32_t *__restrict__ file_row, unsigned long long *__restrict__ fq_err) {
+                        const uint64_t *__restrict__ file_off, const uint64_t *__restrict__ file_len,
+                        unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row,
+                        unsigned long long *__restrict__ fq_err) {
     KF_DYN_SMEM(uint32_t, hist);
     constexpr int NB = 1 << (2 * K);
     __shared__ uint32_t s_next;
     for (int i = threadIdx.x; i < NB; i += THREADS) hist[i] = 0;
     if (threadIdx.x == 0) s_next = 0;
     __syncthreads();
+    const int lane = threadIdx.x & 31;
     const SmemSink emit = make_smem_sink(hist);
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1;) {
         const uint32_t file = tiles[t].file;
         int te = t + 1;
         while (te < t1 && tiles[te].file == file) ++te;
-        // the warps take the segment's tiles from a shared counter (tiles differ in how much sequence they hold)
+        const uint64_t F0 = file_off[file], F1 = F0 + file_len[file];
         for (;;) {
             int tt = 0;
-            if ((threadIdx.x & 31) == 0) tt = t + (int)atomicAdd(&s_next, 1u);
+            if (lane == 0) tt = t + (int)atomicAdd(&s_next, 1u);
             tt = __shfl_sync(FULL, tt, 0);
             if (tt >= te) break;
             const Tile T = tiles[tt];
-            fastq_process_range<K, 4>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[tt], emit, fq_err + file);
+            const uint64_t tb = (uint64_t)T.first_chunk * CHUNK, tend = tb + (uint64_t)T.n_chunks * CHUNK;
+            const uint64_t x0 = tb + (uint64_t)lane * FQ_LANE_BYTES;
+            const uint64_t x1 = x0 + FQ_LANE_BYTES < tend ? x0 + FQ_LANE_BYTES : tend;
+            if (x0 < tend) fastq_lane_records<K>(arena, F0, F1, x0, x1, emit, fq_err + file);
         }
         __syncthreads();
         if (threadIdx.x == 0) s_next = 0;
@@ -1373,17 +1384,21 @@ count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 template <int K, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 count_fastq_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
-                        const uint32_t *__restrict__ tile_type, uint32_t *__restrict__ g_fwd32, uint32_t file_base,
-                        unsigned long long *__restrict__ fq_err) {
+                        const uint64_t *__restrict__ file_off, const uint64_t *__restrict__ file_len,
+                        uint32_t *__restrict__ g_fwd32, uint32_t file_base, unsigned long long *__restrict__ fq_err) {
     constexpr size_t NB = (size_t)1 << (2 * K);
     constexpr int NWARPS = THREADS / 32;
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x] + warp; t < t1; t += NWARPS) {
         const Tile T = tiles[t];
         GmemSink emit;
         emit.g = g_fwd32 + (size_t)(T.file - file_base) * NB;
-        fastq_process_range<K, 3>(arena, T.first_chunk, T.first_chunk + T.n_chunks, tile_type[t], emit, fq_err + T.file);
+        const uint64_t F0 = file_off[T.file], F1 = F0 + file_len[T.file];
+        const uint64_t tb = (uint64_t)T.first_chunk * CHUNK, tend = tb + (uint64_t)T.n_chunks * CHUNK;
+        const uint64_t x0 = tb + (uint64_t)lane * FQ_LANE_BYTES;
+        const uint64_t x1 = x0 + FQ_LANE_BYTES < tend ? x0 + FQ_LANE_BYTES : tend;
+        if (x0 < tend) fastq_lane_records<K>(arena, F0, F1, x0, x1, emit, fq_err + T.file);
     }
 }
 

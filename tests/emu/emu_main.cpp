@@ -133,27 +133,24 @@ int main(int argc, char **argv) {
     }
 #define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); break;
     switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }
-    // FASTQ files: same sequence as kf_api.cu (tile newline counts -> tile line types -> counting kernel)
+    // FASTQ files: same plan as kf_api.cu (tiles of 32 lane ranges; tile_chunks <= 64 shrinks them so that small test
+    // files still span several tiles -- the lane ranges stay FQ_LANE_BYTES, the tile just ends early)
     {
-        std::vector<Tile> fq; std::vector<int> ftb(1, 0);
-        uint32_t fq_tile = tile_chunks > 64 ? 64 : tile_chunks;
+        std::vector<Tile> fq;
+        uint32_t fq_tile = tile_chunks >= 64 ? 32 * FQ_LANE_BYTES / CHUNK : tile_chunks * 8;
         for (int f = 0; f < n; f++) {
             if (!len[f] || arena[off[f]] != '@') continue;
             uint64_t fc0 = off[f] / CHUNK, nch = (len[f] + CHUNK - 1) / CHUNK;
             for (uint64_t pos = 0; pos < nch; pos += fq_tile)
                 fq.push_back(Tile{(uint32_t)(fc0 + pos), (uint32_t)std::min<uint64_t>(fq_tile, nch - pos), (uint32_t)f, (uint32_t)fc0});
-            ftb.push_back((int)fq.size());
         }
         if (!fq.empty()) {
             std::vector<int> cb(grid + 1);
             for (int b = 0; b <= grid; b++) cb[b] = (int)((uint64_t)fq.size() * b / grid);
-            std::vector<uint32_t> nl(fq.size(), 0);
             std::vector<unsigned long long> err(n, ~0ull);
-            emu::launch(2, 64, 0, [&]() { fastq_tile_newlines_kernel(arena.data(), fq.data(), (int)fq.size(), nl.data()); });
-            emu::launch((unsigned)ftb.size() - 1, 64, 0, [&]() { fastq_tile_types_kernel(nl.data(), ftb.data()); });
             size_t smem = sizeof(uint32_t) << (2 * k);
-#define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), file_row.data(), err.data()); }); \
-                          else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), nl.data(), fwd.data(), file_row.data(), err.data()); }); break;
+#define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), off.data(), len.data(), fwd.data(), file_row.data(), err.data()); }); \
+                          else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), off.data(), len.data(), fwd.data(), file_row.data(), err.data()); }); break;
             switch (k) { RUNQ(3) RUNQ(4) RUNQ(5) RUNQ(7) default: return 2; }
             for (int f = 0; f < n; f++)
                 if (err[f] != ~0ull && err[f] - off[f] < len[f]) fprintf(stderr, "fastq layout violation file %d at %llu\n", f, err[f] - off[f]);

@@ -142,3 +142,23 @@ def test_emulated_more_ctas_than_chunks(toy_inputs, tmp_path):
         res = run_emu(7, 32, grid, False, 1, files)
         for f, (tot, counts, _) in zip(files, res):
             assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), 7)), (grid, f)
+
+
+def test_emulated_fastq_many_lanes(tmp_path):
+    """FASTQ files of a few hundred KB: every lane of a warp gets its own 4 KiB range, has to find its first record
+    with the local rule ('@' line whose second-next line starts with '+') and chases records by the quality length."""
+    from fuzzgen import rand_fastq
+
+    def piece(seed):
+        b = rand_fastq(random.Random(seed))
+        return b + b"\n" if b.count(b"\n") % 4 else b   # the generator drops the final newline at times
+
+    files = []
+    for j in range(3):
+        p = str(tmp_path / ("big%d.fq" % j))
+        open(p, "wb").write(b"".join(piece(1000 * j + i) for i in range(40)))
+        files.append(p)
+    for k, thr, grid, tile in ((7, 64, 2, 64), (5, 32, 3, 2), (3, 64, 4, 5)):
+        res = run_emu(k, thr, grid, False, tile, files)
+        for f, (tot, counts, _) in zip(files, res):
+            assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), k)), (k, thr, grid, tile, f)
