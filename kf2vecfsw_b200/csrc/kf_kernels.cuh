@@ -416,6 +416,7 @@ count_fasta_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 //              bytes go through the generic range processor / byte walker with a global-memory sink.
 
 #ifdef KF_EMU
+#define KF_PREFETCH_L2(p) ((void)(p))
 __device__ inline void __syncwarp_emu() { emu::exchange(0, 0); }
 #define KF_SYNCWARP() __syncwarp_emu()
 #define KF_LDCG(p) (*(p))
@@ -425,6 +426,7 @@ __device__ inline void stage_wait(uint64_t *, uint32_t) { KF_SYNCWARP(); }
 __device__ inline uint32_t smem_addr(const void *) { return 0; }
 __device__ inline void red_shared_add(uint32_t *hist, uint32_t, uint32_t off, uint32_t v) { atomicAdd(hist + (off >> 2), v); }
 #else
+#define KF_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define KF_SYNCWARP() __syncwarp()
 #define KF_LDCG(p) __ldcg(p)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1158,7 +1160,7 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
 //   layout     : the line after a sequence line must begin with '+', the byte after the skipped quality line must be
 //                '\n' followed by '@' (or the end of the file); the lowest offending offset per file lands in fq_err and
 //                the host maps it to KF_ERR_FASTQ.
-constexpr uint32_t FQ_LANE_BYTES = 4096;
+constexpr uint32_t FQ_LANE_BYTES = 2048;
 
 struct FqPiece {
     uint32_t bits;   // 16 bases, 2 bits each, first base in bits 31:30 (garbage where the byte is not a base)
@@ -1233,12 +1235,21 @@ __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ a
     uint64_t seq_start = 0;     // first byte of the current sequence line
     uint32_t seqlen = 0;        // its length in bytes once it has ended
     bool fresh = true;          // pos is the first byte of a line whose first byte has to be checked
+    // three pieces in registers: the one being counted, its look-ahead, and the one after (requested one iteration ahead
+    // so that its latency hides behind the counting); a jump to the next record reloads them.
+    uint64_t have_a = ~0ull;   // arena offset the register pieces start at
+    uint4 w = make_uint4(0, 0, 0, 0), wl = w, wll = w;
     while (run) {
         if (pos >= F1) break;
         const uint64_t a = pos & ~15ull;
         const uint32_t off = (uint32_t)(pos - a);
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
-        const uint4 wl = __ldg(reinterpret_cast<const uint4 *>(arena + a + 16));
+        if (a == have_a + 16) { w = wl; wl = wll; }
+        else if (a != have_a) {
+            w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
+            wl = __ldg(reinterpret_cast<const uint4 *>(arena + a + 16));
+        }
+        have_a = a;
+        wll = __ldg(reinterpret_cast<const uint4 *>(arena + a + 32));
         FqPiece P = fq_decode16(w);
         // look-ahead: the next 12 bytes are enough for K <= 12 (K - 1 <= 11)
         uint32_t lbits, linv, lnl;
@@ -1294,6 +1305,7 @@ __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ a
                 seqlen = (uint32_t)(a + e - seq_start);
                 st = PLUS;
                 fresh = true;
+                KF_PREFETCH_L2(arena + a + e + 4 + seqlen);   // where the next record starts if the plus line is bare ("+\n")
             } else {
                 // end of the plus line: jump over the quality line; the next record's header must follow
                 const uint64_t qstart = a + e + 1;
