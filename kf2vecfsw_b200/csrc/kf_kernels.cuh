@@ -704,6 +704,9 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
                 const uint64_t left = seen < plen ? plen - seen : 0;
                 uint64_t nwin = left / ((uint64_t)G::WIN * 2u * nwarps);
                 nwin = nwin < 2 ? 2 : (nwin > 64 ? 64 : nwin);
+#ifdef KF_EMU_RANDOM_UNITS
+                { extern unsigned g_emu_seed; uint64_t z = (seen + g_emu_seed) * 0x9E3779B97F4A7C15ull; z ^= z >> 29; nwin = 1 + (z % 9); }   // tests: any unit size must do
+#endif
                 sz = (uint32_t)(nwin * G::WIN);
             }
             old = atomicAdd(s_cursor, sz);
@@ -783,7 +786,9 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         for (int i = 0; i <= G::NWA; i++) x[i] = sw[i];
 #pragma unroll
         for (int i = 0; i < G::NWA; i++) x[i] = __funnelshift_r(x[i], x[i + 1], ash);
-        const bool nl_ok = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au;
+        // on the grid: my slot ends with a '\n' AND lies inside the file (a short last line + arena padding + the next
+        // file's header can add up to exactly one slot -- profiles/r01: one k-mer in 5e9 counted across two files)
+        const bool nl_ok = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au && B + (uint64_t)(lane + 1) * G::P <= F1;
         // ---- who is on the grid: lines that start before the unit's end ----
         const uint64_t rem = U.Ue - B;                                  // > 0
         const uint32_t nact = rem >= (uint64_t)G::WIN ? 32u : (uint32_t)((rem + G::P - 1) / G::P);
@@ -801,13 +806,15 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             // q = the next line start that is not a header: where the grid restarts.
             KF_T(tq0);
             const uint8_t *lb = buf + woff + f * G::P;
+            const int lim = F1 - sf < (uint64_t)G::P ? (int)(F1 - sf) : G::P;   // bytes of the slot that belong to the file
             int nlp = G::P + 1;   // index of the line's '\n' (none within LW + 1 bytes: the line is longer than the grid's)
 #pragma unroll
             for (int i = 0; i < (G::P + 31) / 32; i++) {
                 const int bi = lane + 32 * i;
-                const unsigned m = __ballot_sync(FULL, bi < G::P && lb[bi] == 0x0Au);
+                const unsigned m = __ballot_sync(FULL, bi < lim && lb[bi] == 0x0Au);
                 if (m && nlp > G::P) nlp = 32 * i + __ffs((int)m) - 1;
             }
+            if (nlp > G::P && lim < G::P) nlp = lim;   // the file ends inside the slot without a final '\n'
             const WindowSrc wsrc{arena, buf, base, (uint32_t)G::STAGE};
             const bool is_hdr = lb[0] == (uint8_t)'>';   // sf is a line start: a '>' here opens a header line
             if (nlp <= G::P && is_hdr) {

@@ -263,12 +263,15 @@ def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_
     L = _load()
     if stream is None:
         stream = torch.cuda.current_stream(arena.device)
+    # torch's default stream has handle 0, which the C ABI reads as "the library's own stream": name the legacy
+    # default stream explicitly (cudaStreamLegacy == 0x1) so that the work is ordered with the caller's torch work
+    handle = stream.cuda_stream if stream.cuda_stream != 0 else 1
     ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     rc = L.kf_count_device(ctypes.c_void_p(arena.tensor.data_ptr()), arena.nbytes, arena.offsets.ctypes.data,
                            arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, k,
                            _flags(pseudocount, raw_cnt, force_walker, no_linegrid), ptr(counts), ptr(freq), ptr(feat),
                            ptr(totals),
-                           ctypes.c_void_p(stream.cuda_stream))
+                           ctypes.c_void_p(handle))
     _check(rc, "kf_count_device")
 
 

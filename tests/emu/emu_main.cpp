@@ -119,7 +119,9 @@ int main(int argc, char **argv) {
     const bool lg = use_lg && k == 7 && !fw;
     emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data(), fwd.data(), file_row.data(), (uint32_t)NB); });
     if (lg) {
-        if (threads == 64) {
+        if (threads == 512) {
+            run_lg<80, 512>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+        } else if (threads == 64) {
             run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
             run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
             run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
@@ -131,7 +133,7 @@ int main(int argc, char **argv) {
         int nlg = 0; for (auto P : file_P) nlg += P != 0;
         fprintf(stderr, "linegrid files: %d of %d\n", nlg, n);
     }
-#define RUN(KK) case KK: if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); break;
+#define RUN(KK) case KK: if (threads == 512) run<KK, 512>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); break;
     switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }
     // FASTQ files: same plan as kf_api.cu (tiles of 32 lane ranges; tile_chunks <= 64 shrinks them so that small test
     // files still span several tiles -- the lane ranges stay FQ_LANE_BYTES, the tile just ends early)

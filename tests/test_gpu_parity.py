@@ -279,3 +279,39 @@ def test_count_windows_vs_oracle(eng, k):
         ref = o.fold_canonical(o.forward_counts(sym, k), k)
         assert np.array_equal(counts[i], ref), i
         assert int(totals[i]) == int(ref.sum())
+
+
+# ---- BASELINE.json configs[1] at FULL size -------------------------------------------------------------------------
+def test_full_size_config_every_row_vs_c_oracle(eng):
+    """1,000 synthetic genomes x 5 Mbp (the bench workload, 5.06 GB) through the device-arena path: every one of the
+    1,000 rows bit-exact against the multi-threaded C oracle, plus size-independent properties (totals from the run
+    structure of a sample, frequencies sum to one, a checksum of checksums over the whole matrix)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    G, NB = 1000, 5_000_000
+    threads = len(os.sched_getaffinity(0))
+    with ThreadPoolExecutor(threads) as ex:
+        gen = list(ex.map(lambda i: eng.synth_fasta(20261018, i, NB), range(G)))
+    arena = eng.DeviceArena(gen)
+    V = eng.vocab_size(7)
+    counts = torch.empty((G, V), dtype=torch.int64, device="cuda")
+    freq = torch.empty((G, V), dtype=torch.float64, device="cuda")
+    totals = torch.empty(G, dtype=torch.int64, device="cuda")
+    eng.count_device(arena, k=7, counts=counts, freq=freq, totals=totals)
+    torch.cuda.synchronize()
+    got = counts.cpu().numpy().astype(np.uint64)
+    ref, _, st = c_oracle.count_buffers_mt(gen, 7, threads=threads, want_freq=False)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(totals.cpu().numpy().astype(np.uint64), ref.sum(axis=1))
+    # checksum of checksums: one number for the whole [1000, 8192] matrix
+    w = (np.arange(V, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1)) & np.uint64(0xFFFFFFFF)
+    assert int((got * w).sum(dtype=np.uint64)) == int((ref * w).sum(dtype=np.uint64))
+    f = freq.cpu().numpy()
+    assert np.all(np.abs(f.sum(axis=1) - 1.0) < 1e-12)
+    assert np.array_equal(f, ref.astype(np.float64) / ref.sum(axis=1, keepdims=True).astype(np.float64))
+    for i in (0, 499, 999):   # totals = sum over maximal ACGT runs of max(0, L - 6)
+        sym = o.symbols_from_bytes(gen[i].tobytes())
+        good = np.concatenate(([0], (sym >= 0).astype(np.int8), [0]))
+        d = np.diff(good)
+        runs = np.flatnonzero(d == -1) - np.flatnonzero(d == 1)
+        assert int(totals[i]) == int(np.maximum(runs - 6, 0).sum())

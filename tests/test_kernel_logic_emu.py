@@ -162,3 +162,28 @@ def test_emulated_fastq_many_lanes(tmp_path):
         res = run_emu(k, thr, grid, False, tile, files)
         for f, (tot, counts, _) in zip(files, res):
             assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), k)), (k, thr, grid, tile, f)
+
+
+def test_emulated_last_line_plus_padding_plus_next_header_is_one_slot(tmp_path):
+    """Found by the full-size GPU test (1 k-mer in 5e9): a short last line (53 bases + '\\n'), 6 bytes of arena padding
+    and the next file's 21-byte header add up to exactly one 81-byte slot whose byte 80 is a '\\n' -- the slot must not
+    pass for a line on the grid, or the byte walker runs on into the next file."""
+    rng = random.Random(835)
+    n = next(n for n in range(200, 2000) if (57 + 81 * n) % 512 == 506)     # header 3 + n full lines + 54 -> 6 bytes of padding
+    seq = "".join(rng.choice("ACGT") for _ in range(80 * n + 53))
+    a = (">a\n" + "\n".join(seq[i:i + 80] for i in range(0, len(seq), 80)) + "\n").encode()
+    assert len(a) % 512 == 506 and seq[-1] in "ACGT"
+    b = (">g00836_c0 syntheti" + seq[-1].lower() + "\n" + "\n".join(seq[i:i + 80] for i in range(0, 8000, 80)) + "\n").encode()
+    assert b.index(b"\n") == 20
+    pa, pb = str(tmp_path / "a.fna"), str(tmp_path / "b.fna")
+    open(pa, "wb").write(a)
+    open(pb, "wb").write(b)
+    for grid, thr in ((1, 64), (2, 32)):
+        res = run_emu(7, thr, grid, False, 1024, [pa, pb])
+        for f, (tot, counts, _) in zip((pa, pb), res):
+            assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), 7)), (grid, thr, f)
+    # same file without its final newline: the file ends inside the slot
+    open(pa, "wb").write(a[:-1])
+    res = run_emu(7, 64, 1, False, 1024, [pa, pb])
+    for f, (tot, counts, _) in zip((pa, pb), res):
+        assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), 7)), f
