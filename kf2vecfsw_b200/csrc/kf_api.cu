@@ -387,10 +387,20 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         g.fq_err_n = (int)f1;
     }
     if (smem_path) {
-        const size_t fsm = NB * sizeof(unsigned long long);
-        CK(cudaFuncSetAttribute(fold_normalize_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
-        fold_normalize_smem_kernel<<<nf, 1024, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
-                                                          use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
+        // u32 staging is exact when no bin can reach 2^32: a file of fewer than 2^32 bytes holds fewer k-mers than that
+        uint64_t max_len = 0;
+        for (uint32_t f = f0; f < f1; f++) max_len = std::max(max_len, lens[f]);
+        if (max_len < (1ull << 32)) {
+            const size_t fsm = NB * sizeof(uint32_t);
+            CK(cudaFuncSetAttribute(fold_normalize_smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            fold_normalize_smem_kernel<uint32_t><<<nf, FOLD_THREADS, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
+                                                                             use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
+        } else {
+            const size_t fsm = NB * sizeof(unsigned long long);
+            CK(cudaFuncSetAttribute(fold_normalize_smem_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+            fold_normalize_smem_kernel<unsigned long long><<<nf, FOLD_THREADS, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
+                                                                                       use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
+        }
     } else
         fold_normalize_kernel<uint32_t><<<nf, 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, nullptr, nullptr,
                                                              d_counts, d_freq, d_feat, d_totals);

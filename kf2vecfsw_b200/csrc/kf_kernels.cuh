@@ -1449,56 +1449,73 @@ __device__ __forceinline__ uint32_t revcomp_std(uint32_t x, int k) {
 }
 __device__ __forceinline__ uint32_t std_to_gray(uint32_t x) { return x ^ ((x >> 1) & 0x55555555u); }
 
-// k <= 7: the file's rows are summed with coalesced loads into shared memory (4^k u64, 128 KB at k = 7), then the
-// canonical gather, the total and the normalisation read from there.
-__global__ void __launch_bounds__(1024)
+// k <= 7: the file's rows are summed with coalesced loads into shared memory (4^k entries: u32 when no bin of the
+// batch can reach 2^32, i.e. every file is shorter than 4 GiB -- 64 KB at k = 7, three CTAs per SM -- else u64), then
+// the canonical gather reads from there.  A thread keeps its (at most FOLD_ITEMS) canonical counts in registers
+// between the total and the normalisation.
+#ifdef KF_EMU
+constexpr int FOLD_THREADS = 64;   // (one OS thread per CUDA thread in the emulation)
+constexpr int FOLD_ITEMS = 128;
+#else
+constexpr int FOLD_THREADS = 512;
+constexpr int FOLD_ITEMS = 16;   // 8,192 canonical 7-mers / 512 threads
+#endif
+template <typename SmT>
+__global__ void __launch_bounds__(FOLD_THREADS)
 fold_normalize_smem_kernel(const unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ canon, int k, long long V,
                            uint32_t flags, const uint32_t *__restrict__ file_P, const uint32_t *__restrict__ file_row,
                            unsigned long long *__restrict__ counts, double *__restrict__ freq, float *__restrict__ feat,
                            unsigned long long *__restrict__ totals) {
-    KF_DYN_SMEM(unsigned long long, row);
+    KF_DYN_SMEM(unsigned long long, fold_smem);
+    SmT *row = reinterpret_cast<SmT *>(fold_smem);
     const uint32_t NB = 1u << (2 * k);
     const uint32_t file = blockIdx.x;
     const uint32_t row0 = file_row[file], nrows = file_row[file + 1] - row0;
     const unsigned long long *g = g_fwd + (size_t)row0 * NB;
     const size_t orow = (size_t)file * (size_t)V;
-    __shared__ unsigned long long red[32];
+    __shared__ unsigned long long red[FOLD_THREADS / 32];
     __shared__ unsigned long long s_total;
     if (NB >= 2) {
-        for (uint32_t i = threadIdx.x; i < NB / 2; i += blockDim.x) {
-            ulonglong2 a = make_ulonglong2(0ull, 0ull);
-            for (uint32_t r = 0; r < nrows; r++) {
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < NB / 2; i += FOLD_THREADS) {
+            ulonglong2 a = reinterpret_cast<const ulonglong2 *>(g)[i];
+            for (uint32_t r = 1; r < nrows; r++) {
                 const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(g + (size_t)r * NB)[i];
                 a.x += v.x;
                 a.y += v.y;
             }
-            row[2 * i] = a.x;
-            row[2 * i + 1] = a.y;
+            row[2 * i] = (SmT)a.x;
+            row[2 * i + 1] = (SmT)a.y;
         }
+    } else {
+        if (threadIdx.x == 0) { unsigned long long a = 0; for (uint32_t r = 0; r < nrows; r++) a += g[(size_t)r * NB]; row[0] = (SmT)a; }
     }
     __syncthreads();
     // rows written by the line kernel (k = 7, file_P != 0) hold the 7-mers with their digits reversed
     const bool rev = file_P != nullptr && file_P[file] != 0;
-    auto canon_count = [&](long long i) -> unsigned long long {
-        const uint32_t m = canon[i];
-        const uint32_t r = revcomp_std(m, k);
-        const uint32_t g0 = std_to_gray(m), g1 = std_to_gray(r);
-        unsigned long long c = row[rev ? digit_rev7(g0) : g0];
-        if (r != m) c += row[rev ? digit_rev7(g1) : g1];
-        return c;
-    };
+    unsigned long long c[FOLD_ITEMS];
     unsigned long long local = 0;
-    for (long long i = threadIdx.x; i < V; i += blockDim.x) {
-        const unsigned long long c = canon_count(i);
-        if (counts) counts[orow + i] = c;
-        local += c;
+#pragma unroll
+    for (int it = 0; it < FOLD_ITEMS; it++) {
+        const long long i = (long long)threadIdx.x + (long long)it * FOLD_THREADS;
+        c[it] = 0;
+        if (i < V) {
+            const uint32_t m = canon[i];
+            const uint32_t r = revcomp_std(m, k);
+            const uint32_t g0 = std_to_gray(m), g1 = std_to_gray(r);
+            unsigned long long v = row[rev ? digit_rev7(g0) : g0];
+            if (r != m) v += row[rev ? digit_rev7(g1) : g1];
+            c[it] = v;
+            if (counts) counts[orow + i] = v;
+            local += v;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
     __syncthreads();
     if (threadIdx.x < 32) {
-        unsigned long long v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0ull;
+        unsigned long long v = (threadIdx.x < FOLD_THREADS / 32) ? red[threadIdx.x] : 0ull;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if (threadIdx.x == 0) { s_total = v; if (totals) totals[file] = v; }
@@ -1507,11 +1524,15 @@ fold_normalize_smem_kernel(const unsigned long long *__restrict__ g_fwd, const u
     if (!freq && !feat) return;
     const bool pc = flags & 1u, raw = flags & 2u;
     const double denom = (double)s_total + (pc ? 0.5 * (double)V : 0.0);
-    for (long long i = threadIdx.x; i < V; i += blockDim.x) {
-        double v = (double)canon_count(i) + (pc ? 0.5 : 0.0);
-        if (!raw) v = v / denom;   // IEEE fp64 division: correctly rounded, bit-exact with numpy
-        if (freq) freq[orow + i] = v;
-        if (feat) feat[orow + i] = (float)(v * 1e4);   // train_classifier_model.py:149,323
+#pragma unroll
+    for (int it = 0; it < FOLD_ITEMS; it++) {
+        const long long i = (long long)threadIdx.x + (long long)it * FOLD_THREADS;
+        if (i < V) {
+            double v = (double)c[it] + (pc ? 0.5 : 0.0);
+            if (!raw) v = v / denom;   // IEEE fp64 division: correctly rounded, bit-exact with numpy
+            if (freq) freq[orow + i] = v;
+            if (feat) feat[orow + i] = (float)(v * 1e4);   // train_classifier_model.py:149,323
+        }
     }
 }
 

@@ -162,7 +162,7 @@ int main(int argc, char **argv) {
     long long V = (long long)canon.size();
     std::vector<unsigned long long> counts((size_t)n * V), totals(n);
     std::vector<double> freq((size_t)n * V);
-    emu::launch(n, 64, NB * sizeof(unsigned long long), [&]() { fold_normalize_smem_kernel(fwd.data(), canon.data(), k, V, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data()); });
+    emu::launch(n, FOLD_THREADS, NB * sizeof(unsigned long long), [&]() { fold_normalize_smem_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data()); });
     for (int f = 0; f < n; f++) {
         printf("%llu", totals[f]);
         for (long long i = 0; i < V; i++) printf(" %llu", counts[(size_t)f * V + i]);
