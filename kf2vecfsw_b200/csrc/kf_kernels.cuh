@@ -1169,31 +1169,6 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
 //                the host maps it to KF_ERR_FASTQ.
 constexpr uint32_t FQ_LANE_BYTES = 2048;
 
-struct FqPiece {
-    uint32_t bits;   // 16 bases, 2 bits each, first base in bits 31:30 (garbage where the byte is not a base)
-    uint32_t inv;    // 16-bit: byte is not A/C/G/T
-    uint32_t nl;     // 16-bit: byte is '\n' (subset of inv)
-};
-__device__ __forceinline__ FqPiece fq_decode16(const uint4 w) {
-    uint32_t p0, p1, p2, p3, V0, V1, V2, V3;
-    decode_word(w.x, p0, V0);
-    decode_word(w.y, p1, V1);
-    decode_word(w.z, p2, V2);
-    decode_word(w.w, p3, V3);
-    const uint32_t r1 = __byte_perm(p3, p2, 0x0073);
-    const uint32_t r2 = __byte_perm(p1, p0, 0x0073);
-    FqPiece L;
-    L.bits = __byte_perm(r1, r2, 0x5410);
-    L.inv = 0;
-    L.nl = 0;
-    if (V0 | V1 | V2 | V3) {
-        L.inv = movemask4(nonzero_bytes(V0)) | (movemask4(nonzero_bytes(V1)) << 4) | (movemask4(nonzero_bytes(V2)) << 8) |
-                (movemask4(nonzero_bytes(V3)) << 12);
-        L.nl = newline_mask16(w);
-    }
-    return L;
-}
-
 // position of the first '\n' at or after p (p < end), or end.  16-byte pieces of the arena.
 __device__ __forceinline__ uint64_t fq_next_newline(const uint8_t *__restrict__ arena, uint64_t p, uint64_t end) {
     while (p < end) {
@@ -1209,7 +1184,57 @@ __device__ __forceinline__ uint64_t fq_next_newline(const uint8_t *__restrict__ 
     return end;
 }
 
+// Same, for a line that starts at p: also checks the line's first byte (`first`: '@' or '+') and, when `prev_nl` is set,
+// that the byte before p is a '\n' (the end of the quality line that was skipped by length).  Returns ~0 on a violation.
+__device__ __forceinline__ uint64_t fq_line_end_checked(const uint8_t *__restrict__ arena, uint64_t p, uint64_t end, uint32_t first,
+                                                        bool prev_nl) {
+    const uint64_t a0 = p & ~15ull;
+    const uint32_t off = (uint32_t)(p - a0);
+    uint4 w = __ldg(reinterpret_cast<const uint4 *>(arena + a0));
+    if (byte_of(w, (int)off) != first) return ~0ull;
+    if (prev_nl) {
+        const uint32_t pb = off ? byte_of(w, (int)off - 1) : (uint32_t)arena[p - 1];
+        if (pb != 0x0Au) return ~0ull;
+    }
+    uint32_t m = newline_mask16(w) & ~((1u << off) - 1u);
+    uint64_t a = a0;
+    for (;;) {
+        if (m) {
+            const uint64_t q = a + (uint32_t)(__ffs((int)m) - 1);
+            return q < end ? q : end;
+        }
+        a += 16;
+        if (a >= end) return end;
+        w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
+        m = newline_mask16(w);
+    }
+}
+
+// k-mers that start in one 16-byte piece: hi = its bases, lo = the next piece's, bad32 = bad bits of both (piece in the
+// low half); the k-mer at byte j counts iff bad[j .. j+K) is clear.
+template <int K, class Sink>
+__device__ __forceinline__ void fq_emit16(uint32_t hi, uint32_t lo, uint32_t bad32, Sink sink) {
+    uint32_t o = bad32;
+    int cover = 1;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        if (cover < K) {
+            const int sft = (cover < K - cover) ? cover : K - cover;
+            o |= o >> sft;
+            cover += sft;
+        }
+    }
+    const uint32_t ok = ~o & 0xFFFFu;
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if ((ok >> j) & 1u) sink(kmer_off_at<K>(hi, lo, j));
+    }
+}
+
 // One lane: count the k-mers of every record whose header line starts in [X0, X1) of the file [F0, F1).
+// The lanes of a warp walk their records in step: header lines together, sequence lines together (16-byte pieces, the
+// previous piece is counted when the next one -- its look-ahead -- has been decoded), plus lines together, jump.
 template <int K, class Sink>
 __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ arena, uint64_t F0, uint64_t F1, uint64_t X0,
                                                    uint64_t X1, Sink sink, unsigned long long *fq_err) {
@@ -1219,9 +1244,8 @@ __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ a
     uint64_t pos = X0;          // a record (header line) start, once synchronised
     bool run = X0 < X1;
     if (run && X0 > F0) {
-        // line starts after X0 - 1: s1, s2, s3 ...; the first s_i that holds '@' while s_(i+2) holds '+'
-        uint64_t n = fq_next_newline(arena, X0 - 1, F1);
-        uint64_t s0 = n + 1;
+        // line starts after X0 - 1: s0, s1, s2 ...; the first s_i that holds '@' while s_(i+2) holds '+'
+        uint64_t s0 = fq_next_newline(arena, X0 - 1, F1) + 1;
         uint64_t s1 = s0 < F1 ? fq_next_newline(arena, s0, F1) + 1 : F1 + 1;
         run = false;
         for (int it = 0; it < 8; it++) {
@@ -1236,121 +1260,66 @@ __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ a
             s1 = s2;
         }
     }
-    // ---- the chain: one 16-byte piece per iteration ----
-    enum { HDR = 0, SEQ = 1, PLUS = 2 };
-    uint32_t st = HDR;
-    uint64_t seq_start = 0;     // first byte of the current sequence line
-    uint32_t seqlen = 0;        // its length in bytes once it has ended
-    bool fresh = true;          // pos is the first byte of a line whose first byte has to be checked
-    // three pieces in registers: the one being counted, its look-ahead, and the one after (requested one iteration ahead
-    // so that its latency hides behind the counting); a jump to the next record reloads them.
-    uint64_t have_a = ~0ull;   // arena offset the register pieces start at
-    uint4 w = make_uint4(0, 0, 0, 0), wl = w, wll = w;
-    while (run) {
-        if (pos >= F1) break;
-        const uint64_t a = pos & ~15ull;
-        const uint32_t off = (uint32_t)(pos - a);
-        if (a == have_a + 16) { w = wl; wl = wll; }
-        else if (a != have_a) {
-            w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
-            wl = __ldg(reinterpret_cast<const uint4 *>(arena + a + 16));
-        }
-        have_a = a;
-        wll = __ldg(reinterpret_cast<const uint4 *>(arena + a + 32));
-        FqPiece P = fq_decode16(w);
-        // look-ahead: the next 12 bytes are enough for K <= 12 (K - 1 <= 11)
-        uint32_t lbits, linv, lnl;
-        {
-            uint32_t q0, q1, q2, W0, W1, W2;
-            decode_word(wl.x, q0, W0);
-            decode_word(wl.y, q1, W1);
-            decode_word(wl.z, q2, W2);
-            const uint32_t r2 = __byte_perm(q1, q0, 0x0073);
-            lbits = __byte_perm(q2 >> 24, r2, 0x5400) & 0xFFFFFF00u;   // [q0.b3, q1.b3, q2.b3, 0]
-            linv = 0;
-            lnl = 0;
-            if (W0 | W1 | W2) {
-                linv = movemask4(nonzero_bytes(W0)) | (movemask4(nonzero_bytes(W1)) << 4) | (movemask4(nonzero_bytes(W2)) << 8);
-                lnl = (movemask4(~nonzero_bytes(wl.x ^ 0x0A0A0A0Au) & 0x80808080u)) | (movemask4(~nonzero_bytes(wl.y ^ 0x0A0A0A0Au) & 0x80808080u) << 4) |
-                      (movemask4(~nonzero_bytes(wl.z ^ 0x0A0A0A0Au) & 0x80808080u) << 8);
-            }
-        }
-        // bytes at or beyond the end of the file behave like a '\n' followed by garbage
-        if (a + 16 > F1) { const uint32_t v = (uint32_t)(F1 - a); P.inv |= 0xFFFFu & ~((1u << v) - 1u); P.nl |= 1u << v; }
-        if (a + 28 > F1) {
-            const uint32_t v = F1 > a + 16 ? (uint32_t)(F1 - a - 16) : 0u;
-            linv |= 0xFFFu & ~((1u << v) - 1u);
-            lnl |= 1u << v;
-        }
-        // ---- state transitions inside this piece; seqm = its bytes that belong to a sequence line ----
-        uint32_t cur = off, seqm = 0;
-        bool seq_runs_on = false;   // the sequence line continues into the next piece
-        bool jumped = false;
+    bool after_jump = false;   // pos was reached by skipping a quality line: the byte before it must be its '\n'
+    while (run && pos < F1) {
+        // ---- header line ----
+        const uint64_t hn = fq_line_end_checked(arena, pos, F1, (uint32_t)'@', after_jump);
+        if (hn == ~0ull) { atomicMin(fq_err, pos); break; }
+        if (hn >= F1) break;
+        const uint64_t s = hn + 1;   // first byte of the sequence line
+        // ---- sequence line ----
+        uint64_t a = s & ~15ull;
+        uint4 w = __ldg(reinterpret_cast<const uint4 *>(arena + a));
+        uint32_t lead = (1u << (uint32_t)(s - a)) - 1u;   // bytes of the first piece that lie before the sequence
+        uint32_t pbits = 0, pbad = 0xFFFFu, plus_byte = 0;
+        bool have_prev = false, plus_known = false;
+        uint64_t seq_end;
         for (;;) {
-            if (fresh && cur < 16u) {
-                // first byte of a header / plus line
-                const uint32_t c = byte_of(w, (int)cur);
-                const uint64_t at = a + cur;
-                if (at < F1 && ((st == HDR && c != (uint32_t)'@') || (st == PLUS && c != (uint32_t)'+'))) {
-                    atomicMin(fq_err, at);
-                    run = false;
-                    break;
-                }
-                fresh = false;
+            const uint4 wn = __ldg(reinterpret_cast<const uint4 *>(arena + a + 16));   // next piece, asked for early
+            uint32_t p0, p1, p2, p3, V0, V1, V2, V3;
+            decode_word(w.x, p0, V0);
+            decode_word(w.y, p1, V1);
+            decode_word(w.z, p2, V2);
+            decode_word(w.w, p3, V3);
+            const uint32_t r1 = __byte_perm(p3, p2, 0x0073);
+            const uint32_t r2 = __byte_perm(p1, p0, 0x0073);
+            const uint32_t bits = __byte_perm(r1, r2, 0x5410);
+            uint32_t inv = 0, nlm = 0;
+            if (V0 | V1 | V2 | V3) {
+                inv = movemask4(nonzero_bytes(V0)) | (movemask4(nonzero_bytes(V1)) << 4) | (movemask4(nonzero_bytes(V2)) << 8) |
+                      (movemask4(nonzero_bytes(V3)) << 12);
+                nlm = newline_mask16(w);
             }
-            if (cur >= 16u) break;
-            const uint32_t m = P.nl & ~((1u << cur) - 1u);
-            const uint32_t e = m ? (uint32_t)(__ffs((int)m) - 1) : 16u;   // this line's '\n' in the piece, or 16
-            if (st == SEQ) seqm |= ((1u << e) - 1u) & ~((1u << cur) - 1u);
-            if (e == 16u) { seq_runs_on = st == SEQ; break; }
-            cur = e + 1u;
-            if (st == HDR) {
-                if (a + e + 1 > F1) { run = false; break; }
-                st = SEQ;
-                seq_start = a + e + 1;
-            } else if (st == SEQ) {
-                seqlen = (uint32_t)(a + e - seq_start);
-                st = PLUS;
-                fresh = true;
-                KF_PREFETCH_L2(arena + a + e + 4 + seqlen);   // where the next record starts if the plus line is bare ("+\n")
-            } else {
-                // end of the plus line: jump over the quality line; the next record's header must follow
-                const uint64_t qstart = a + e + 1;
-                const uint64_t nxt = qstart + seqlen + 1;
-                if (nxt - 1 < F1 && arena[nxt - 1] != 0x0Au) { atomicMin(fq_err, nxt - 1); run = false; break; }
-                pos = nxt;
-                st = HDR;
-                fresh = true;
-                jumped = true;
-                if (pos >= X1) run = false;   // that record belongs to the next range
+            if (a + 16 > F1) { const uint32_t v = (uint32_t)(F1 - a); inv |= 0xFFFFu & ~((1u << v) - 1u); nlm |= 1u << v; }   // file end = line end
+            nlm &= ~lead;
+            const uint32_t e = nlm ? (uint32_t)(__ffs((int)nlm) - 1) : 16u;   // the line's end inside this piece
+            const uint32_t bad = (inv | lead | (0xFFFFu & ~((1u << e) - 1u))) & 0xFFFFu;
+            if (have_prev) fq_emit16<K>(pbits, bits, pbad | (bad << 16), sink);
+            have_prev = true;
+            pbits = bits;
+            pbad = bad;
+            lead = 0;
+            if (e < 16u) {
+                seq_end = a + e;
+                if (e < 15u) { plus_byte = byte_of(w, (int)e + 1); plus_known = true; }
                 break;
             }
+            a += 16;
+            w = wn;
         }
-        // ---- count: k-mer at byte j iff bad[j .. j+K) clear; look-ahead bytes count only while the line runs on ----
-        if (seqm) {
-            const uint32_t bad = (P.inv | ~seqm) & 0xFFFFu;
-            uint32_t lbad = 0xFFFu;
-            if (seq_runs_on) lbad = linv | (lnl ? (0xFFFu & ~((1u << (__ffs((int)lnl) - 1)) - 1u)) : 0u);
-            uint32_t o = bad | (lbad << 16) | 0xF0000000u;
-            {
-                int cover = 1;
-#pragma unroll
-                for (int it = 0; it < 4; it++) {
-                    if (cover < K) {
-                        const int sft = (cover < K - cover) ? cover : K - cover;
-                        o |= o >> sft;
-                        cover += sft;
-                    }
-                }
-            }
-            const uint32_t ok = ~o & 0xFFFFu;
-            if (ok) {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if ((ok >> j) & 1u) sink(kmer_off_at<K>(P.bits, lbits, j));
-            }
-        }
-        if (!jumped) pos = a + 16;
+        fq_emit16<K>(pbits, 0u, pbad | 0xFFFF0000u, sink);
+        const uint32_t seqlen = (uint32_t)(seq_end - s);
+        KF_PREFETCH_L2(arena + seq_end + 4 + seqlen);   // where the next record starts if the plus line is bare ("+\n")
+        // ---- plus line, then jump over the quality line ----
+        const uint64_t pp = seq_end + 1;
+        if (pp >= F1) break;
+        if (plus_known && plus_byte != (uint32_t)'+') { atomicMin(fq_err, pp); break; }
+        const uint64_t pn = fq_line_end_checked(arena, pp, F1, (uint32_t)'+', false);
+        if (pn == ~0ull) { atomicMin(fq_err, pp); break; }
+        if (pn >= F1) break;
+        pos = pn + 1 + seqlen + 1;   // quality line: seqlen bytes and its '\n'
+        after_jump = true;
+        if (pos >= X1) break;        // that record belongs to the next range
     }
 }
 
