@@ -125,6 +125,19 @@ int64_t kf_format_row(const char *sample, const double *row, int64_t V, int int_
 int kf_write_kf(const char *out_path, const char *sample, const double *row, int64_t V, int int_mode,
                 int append);
 
+/* All chunk rows of one genome into one file with one open (main.py:895-915).  labels: n NUL-terminated strings back to
+ * back; int_modes[i] as int_mode above (may be NULL = all 0). */
+int kf_write_kf_rows(const char *out_path, const char *labels, const double *rows, int64_t n, int64_t V, const uint8_t *int_modes,
+                     int append);
+
+/* ---- chunked-genome text preparation: seqtk seq -l 0 (main.py:732), awk N-run collapse (:740), seqkit seq -g -m (:753) ---- */
+/* One pass over a FASTA buffer: linearise every record, collapse each run of 'N' / 'n' / '|' to one 'N', remove the gap
+ * characters '-', '.', ' ', keep the records of at least min_len bytes.  Kept sequences land back to back in seq_out
+ * (capacity seq_cap >= len is always enough); record r is seq_out[seq_off[r] .. +seq_len[r]) and its header line (without
+ * '>') is data[id_off[r] .. +id_len[r]).  Returns the number of kept records (only the first max_records are stored). */
+int64_t kf_linearise_fasta(const uint8_t *data, size_t len, uint64_t min_len, uint8_t *seq_out, size_t seq_cap, uint64_t *seq_off,
+                           uint64_t *seq_len, uint64_t *id_off, uint32_t *id_len, int64_t max_records);
+
 /* ---- .kf reader: utils.py:436-437 (my_read_csv), classify.py:102-114, query.py:148-158 ---------------------- */
 /* Parses "label,v1,...,vV\n" rows from a text buffer (one or many .kf files concatenated, as query.py:153 does with
  * `cat`).  out [rows][V] double (may be NULL), feat_out [rows][V] float = float(v * 1e4) as the trainers build it

@@ -25,6 +25,8 @@ from .engine import (  # noqa: F401
     vocab_codes,
     vocab_size,
     write_kf,
+    write_kf_rows,
+    linearise_fasta,
 )
 from .frequencies import get_frequencies, frequency_matrix  # noqa: F401
 from .chunks import get_chunks  # noqa: F401

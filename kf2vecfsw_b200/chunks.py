@@ -14,7 +14,6 @@ from __future__ import annotations
 import logging
 import math
 import os
-import re
 import sys
 import time
 from typing import List, Tuple
@@ -26,8 +25,6 @@ from .frequencies import list_inputs, DEFAULT_K
 
 CHUNK_SZ = 10000     # main.py:100
 CHUNK_CNT_THR = 5    # main.py:101
-_N_RUN = re.compile(rb"[N|n]+")   # main.py:740 -- the awk class holds 'N', '|' and 'n'
-_GAPS = b"-. "                    # seqkit seq -g (main.py:753)
 
 
 def hms(sec_elapsed):   # utils.py:320-328
@@ -35,17 +32,6 @@ def hms(sec_elapsed):   # utils.py:320-328
     m = int((sec_elapsed % (60 * 60)) / 60)
     s = int(sec_elapsed % 60)
     return h, m, s
-
-
-def fasta_records(data: bytes) -> List[Tuple[str, bytes]]:
-    """(header text without '>', linearised sequence) per record -- seqtk seq -l 0 (main.py:732)."""
-    recs: List[Tuple[str, bytes]] = []
-    for block in data.split(b"\n>") if data.startswith(b">") else []:
-        if block.startswith(b">"):
-            block = block[1:]
-        head, _, body = block.partition(b"\n")
-        recs.append((head.decode("latin-1"), body.replace(b"\n", b"").replace(b"\r", b"")))
-    return recs
 
 
 def window_plan(length: int) -> List[Tuple[int, int]]:
@@ -61,22 +47,19 @@ def window_plan(length: int) -> List[Tuple[int, int]]:
 
 
 def plan_genome(sample: str, data: bytes):
-    """Host-side text preparation of one genome.  Returns (sequence buffer, window offsets, window lengths, labels)."""
-    parts, offs, lens, labels = [], [], [], []
-    base = 0
-    for header, seq in fasta_records(data):
-        seq = _N_RUN.sub(b"N", seq).translate(None, _GAPS)
-        if len(seq) < CHUNK_SZ:                                   # seqkit seq -m 10000 (main.py:753)
-            continue
+    """Host-side text preparation of one genome (one C++ pass: linearise, collapse N runs, strip gaps, drop contigs
+    under 10 kbp; main.py:730-753) and the sliding-window plan (main.py:813-824).
+    Returns (sequence buffer uint8, window offsets, window lengths, labels)."""
+    seq, recs = engine.linearise_fasta(data, CHUNK_SZ)
+    offs, lens, labels = [], [], []
+    for header, off, length in recs:
         cid = header.split()[0] if header.split() else ""
-        for (a, b) in window_plan(len(seq)):
-            offs.append(base + a - 1)
+        for (a, b) in window_plan(length):
+            offs.append(off + a - 1)
             lens.append(b - a + 1)
             # file name seqkit split gives the chunk, minus '.fna' (main.py:895-896)
             labels.append("{}.part_{}.part_{}_sliding__{}-{}".format(sample, cid, cid, a, b))
-        parts.append(seq)
-        base += len(seq)
-    return b"".join(parts), np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint32), labels
+    return seq, np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint32), labels
 
 
 def chunk_rows(sample: str, data: bytes, k: int = DEFAULT_K, pseudocount: bool = False):
@@ -84,7 +67,7 @@ def chunk_rows(sample: str, data: bytes, k: int = DEFAULT_K, pseudocount: bool =
     seq, offs, lens, labels = plan_genome(sample, data)
     if len(labels) < CHUNK_CNT_THR:
         return labels, None
-    counts, _, _ = engine.count_windows(np.frombuffer(seq, dtype=np.uint8), offs, lens, k=k)
+    counts, _, _ = engine.count_windows(seq, offs, lens, k=k)
     return labels, counts
 
 
@@ -139,19 +122,16 @@ def get_chunks(args) -> None:
             continue
         log.info('\n==> Done chunk processing for {}. Time: {}\n'.format(fname, stamp()))
 
-        counts, _, _ = engine.count_windows(np.frombuffer(seq, dtype=np.uint8), offs, lens, k=k)
+        counts, _, _ = engine.count_windows(seq, offs, lens, k=k)
         log.info('\n==> Done computing k-mer frequences for {}. Time: {}\n'.format(fname, stamp()))
 
         # get_frequencies(raw_cnt=True) rows (main.py:327-357): pandas keeps int64 only when no k-mer is missing
         out_path = os.path.join(args.output_dir, "{}.{}".format(sample, "kf"))
-        if os.path.exists(out_path):
-            os.remove(out_path)
         vals = counts.astype(np.float64)
         if pseudocount:
             vals += 0.5
-        for i, label in enumerate(labels):
-            int_mode = (not pseudocount) and bool(np.all(counts[i] > 0))
-            engine.write_kf(out_path, label, vals[i], int_mode=int_mode, append=True)
+        int_modes = np.zeros(len(labels), dtype=np.uint8) if pseudocount else (counts > 0).all(axis=1).astype(np.uint8)
+        engine.write_kf_rows(out_path, labels, vals, int_modes=int_modes)
 
     log.info('\n==> Done getting chunks. Time: {}\n'.format(stamp()))
     for h in (fh, sh):

@@ -220,12 +220,94 @@ int64_t kf_format_row(const char *sample, const double *row, int64_t V, int int_
             auto r = std::to_chars(p, p + 24, (long long)row[i]);
             p = r.ptr;
         } else {
-            p += kf::format_repr(row[i], p);
+            const double v = row[i];
+            if (v >= 0.0 && v < 1e15 && v == (double)(long long)v) {   // raw counts: "16.0" without the shortest-digits search
+                auto r = std::to_chars(p, p + 24, (long long)v);
+                p = r.ptr;
+                *p++ = '.';
+                *p++ = '0';
+            } else {
+                p += kf::format_repr(v, p);
+            }
         }
     }
     *p++ = '\n';
     *p = 0;
     return (int64_t)(p - out);
+}
+
+// Several rows into one file with one open: the chunked-genome output (main.py:895-915 concatenates one row per chunk).
+// labels: n NUL-terminated strings back to back; int_modes[i] as in kf_format_row.
+int kf_write_kf_rows(const char *out_path, const char *labels, const double *rows, int64_t n, int64_t V, const uint8_t *int_modes,
+                     int append) {
+    if (!out_path || !labels || !rows || n < 0 || V < 0) return KF_ERR_ARG;
+    FILE *f = fopen(out_path, append ? "ab" : "wb");
+    if (!f) return KF_ERR_IO;
+    std::vector<char> buf;
+    const char *lab = labels;
+    int rc = KF_OK;
+    for (int64_t i = 0; i < n && rc == KF_OK; i++) {
+        const size_t sl = strlen(lab);
+        buf.resize(sl + 2 + (size_t)V * 32 + 1);
+        const int64_t m = kf_format_row(lab, rows + (size_t)i * (size_t)V, V, int_modes ? int_modes[i] : 0, buf.data(), buf.size());
+        if (m < 0) rc = (int)m;
+        else if (fwrite(buf.data(), 1, (size_t)m, f) != (size_t)m) rc = KF_ERR_IO;
+        lab += sl + 1;
+    }
+    if (fclose(f) != 0 && rc == KF_OK) rc = KF_ERR_IO;
+    return rc;
+}
+
+// ---- chunked-genome text preparation: main.py:730-753 ------------------------------------------------------------
+// One pass over a FASTA buffer doing what the reference shells out for: `seqtk seq -l 0` (linearise, :732), awk
+// gsub(/[N|n]+/,"N") on sequence lines (:740 -- the class holds 'N', '|' and 'n'), `seqkit seq -g -m min_len` (:753:
+// remove the gap characters '-', '.', ' ', then drop records shorter than min_len).  The kept sequences are written back
+// to back into seq_out; record r is seq_out[seq_off[r] .. +seq_len[r]) and its header text is data[id_off[r] .. +id_len[r])
+// (the whole header line without '>'; the contig id is its first white-space separated token).
+// Returns the number of kept records (only the first max_records are stored), or a negative error.
+int64_t kf_linearise_fasta(const uint8_t *data, size_t len, uint64_t min_len, uint8_t *seq_out, size_t seq_cap, uint64_t *seq_off,
+                           uint64_t *seq_len, uint64_t *id_off, uint32_t *id_len, int64_t max_records) {
+    if (!data || !seq_out) return KF_ERR_ARG;
+    if (len == 0 || data[0] != '>') return 0;
+    size_t p = 0, w = 0;
+    int64_t kept = 0;
+    while (p < len) {
+        // header line (p is at a '>')
+        const size_t h0 = p + 1;
+        const uint8_t *nl = (const uint8_t *)memchr(data + p, '\n', len - p);
+        size_t h1 = nl ? (size_t)(nl - data) : len;
+        p = nl ? h1 + 1 : len;
+        if (h1 > h0 && data[h1 - 1] == '\r') h1--;
+        const size_t start = w;
+        bool in_run = false;   // inside a run of N / n / |
+        // sequence lines up to the next line that begins with '>'
+        while (p < len && data[p] != '>') {
+            const uint8_t *e = (const uint8_t *)memchr(data + p, '\n', len - p);
+            const size_t le = e ? (size_t)(e - data) : len;
+            if (w + (le - p) > seq_cap) return KF_ERR_ARG;
+            for (size_t i = p; i < le; i++) {
+                const uint8_t c = data[i];
+                if (c == 'N' || c == 'n' || c == '|') { if (!in_run) seq_out[w++] = 'N'; in_run = true; continue; }
+                if (c == '\r') continue;   // line ends are dropped before the runs are collapsed (a run may span lines)
+                in_run = false;
+                if (c == '-' || c == '.' || c == ' ') continue;   // gaps go after the collapse: "N-N" stays two Ns
+                seq_out[w++] = c;
+            }
+            p = e ? le + 1 : len;
+        }
+        if (w - start >= min_len) {
+            if (kept < max_records) {
+                if (seq_off) seq_off[kept] = start;
+                if (seq_len) seq_len[kept] = w - start;
+                if (id_off) id_off[kept] = h0;
+                if (id_len) id_len[kept] = (uint32_t)(h1 - h0);
+            }
+            kept++;
+        } else {
+            w = start;   // dropped: reuse the space
+        }
+    }
+    return kept;
 }
 
 int kf_write_kf(const char *out_path, const char *sample, const double *row, int64_t V, int int_mode,

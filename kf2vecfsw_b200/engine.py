@@ -86,6 +86,11 @@ def _load():
     L.kf_format_row.restype = ctypes.c_int64
     L.kf_write_kf.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                               ctypes.c_int]
+    L.kf_write_kf_rows.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                   ctypes.c_void_p, ctypes.c_int]
+    L.kf_linearise_fasta.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    L.kf_linearise_fasta.restype = ctypes.c_int64
     L.kf_parse_kf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.kf_parse_kf.restype = ctypes.c_int64
@@ -309,6 +314,40 @@ def write_kf(path: str, sample: str, row: np.ndarray, int_mode: bool = False, ap
     row = np.ascontiguousarray(row, dtype=np.float64)
     _check(_load().kf_write_kf(os.fsencode(path), sample.encode(), row.ctypes.data, row.size, 1 if int_mode else 0,
                                1 if append else 0), "kf_write_kf(%s)" % path)
+
+
+def write_kf_rows(path: str, labels: Sequence[str], rows: np.ndarray, int_modes=None, append: bool = False) -> None:
+    """All rows of a chunked-genome .kf file with one open (main.py:895-915)."""
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    n, V = rows.shape
+    lab = b"".join(l.encode() + b"\0" for l in labels)
+    im = np.ascontiguousarray(int_modes, dtype=np.uint8) if int_modes is not None else None
+    _check(_load().kf_write_kf_rows(os.fsencode(path), lab, rows.ctypes.data, n, V, im.ctypes.data if im is not None else None,
+                                    1 if append else 0), "kf_write_kf_rows(%s)" % path)
+
+
+def linearise_fasta(data, min_len: int):
+    """seqtk seq -l 0 + N-run collapse + gap strip + min-length filter (main.py:730-753) in one pass.
+    Returns (seq uint8 array, [(header text, seq offset, seq length), ...])."""
+    L = _load()
+    a = _as_u8(data)
+    seq = np.empty(max(a.size, 1), dtype=np.uint8)
+    cap = 1024
+    while True:
+        so = np.zeros(cap, dtype=np.uint64)
+        sl = np.zeros(cap, dtype=np.uint64)
+        io = np.zeros(cap, dtype=np.uint64)
+        il = np.zeros(cap, dtype=np.uint32)
+        n = int(L.kf_linearise_fasta(a.ctypes.data if a.size else None, a.size, min_len, seq.ctypes.data, seq.size, so.ctypes.data,
+                                     sl.ctypes.data, io.ctypes.data, il.ctypes.data, cap)) if a.size else 0
+        if n < 0:
+            raise KfError(n, "kf_linearise_fasta")
+        if n <= cap:
+            break
+        cap = n
+    recs = [(a[int(io[i]): int(io[i]) + int(il[i])].tobytes().decode("latin-1"), int(so[i]), int(sl[i])) for i in range(n)]
+    total = (recs[-1][1] + recs[-1][2]) if recs else 0
+    return seq[:total], recs
 
 
 def parse_kf(text: bytes, V: int, want_rows: bool = True, want_feat: bool = False):
