@@ -315,3 +315,22 @@ def test_full_size_config_every_row_vs_c_oracle(eng):
         d = np.diff(good)
         runs = np.flatnonzero(d == -1) - np.flatnonzero(d == 1)
         assert int(totals[i]) == int(np.maximum(runs - 6, 0).sum())
+
+
+def test_big_single_files_and_mixed_batch(eng):
+    """One 150 Mbp single-contig genome (every line-kernel CTA holds a piece of the same file: 148 rows summed by the
+    fold), one 60-column and one 70-column genome, an unwrapped one, FASTQ reads, an empty and an unsupported file in
+    the same batch -- each row against the C oracle."""
+    big = eng.synth_fasta(7, 1, 150_000_000, max_contigs=1, n_runs=25)
+    g60 = eng.synth_fasta(7, 2, 20_000_000, line_width=60)
+    g70 = eng.synth_fasta(7, 3, 20_000_000, line_width=70)
+    flat = eng.synth_fasta(7, 4, 3_000_000, line_width=10 ** 8, max_contigs=5)
+    fq = eng.synth_fastq(7, 5, 1_000_000, 100_000, 150)
+    bufs = [big, b"", g60, b"ACGT\n", g70, flat, fq]
+    counts, freq, totals, status = eng.count_buffers(bufs, k=7)
+    assert list(status) == [0, -9, 0, -5, 0, 0, 0]
+    for i in (0, 2, 4, 5, 6):
+        ref = c_oracle.count_buffer(bytes(bufs[i]) if not isinstance(bufs[i], np.ndarray) else bufs[i].tobytes(), 7)
+        assert np.array_equal(counts[i], ref), i
+        assert int(totals[i]) == int(ref.sum())
+    assert not counts[1].any() and not counts[3].any()
