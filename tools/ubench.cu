@@ -345,8 +345,6 @@ int main(int argc, char **argv) {
     run<SIMPLE_U32, 7, 512, 2>("simple fast path u32", arena, bytes, sms, g_out, d_clk);
     run<FULL_PROD, 7, 512, 2, 3>("production range processor", arena, bytes, sms, g_out, d_clk);
     run_lg<512>(arena, bytes, sms);
-    run_lg<640>(arena, bytes, sms);
-    run_lg<768>(arena, bytes, sms);
     for (int nf : {148, 1000, 4000}) run_lg_files<512>(arena, bytes, nf, sms);
     run_lg_files<512>(arena, bytes, 296, sms, 1, 0, 5000000);
     run_lg_files<512>(arena, bytes, 296, sms, 50, 0, 5000000);
