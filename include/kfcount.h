@@ -41,7 +41,8 @@ extern "C" {
 #define KF_FLAG_PSEUDOCOUNT 1u   /* main.py:332-334  counts += 0.5 before normalising           */
 #define KF_FLAG_RAW_CNT 2u       /* main.py:340-342  skip the normalisation                      */
 #define KF_FLAG_FORCE_WALKER 4u  /* debug: disable the vectorised fast path (byte walker only)   */
-#define KF_FLAG_NO_LINEGRID 8u   /* debug: skip the fixed-line-width kernel (generic kernel only) */
+#define KF_FLAG_NO_LINEGRID 8u   /* debug: generic kernels only (no fixed-line-width kernel at k = 7, no partitioned kernel at k = 8..10) */
+#define KF_FLAG_PART_ALL 16u     /* debug: k = 8..10 partitioned kernel for files of any size (default: >= 256 KiB) */
 
 /* limits */
 #define KF_MIN_K 1

@@ -21,6 +21,9 @@ constexpr int THREADS_GMEM = 512;
 constexpr int THREADS_LG = 512;     // line-grid kernel: 1 CTA/SM (128 KiB pair histogram + per-warp TMA staging)
 constexpr uint32_t TILE_CHUNKS = 1024;                 // 512 KiB per tile: 64 chunks per warp
 constexpr size_t GMEM_WS_LIMIT = (size_t)12 << 30;     // forward-count workspace cap for k >= 8
+constexpr int THREADS_PART = 1024;                     // partitioned kernel (k = 8..10): 1 CTA/SM, 128 KiB histogram, 64 regs/thread
+constexpr uint64_t PART_MIN_BYTES = 256 << 10;         // smaller files (chunked-mode windows ...) stay on global REDs
+constexpr int part_bases(int k) { return k - 8; }      // leading bases that select the partition: 4^(k-8) partitions
 
 struct Ctx {
     int device = -1;
@@ -41,6 +44,12 @@ struct Ctx {
     uint32_t *d_file_row = nullptr; size_t frow_cap = 0;          // first forward-count row of every file (+ total)
     uint32_t *d_cta_first_rank = nullptr; size_t cfr_cap = 0;    // per line-kernel CTA: how many earlier CTAs hold a piece of its first file
     uint32_t pc_rows = 0;
+    // k = 8..10: (file, partition) work items of the partitioned shared-memory kernel
+    int *d_file_t0 = nullptr; size_t ft0_cap = 0;
+    uint32_t *d_items = nullptr; size_t items_cap = 0;
+    unsigned int *d_item_counter = nullptr;
+    int pc_items = 0;
+    uint32_t pc_part_mode = 0;
     // FASTQ plan: 128 KiB tiles (32 lane ranges), layout-violation offsets
     Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
     int *d_fq_cta_begin = nullptr; size_t fq_cta_cap = 0;
@@ -255,10 +264,24 @@ int launch_smem(const uint8_t *d_arena, int grid, bool force_walker, cudaStream_
 template <int K>
 int launch_gmem(const uint8_t *d_arena, int grid, bool force_walker, uint32_t file_base, cudaStream_t s) {
     uint32_t *fwd = (uint32_t *)g.d_fwd;
+    if constexpr (K >= 8 && K <= 10) {
+        if (g.pc_items > 0 && !force_walker) {
+            constexpr int PB = part_bases(K);
+            constexpr size_t smem = PartSink<K, PB>::NWORDS * sizeof(uint32_t);
+            auto kern = count_fasta_part_kernel<K, PB, THREADS_PART>;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaMemsetAsync(g.d_item_counter, 0, sizeof(unsigned int), s));
+            kern<<<std::min(g.sm_count, g.pc_items), THREADS_PART, smem, s>>>(d_arena, g.d_tiles, g.d_file_t0, g.d_items, g.pc_items, fwd, file_base,
+                                                                             g.d_item_counter);
+            CK(cudaGetLastError());
+            g.last_launches++;
+        }
+    }
+    const uint32_t *skip = (g.pc_items > 0 && !force_walker) ? g.d_file_P : nullptr;   // files taken by the partitioned kernel
     if (force_walker)
-        count_fasta_gmem_kernel<K, THREADS_GMEM, true><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, file_base);
+        count_fasta_gmem_kernel<K, THREADS_GMEM, true><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, file_base, skip);
     else
-        count_fasta_gmem_kernel<K, THREADS_GMEM, false><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, file_base);
+        count_fasta_gmem_kernel<K, THREADS_GMEM, false><<<grid, THREADS_GMEM, 0, s>>>(d_arena, g.d_tiles, g.d_cta_begin, fwd, file_base, skip);
     CK(cudaGetLastError());
     return KF_OK;
 }
@@ -294,8 +317,9 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     if ((rc = ensure_canon(k)) != KF_OK) return rc;
     if (smem_path && f0 != 0) return KF_ERR_ARG;   // only the k >= 8 path is run in file batches
 
+    const uint32_t part_mode = (flags & KF_FLAG_NO_LINEGRID) ? 0u : (flags & KF_FLAG_PART_ALL) ? 2u : 1u;
     // plan (cached on layout)
-    bool hit = g.pc_k == k && g.pc_grid == grid && g.pc_f0 == f0 && g.pc_f1 == f1 &&
+    bool hit = g.pc_k == k && g.pc_grid == grid && g.pc_f0 == f0 && g.pc_f1 == f1 && g.pc_part_mode == part_mode &&
                g.pc_offsets.size() == (size_t)nf && std::equal(g.pc_offsets.begin(), g.pc_offsets.end(), offsets + f0) &&
                std::equal(g.pc_lens.begin(), g.pc_lens.end(), lens + f0) &&
                std::equal(g.pc_formats.begin(), g.pc_formats.end(), formats + f0);
@@ -329,6 +353,34 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 CK(cudaMemcpy(g.d_fq_tiles, fq_tiles.data(), fq_tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
                 CK(cudaMemcpy(g.d_fq_cta_begin, fq_cta_begin.data(), fq_cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
             }
+        }
+        g.pc_items = 0;
+        g.pc_part_mode = part_mode;
+        if (k >= 8 && k <= 10 && part_mode != 0) {
+            // (file, partition) items for FASTA files of at least PART_MIN_BYTES; file_P doubles as the "taken" flag
+            std::vector<int> file_t0((size_t)f1 + 1, 0);
+            {
+                size_t t = 0;
+                for (uint32_t f = 0; f < f1; f++) {
+                    file_t0[f] = (int)t;
+                    while (t < tiles.size() && tiles[t].file == f) t++;
+                }
+                file_t0[f1] = (int)t;
+            }
+            std::vector<uint32_t> items, taken((size_t)f1, 0u);
+            const uint32_t P = 1u << (2 * part_bases(k));
+            for (uint32_t f = f0; f < f1; f++) {
+                if (formats[f] != '>' || lens[f] == 0 || (lens[f] < PART_MIN_BYTES && part_mode != 2)) continue;
+                taken[f] = 1u;
+                for (uint32_t pp = 0; pp < P; pp++) items.push_back((f << 8) | pp);
+            }
+            if (f1 >= (1u << 24)) items.clear(), std::fill(taken.begin(), taken.end(), 0u);   // (file id must fit the item word)
+            if ((rc = ensure(g.d_file_t0, g.ft0_cap, file_t0.size() * sizeof(int))) != KF_OK) return rc;
+            if ((rc = ensure(g.d_items, g.items_cap, (items.size() + 1) * sizeof(uint32_t))) != KF_OK) return rc;
+            CK(cudaMemcpy(g.d_file_t0, file_t0.data(), file_t0.size() * sizeof(int), cudaMemcpyHostToDevice));
+            if (!items.empty()) CK(cudaMemcpy(g.d_items, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(g.d_file_P, taken.data(), (size_t)f1 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            g.pc_items = (int)items.size();
         }
         if (smem_path) {
             std::vector<uint32_t> file_row, cta_first_rank;
@@ -466,6 +518,7 @@ int kf_init(int device) {
     CK(cudaEventCreate(&g.ev_k0));
     CK(cudaEventCreate(&g.ev_k1));
     CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&g.d_item_counter, sizeof(unsigned int)));
     g.sm_count = prop.multiProcessorCount;
     g.device = device;
     return KF_OK;

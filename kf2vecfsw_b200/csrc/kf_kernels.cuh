@@ -240,8 +240,11 @@ __device__ __forceinline__ uint32_t kmer_off_at(uint32_t hi, uint32_t lo, int j)
 // rotates at compile time).  Sinks take the byte offset 4*kmer.
 // Optional ownership clip [own_lo, own_hi) in arena bytes (own_lo must be a line start): only k-mers whose
 // first base lies inside it are counted; lanes cut by a bound use the walker on their part.
+// A sink may take a lane's whole 16-byte piece at once (window(hi, lo, n): the k-mers that start at bases 0..n-1 of the
+// 32-base window hi:lo) instead of one k-mer at a time.
+template <class S> struct sink_takes_window { static constexpr bool value = false; };
 template <int K, bool FORCE_WALKER, int PF, class Sink, class Src>
-__device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, uint32_t c1, uint32_t file_c0, Sink sink,
+__device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, uint32_t c1, uint32_t file_c0, Sink &sink,
                                                     uint64_t own_lo = 0, uint64_t own_hi = ~0ull,
                                                     bool skip_backscan = false) {
     static_assert(PF >= 2 && PF <= 6, "prefetch depth");
@@ -283,9 +286,13 @@ __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, 
                     const uint32_t nb = nbw & ~3u;
                     uint32_t hi = cur.bits, lo = nb;
                     if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
+                    if constexpr (sink_takes_window<Sink>::value) {
+                        sink.window(hi, lo, cur.n);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 15; j++) sink(kmer_off_at<K>(hi, lo, j));
-                    if (cur.n == 16) sink(kmer_off_at<K>(hi, lo, 15));
+                        for (int j = 0; j < 15; j++) sink(kmer_off_at<K>(hi, lo, j));
+                        if (cur.n == 16) sink(kmer_off_at<K>(hi, lo, 15));
+                    }
                 } else if (pb < own_lo) {
                     fasta_walk_lane<K>(src, own_lo, pb + 16 < own_hi ? pb + 16 : own_hi, false, true, emit);
                 } else {
@@ -378,13 +385,15 @@ count_fasta_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 template <int K, int THREADS, bool FORCE_WALKER>
 __global__ void __launch_bounds__(THREADS)
 count_fasta_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles,
-                        const int *__restrict__ cta_begin, uint32_t *__restrict__ g_fwd32, uint32_t file_base) {
+                        const int *__restrict__ cta_begin, uint32_t *__restrict__ g_fwd32, uint32_t file_base,
+                        const uint32_t *__restrict__ file_skip) {
     constexpr size_t NB = (size_t)1 << (2 * K);
     constexpr int NWARPS = THREADS / 32;
     const int warp = threadIdx.x >> 5;
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
         const Tile T = tiles[t];
+        if (file_skip && file_skip[T.file]) continue;   // counted by the partitioned kernel
         GmemSink emit;
         emit.g = g_fwd32 + (size_t)(T.file - file_base) * NB;
         const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
@@ -459,6 +468,154 @@ __device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32
 }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// k = 8..10: partitioned shared-memory histogram
+// ------------------------------------------------------------------------------------------------
+// 4^k counters do not fit in shared memory, and one RED per occurrence into an L2-resident row runs at the L2's atomic
+// rate (~0.1 Tbases/s).  Instead the k-mer space is cut by the k-mer's first PB bases into 4^PB partitions of
+// 4^(k-PB) = 65,536 bins, which fit as 32,768 words of two u16 halves; a work item is (file, partition): the CTA reads the
+// whole file (the partitions of a file run side by side on different SMs, so the re-reads are L2 hits mostly), counts
+// the k-mers of its partition and owns that part of the file's row outright -- plain read-add-write, no global atomics.
+//   word w of the histogram: low half = occurrences of bins 2w and 2w+1, high half = those of bin 2w+1 (one RED with
+//   addend 1 or 0x10001).  A half can wrap: the histogram is drained every PART_FLUSH_TILES tiles, and at every drain
+//   the sum of the low halves must equal the number of REDs issued; if not, the interval is recounted with global REDs.
+constexpr int PART_FLUSH_TILES = 8;
+
+template <int K, int PB>
+struct PartSink {
+    static_assert(PB >= 0 && PB <= 2 && K - PB <= 8 && K - PB >= 2, "partition geometry");
+    static constexpr uint32_t NBINS = 1u << (2 * (K - PB));
+    static constexpr uint32_t NWORDS = NBINS / 2;
+    static constexpr uint32_t AMASK = (NBINS << 1) - 4u;    // byte address of the word, taken from kmer << 1
+    uint32_t *hist;
+    uint32_t base;     // shared-window address of word 0
+    uint32_t part;     // the PB leading bases this CTA counts (gray codes, first base most significant)
+    uint32_t issued;   // REDs issued by this thread since the last drain
+    // sv: the k-mer (at least its low 2(K-PB) bits) on bits 2(K-PB):1
+    __device__ __forceinline__ void add(uint32_t sv) { red_shared_add(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u); }
+    // one k-mer at a time (rare paths): off = 4 * kmer
+    __device__ __forceinline__ void operator()(uint32_t off) {
+        if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) { add(off >> 1); issued++; }
+    }
+    // 0x55555555-style mask: bit 30 - 2j set iff base j of the window (bits 31-2j:30-2j) equals code c
+    static __device__ __forceinline__ uint32_t match(uint32_t w, uint32_t c) {
+        const uint32_t x = w ^ (c * 0x55555555u);
+        return ~(x | (x >> 1)) & 0x55555555u;
+    }
+    __device__ __forceinline__ void window(uint32_t hi, uint32_t lo, uint32_t n) {
+        uint32_t t = 0x55555555u;
+        if (PB == 1) t = match(hi, part);
+        if (PB == 2) t = match(hi, part >> 2) & match(__funnelshift_l(lo, hi, 2), part & 3u);
+        if (n == 15) t &= ~1u;
+        issued += (uint32_t)__popc(t);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (t & (1u << (30 - 2 * j))) {
+                const int r = 63 - 2 * K - 2 * j;   // k-mer j on bits 2K:1 of (hi:lo) >> r
+                add(r >= 32 ? (hi >> (r - 32)) : __funnelshift_r(lo, hi, r));
+            }
+        }
+    }
+};
+template <int K, int PB> struct sink_takes_window<PartSink<K, PB>> { static constexpr bool value = true; };
+
+template <int K, int PB>
+struct PartGmemSink {   // exact recount of one partition after a wrapped half: one global RED per occurrence
+    uint32_t *g;        // the file's row
+    uint32_t part;
+    __device__ __forceinline__ void operator()(uint32_t off) const {
+        if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g) + off), 1u);
+    }
+};
+
+// items: (file, partition) pairs, the partitions of a file next to each other; CTAs take them from a global counter.
+// file_t0[f] .. file_t0[f + 1]: the file's tiles in `tiles` (consecutive); files with no tiles or with small == 1 are
+// left to the global-atomic kernel.  Rows are zero when the kernel starts.
+template <int K, int PB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ file_t0,
+                        const uint32_t *__restrict__ items, int n_items, uint32_t *__restrict__ g_fwd32, uint32_t file_base,
+                        unsigned int *__restrict__ item_counter) {
+    using S = PartSink<K, PB>;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr size_t NB = (size_t)1 << (2 * K);
+    KF_DYN_SMEM(uint32_t, hist);
+    __shared__ unsigned long long s_red[2 * (THREADS / 32)];
+    __shared__ int s_item;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < S::NWORDS; i += THREADS) hist[i] = 0;
+    S sink;
+    sink.hist = hist;
+    sink.base = smem_addr(hist);
+    sink.issued = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(item_counter, 1u);
+        __syncthreads();
+        const int it = s_item;
+        if (it >= n_items) break;
+        const uint32_t file = items[it] >> 8, part = items[it] & 0xFFu;
+        sink.part = part;
+        uint32_t *row = g_fwd32 + (size_t)(file - file_base) * NB + ((size_t)part << (2 * (K - PB)));
+        const int t0 = file_t0[file], t1 = file_t0[file + 1];
+        for (int ta = t0; ta < t1; ta += PART_FLUSH_TILES) {
+            const int tb = ta + PART_FLUSH_TILES < t1 ? ta + PART_FLUSH_TILES : t1;
+            for (int t = ta; t < tb; ++t) {
+                const Tile T = tiles[t];
+                const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
+                const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
+                const uint32_t cend = T.first_chunk + T.n_chunks;
+                const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
+                if (c0 < c1) fasta_process_range<K, false, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, sink);
+            }
+            // ---- drain: checksum, then add the interval's counts to the row ----
+            unsigned long long iss = sink.issued;
+            sink.issued = 0;
+            __syncthreads();
+            unsigned long long low = 0;
+            for (uint32_t i = threadIdx.x; i < S::NWORDS; i += THREADS) low += hist[i] & 0xFFFFu;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { iss += __shfl_xor_sync(FULL, iss, o); low += __shfl_xor_sync(FULL, low, o); }
+            if (lane == 0) { s_red[warp] = iss; s_red[NWARPS + warp] = low; }
+            __syncthreads();
+            unsigned long long ti = 0, tl = 0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; w++) { ti += s_red[w]; tl += s_red[NWARPS + w]; }
+            const bool ok = ti == tl;
+            for (uint32_t i = threadIdx.x; i < S::NWORDS; i += THREADS) {
+                const uint32_t w = hist[i];
+                hist[i] = 0;
+                if (ok && w) {
+                    uint2 *rp = reinterpret_cast<uint2 *>(row) + i;
+                    uint2 v = KF_LDCG(rp);   // (not through L1: an exact recount adds to these bins with REDs)
+                    v.x += (w & 0xFFFFu) - (w >> 16);
+                    v.y += w >> 16;
+                    *rp = v;
+                }
+            }
+            if (!ok) {
+                // a half wrapped: this interval again, straight into the row (other CTAs never touch this partition's bins,
+                // but this CTA's threads now share them: REDs)
+                __threadfence();
+                __syncthreads();
+                PartGmemSink<K, PB> gs;
+                gs.g = g_fwd32 + (size_t)(file - file_base) * NB;
+                gs.part = part;
+                for (int t = ta; t < tb; ++t) {
+                    const Tile T = tiles[t];
+                    const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
+                    const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
+                    const uint32_t cend = T.first_chunk + T.n_chunks;
+                    const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
+                    if (c0 < c1) fasta_process_range<K, false, 2>(GlobalSrc{arena}, c0, c1, T.file_chunk0, gs);
+                }
+                __threadfence();
+            }
+            __syncthreads();   // the histogram is empty again: the next interval's REDs may start
+        }
+    }
+}
+
 // Sinks of the line kernel's rare paths (byte walker, off-grid lines).  Both take off = 4 * kmer with the first base
 // most significant and store it in the pair histogram's orientation (7-mer digits reversed: first base in bits 1:0).
 __device__ __forceinline__ uint32_t rev7_of_off(uint32_t off) {   // off = 4 * kmer, 14-bit kmer
@@ -511,7 +668,7 @@ __device__ KF_NOINLINE uint64_t fasta_line_start_at_or_after(const Src src, uint
 
 // Exact but slow: the generic range processor over the lines starting in [lo, hi), global sink.
 template <int K, class Src, class Sink>
-__device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64_t hi, uint32_t file_c0, Sink gs) {
+__device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64_t hi, uint32_t file_c0, Sink &gs) {
     if (lo >= hi) return;
     const uint32_t c0 = (uint32_t)(lo / CHUNK), c1 = (uint32_t)((hi + CHUNK - 1) / CHUNK);
     fasta_process_range<K, false, 2>(src, c0, c1, file_c0, gs, lo, hi, true);

@@ -18,6 +18,7 @@ KF_FLAG_FORCE_WALKER = 4
 KF_CHUNK = 512
 KF_TAIL_PAD = 4096
 KF_FLAG_NO_LINEGRID = 8
+KF_FLAG_PART_ALL = 16
 KF_MAX_K = 12
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -112,9 +113,10 @@ def _check(rc: int, what: str = ""):
         raise KfError(rc, what)
 
 
-def _flags(pseudocount: bool, raw_cnt: bool, force_walker: bool = False, no_linegrid: bool = False) -> int:
+def _flags(pseudocount: bool, raw_cnt: bool, force_walker: bool = False, no_linegrid: bool = False, part_all: bool = False) -> int:
     return (KF_FLAG_PSEUDOCOUNT if pseudocount else 0) | (KF_FLAG_RAW_CNT if raw_cnt else 0) | \
-           (KF_FLAG_FORCE_WALKER if force_walker else 0) | (KF_FLAG_NO_LINEGRID if no_linegrid else 0)
+           (KF_FLAG_FORCE_WALKER if force_walker else 0) | (KF_FLAG_NO_LINEGRID if no_linegrid else 0) | \
+           (KF_FLAG_PART_ALL if part_all else 0)
 
 
 # ---- lifecycle -----------------------------------------------------------------------------------
@@ -170,8 +172,8 @@ def _as_u8(b) -> np.ndarray:
 
 def count_buffers(bufs: Sequence, k: int = 7, pseudocount: bool = False, raw_cnt: bool = False,
                   want_counts: bool = True, want_freq: bool = True, force_walker: bool = False,
-                  no_linegrid: bool = False, out_counts: Optional[np.ndarray] = None, out_freq: Optional[np.ndarray] = None
-                  ) -> Tuple[Optional[np.ndarray], Optional[np.ndarray], np.ndarray, np.ndarray]:
+                  no_linegrid: bool = False, out_counts: Optional[np.ndarray] = None, out_freq: Optional[np.ndarray] = None,
+                  part_all: bool = False) -> Tuple[Optional[np.ndarray], Optional[np.ndarray], np.ndarray, np.ndarray]:
     """End-to-end call on host buffers (one per input file).  Returns (counts u64 [n,V] | None,
     freq f64 [n,V] | None, totals u64 [n], status i32 [n])."""
     _require_init()
@@ -185,7 +187,7 @@ def count_buffers(bufs: Sequence, k: int = 7, pseudocount: bool = False, raw_cnt
     freq = out_freq if out_freq is not None else (np.empty((n, V), dtype=np.float64) if want_freq else None)
     totals = np.zeros(n, dtype=np.uint64)
     status = np.zeros(n, dtype=np.int32)
-    rc = L.kf_count_buffers(ptrs, lens, n, k, _flags(pseudocount, raw_cnt, force_walker, no_linegrid),
+    rc = L.kf_count_buffers(ptrs, lens, n, k, _flags(pseudocount, raw_cnt, force_walker, no_linegrid, part_all),
                             counts.ctypes.data if counts is not None else None,
                             freq.ctypes.data if freq is not None else None, totals.ctypes.data, status.ctypes.data)
     _check(rc, "kf_count_buffers")
@@ -259,7 +261,7 @@ class DeviceArena:
 
 def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_cnt: bool = False,
                  counts=None, freq=None, feat=None, totals=None, force_walker: bool = False, no_linegrid: bool = False,
-                 stream=None):
+                 stream=None, part_all: bool = False):
     """Enqueues count + fold/normalise for the arena on ``stream`` (default: torch's current stream).
     Output tensors (torch, on the arena's device) are optional: counts int64/uint64 [n,V], freq float64
     [n,V], feat float32 [n,V] (= fp32(freq*1e4), the matrix the trainers consume), totals int64 [n]."""
@@ -274,7 +276,7 @@ def count_device(arena: DeviceArena, k: int = 7, pseudocount: bool = False, raw_
     ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
     rc = L.kf_count_device(ctypes.c_void_p(arena.tensor.data_ptr()), arena.nbytes, arena.offsets.ctypes.data,
                            arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, k,
-                           _flags(pseudocount, raw_cnt, force_walker, no_linegrid), ptr(counts), ptr(freq), ptr(feat),
+                           _flags(pseudocount, raw_cnt, force_walker, no_linegrid, part_all), ptr(counts), ptr(freq), ptr(feat),
                            ptr(totals),
                            ctypes.c_void_p(handle))
     _check(rc, "kf_count_device")

@@ -60,7 +60,8 @@ int main(int argc, char **argv) {
     int k = atoi(argv[1]), threads = atoi(argv[2]), grid = atoi(argv[3]);
     bool fw = atoi(argv[4]) != 0;
     uint32_t tile_chunks = (uint32_t)atoi(argv[5]);
-    bool use_lg = atoi(argv[6]) != 0;
+    const int mode = atoi(argv[6]);   // 0 generic, 1 line kernel allowed, 2 partitioned kernel (k = 4, 5 stand in for 9, 10)
+    bool use_lg = mode == 1;
     argv += 1; argc -= 1;
     int n = argc - 6;
     std::vector<uint64_t> off(n), len(n);
@@ -96,6 +97,32 @@ int main(int argc, char **argv) {
     }
     while (cta < grid) { cta++; cta_begin[cta] = (int)tiles.size(); }
     size_t NB = (size_t)1 << (2 * k);
+    if (mode == 2) {
+        // partitioned shared-memory kernel + u32 fold, as kf_api.cu launches them for k = 8..10
+        std::vector<int> file_t0(n + 1, 0);
+        { size_t t = 0; for (int f = 0; f < n; f++) { file_t0[f] = (int)t; while (t < tiles.size() && tiles[t].file == (uint32_t)f) t++; } file_t0[n] = (int)t; }
+        const int PB = k - 3;   // k = 4: 4 partitions, k = 5: 16
+        std::vector<uint32_t> items;
+        for (int f = 0; f < n; f++) if (len[f] && arena[off[f]] == '>') for (uint32_t pp = 0; pp < (1u << (2 * PB)); pp++) items.push_back(((uint32_t)f << 8) | pp);
+        std::vector<uint32_t> fwd32((size_t)n * NB, 0u);
+        unsigned int counter = 0;
+        if (k == 4) emu::launch(grid, threads == 512 ? 64 : threads, PartSink<4, 1>::NWORDS * 4, [&]() { if (threads == 32) count_fasta_part_kernel<4, 1, 32>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); else count_fasta_part_kernel<4, 1, 64>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); });
+        else if (k == 5) emu::launch(grid, threads == 512 ? 64 : threads, PartSink<5, 2>::NWORDS * 4, [&]() { if (threads == 32) count_fasta_part_kernel<5, 2, 32>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); else count_fasta_part_kernel<5, 2, 64>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); });
+        else { fprintf(stderr, "partitioned emu: k = 4 or 5\n"); return 2; }
+        std::vector<uint32_t> canon; canonical_codes(k, canon);
+        long long V = (long long)canon.size();
+        std::vector<unsigned long long> counts((size_t)n * V), totals(n);
+        std::vector<double> freq((size_t)n * V);
+        emu::launch(n, 64, 0, [&]() { fold_normalize_kernel<uint32_t>(fwd32.data(), canon.data(), k, V, 0u, 0u, (const uint32_t *)nullptr, (const uint32_t *)nullptr, counts.data(), freq.data(), (float *)nullptr, totals.data()); });
+        for (int f = 0; f < n; f++) {
+            printf("%llu", totals[f]);
+            for (long long i = 0; i < V; i++) printf(" %llu", counts[(size_t)f * V + i]);
+            printf("\nF");
+            for (long long i = 0; i < V; i++) printf(" %.17g", freq[(size_t)f * V + i]);
+            printf("\n");
+        }
+        return 0;
+    }
     // rows: same rule as kf_api.cu:build_rows with stride 1 (every emulated CTA is a line-kernel CTA)
     std::vector<uint32_t> file_row(n + 1, 0), file_first_cta(grid, 0);   // (second one: rank of each CTA for its first file)
     {

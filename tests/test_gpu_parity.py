@@ -334,3 +334,27 @@ def test_big_single_files_and_mixed_batch(eng):
         assert np.array_equal(counts[i], ref), i
         assert int(totals[i]) == int(ref.sum())
     assert not counts[1].any() and not counts[3].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [8, 9, 10])
+def test_partitioned_kernel_large_k(eng, k):
+    """k = 8..10: the partitioned shared-memory kernel ((file, partition) work items, u16 halves, plain read-add-write
+    of the file's row) against the oracle and against the global-RED kernel; small and large files, FASTA and FASTQ in
+    one batch; every file size through the partitioned kernel (part_all); a half that wraps (poly-A) recounted."""
+    import random
+    from fuzzgen import rand_fasta, rand_fasta_grid, rand_fastq
+    rng = random.Random(1234 + k)
+    bufs = [rand_fasta(rng), eng.synth_fasta(7, 0, 700_000).tobytes(), rand_fasta_grid(rng), rand_fastq(rng),
+            eng.synth_fasta(7, 1, 3_000_000).tobytes(), b">only a header\n"]
+    ref = [o.canonical_counts_bytes(bytes(b), k) for b in bufs]
+    for kw in ({}, {"part_all": True}, {"no_linegrid": True}):
+        counts, freq, totals, status = eng.count_buffers(bufs, k=k, **kw)
+        for i in range(len(bufs)):
+            assert np.array_equal(counts[i], ref[i]), (k, kw, i)
+    seq = "A" * 5_000_000 + "ACGTTGCAAGGCTTAACCGGTTAA" * 500 + "N" * 50 + "C" * 1_600_001
+    data = (">polyA\n" + "\n".join(seq[i:i + 80] for i in range(0, len(seq), 80)) + "\n").encode()
+    r = c_oracle.count_buffer(data, k)
+    assert int(r.max()) > 4_000_000
+    counts, freq, totals, status = eng.count_buffers([data], k=k)
+    assert np.array_equal(counts[0], r)

@@ -26,9 +26,9 @@ def emu_binary():
                                "-pthread"] + srcs + ["-o", BIN])
 
 
-def run_emu(k, threads, grid, force_walker, tile_chunks, files, linegrid=True):
+def run_emu(k, threads, grid, force_walker, tile_chunks, files, linegrid=True, mode=None):
     out = subprocess.run([BIN, str(k), str(threads), str(grid), str(int(force_walker)), str(tile_chunks),
-                          str(int(linegrid))] + files,
+                          str(int(linegrid) if mode is None else mode)] + files,
                          capture_output=True, text=True, check=True).stdout.strip().split("\n")
     res = []
     for i in range(len(files)):
@@ -187,3 +187,32 @@ def test_emulated_last_line_plus_padding_plus_next_header_is_one_slot(tmp_path):
     res = run_emu(7, 64, 1, False, 1024, [pa, pb])
     for f, (tot, counts, _) in zip((pa, pb), res):
         assert np.array_equal(counts, o.canonical_counts_bytes(open(f, "rb").read(), 7)), f
+
+
+def test_emulated_partitioned_kernel_fuzz(tmp_path):
+    """The k = 8..10 partitioned shared-memory kernel, instantiated small for the emulation (k = 4: 4 partitions of 64
+    bins, k = 5: 16 partitions): (file, partition) items from a counter, u16 halves with the low-half checksum, drains
+    every PART_FLUSH_TILES tiles, plain read-add-write of the row, exact recount after a wrapped half."""
+    for s in range(800, 830):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 3)):
+            p = str(tmp_path / ("p%d_%d.fa" % (s, i)))
+            open(p, "wb").write(rand_fasta(rng) if rng.random() < 0.5 else rand_fasta_grid(rng))
+            files.append(p)
+        k = rng.choice([4, 5])
+        grid, thr, tile = rng.randint(1, 4), rng.choice([32, 64]), rng.choice([1, 3, 8, 64])
+        res = run_emu(k, thr, grid, False, tile, files, mode=2)
+        for f, (tot, counts, _) in zip(files, res):
+            ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
+            assert np.array_equal(counts, ref), (s, k, grid, thr, tile, f)
+    seq = "A" * 300000 + "ACGTTGCAAGGCTTAACCGGTTAA" * 500 + "N" * 50 + "C" * 160001
+    data = (">polyA\n" + "\n".join(seq[i:i + 80] for i in range(0, len(seq), 80)) + "\n").encode()
+    p = str(tmp_path / "pa.fa")
+    open(p, "wb").write(data)
+    for k in (4, 5):
+        ref = o.canonical_counts_bytes(data, k)
+        assert int(ref.max()) > 2 * 65535
+        for grid, thr, tile in ((1, 64, 64), (3, 32, 8)):
+            tot, counts, _ = run_emu(k, thr, grid, False, tile, [p], mode=2)[0]
+            assert np.array_equal(counts, ref), (k, grid, thr, tile)
