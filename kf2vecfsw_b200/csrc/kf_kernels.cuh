@@ -243,6 +243,9 @@ __device__ __forceinline__ uint32_t kmer_off_at(uint32_t hi, uint32_t lo, int j)
 // A sink may take a lane's whole 16-byte piece at once (window(hi, lo, n): the k-mers that start at bases 0..n-1 of the
 // 32-base window hi:lo) instead of one k-mer at a time.
 template <class S> struct sink_takes_window { static constexpr bool value = false; };
+// What the rare paths (byte walker, out of line) count into: a by-value functor, so that the address of the sink proper
+// is never taken and its state stays in registers on the hot path.  Default: a copy of the sink.
+template <class S> __device__ __forceinline__ S sink_slow(const S &s) { return s; }
 template <int K, bool FORCE_WALKER, int PF, class Sink, class Src>
 __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, uint32_t c1, uint32_t file_c0, Sink &sink,
                                                     uint64_t own_lo = 0, uint64_t own_hi = ~0ull,
@@ -259,7 +262,8 @@ __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, 
 #pragma unroll
     for (int i = 0; i < PF; i++) slot[i] = src.load16(min(c0 + i, cmax), lane);
     Lane cur = decode16(slot[0]);
-    auto emit = [&](uint32_t x) { sink(x << 2); };
+    auto slow_sink = sink_slow(sink);
+    auto emit = [slow_sink](uint32_t x) mutable { slow_sink(x << 2); };
     for (uint32_t cg = c0; cg < c1; cg += PF) {
 #pragma unroll
         for (int u = 0; u < PF; u++) {
@@ -434,6 +438,7 @@ __device__ inline void stage_issue(void *dst, const void *src, uint32_t bytes, u
 __device__ inline void stage_wait(uint64_t *, uint32_t) { KF_SYNCWARP(); }
 __device__ inline uint32_t smem_addr(const void *) { return 0; }
 __device__ inline void red_shared_add(uint32_t *hist, uint32_t, uint32_t off, uint32_t v) { atomicAdd(hist + (off >> 2), v); }
+__device__ inline void red_shared_add_if(uint32_t *hist, uint32_t, uint32_t off, uint32_t v, uint32_t t, uint32_t bit) { if (t & bit) atomicAdd(hist + (off >> 2), v); }
 #else
 #define KF_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define KF_SYNCWARP() __syncwarp()
@@ -463,6 +468,12 @@ __device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return smem_u32(p); }
+// RED iff (t & bit) != 0, as a predicated instruction (no branch, no reconvergence barrier around it)
+__device__ __forceinline__ void red_shared_add_if(uint32_t *, uint32_t base, uint32_t off, uint32_t v, uint32_t t, uint32_t bit) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 a;\n\tand.b32 a, %2, %3;\n\tsetp.ne.u32 p, a, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(base + off),
+                 "r"(v), "r"(t), "r"(bit)
+                 : "memory");
+}
 __device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32_t off, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + off), "r"(v) : "memory");
 }
@@ -493,10 +504,7 @@ struct PartSink {
     uint32_t issued;   // REDs issued by this thread since the last drain
     // sv: the k-mer (at least its low 2(K-PB) bits) on bits 2(K-PB):1
     __device__ __forceinline__ void add(uint32_t sv) { red_shared_add(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u); }
-    // one k-mer at a time (rare paths): off = 4 * kmer
-    __device__ __forceinline__ void operator()(uint32_t off) {
-        if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) { add(off >> 1); issued++; }
-    }
+    uint32_t *s_slow;  // shared: REDs issued by the rare paths since the last drain
     // 0x55555555-style mask: bit 30 - 2j set iff base j of the window (bits 31-2j:30-2j) equals code c
     static __device__ __forceinline__ uint32_t match(uint32_t w, uint32_t c) {
         const uint32_t x = w ^ (c * 0x55555555u);
@@ -512,14 +520,30 @@ struct PartSink {
         //  costs more than 16 predicated-off REDs)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            if (t & (1u << (30 - 2 * j))) {
-                const int r = 63 - 2 * K - 2 * j;   // k-mer j on bits 2K:1 of (hi:lo) >> r
-                add(r >= 32 ? (hi >> (r - 32)) : __funnelshift_r(lo, hi, r));
-            }
+            const int r = 63 - 2 * K - 2 * j;   // k-mer j on bits 2K:1 of (hi:lo) >> r
+            const uint32_t sv = r >= 32 ? (hi >> (r - 32)) : __funnelshift_r(lo, hi, r);
+            if (PB == 0 && j < 15) add(sv);
+            else red_shared_add_if(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u, t, 1u << (30 - 2 * j));
         }
     }
 };
 template <int K, int PB> struct sink_takes_window<PartSink<K, PB>> { static constexpr bool value = true; };
+template <int K, int PB>
+struct PartSlowSink {   // one k-mer at a time (rare paths): off = 4 * kmer
+    uint32_t *hist;
+    uint32_t base, part;
+    uint32_t *s_slow;
+    __device__ __forceinline__ void operator()(uint32_t off) const {
+        if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) {
+            const uint32_t sv = off >> 1;
+            red_shared_add(hist, base, sv & PartSink<K, PB>::AMASK, (sv & 2u) * 0x8000u + 1u);
+            atomicAdd(s_slow, 1u);
+        }
+    }
+};
+template <int K, int PB> __device__ __forceinline__ PartSlowSink<K, PB> sink_slow(const PartSink<K, PB> &s) {
+    return PartSlowSink<K, PB>{s.hist, s.base, s.part, s.s_slow};
+}
 
 template <int K, int PB>
 struct PartGmemSink {   // exact recount of one partition after a wrapped half: one global RED per occurrence
@@ -544,12 +568,15 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
     KF_DYN_SMEM(uint32_t, hist);
     __shared__ unsigned long long s_red[2 * (THREADS / 32)];
     __shared__ int s_item;
+    __shared__ uint32_t s_slow;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t i = threadIdx.x; i < S::NWORDS; i += THREADS) hist[i] = 0;
+    if (threadIdx.x == 0) s_slow = 0;
     S sink;
     sink.hist = hist;
     sink.base = smem_addr(hist);
     sink.issued = 0;
+    sink.s_slow = &s_slow;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = (int)atomicAdd(item_counter, 1u);
@@ -580,10 +607,12 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
             for (int o = 16; o > 0; o >>= 1) { iss += __shfl_xor_sync(FULL, iss, o); low += __shfl_xor_sync(FULL, low, o); }
             if (lane == 0) { s_red[warp] = iss; s_red[NWARPS + warp] = low; }
             __syncthreads();
-            unsigned long long ti = 0, tl = 0;
+            unsigned long long ti = s_slow, tl = 0;
 #pragma unroll
             for (int w = 0; w < NWARPS; w++) { ti += s_red[w]; tl += s_red[NWARPS + w]; }
             const bool ok = ti == tl;
+            __syncthreads();
+            if (threadIdx.x == 0) s_slow = 0;
             for (uint32_t i = threadIdx.x; i < S::NWORDS; i += THREADS) {
                 const uint32_t w = hist[i];
                 hist[i] = 0;
