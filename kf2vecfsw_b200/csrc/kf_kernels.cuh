@@ -315,13 +315,23 @@ struct SmemSink {   // per-CTA privatised u32 histogram in shared memory
 #ifdef KF_EMU
     uint32_t *hist;
     __device__ __forceinline__ void operator()(uint32_t off) const { atomicAdd(hist + (off >> 2), 1u); }
+    __device__ __forceinline__ void add_if(uint32_t off, uint32_t t, uint32_t bit) const { if (t & bit) atomicAdd(hist + (off >> 2), 1u); }
 #else
     uint32_t base;  // shared-window byte address of bin 0
     __device__ __forceinline__ void operator()(uint32_t off) const {
         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base + off) : "memory");
     }
+    // count iff (t & bit) != 0: one predicated RED, no branch
+    __device__ __forceinline__ void add_if(uint32_t off, uint32_t t, uint32_t bit) const {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 a;\n\tand.b32 a, %1, %2;\n\tsetp.ne.u32 p, a, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(base + off),
+                     "r"(t), "r"(bit)
+                     : "memory");
+    }
 #endif
 };
+template <class S> struct sink_has_add_if { static constexpr bool value = false; };
+template <> struct sink_has_add_if<SmemSink> { static constexpr bool value = true; };
+template <> struct sink_has_add_if<const SmemSink> { static constexpr bool value = true; };
 __device__ __forceinline__ SmemSink make_smem_sink(uint32_t *hist) {
     SmemSink s;
 #ifdef KF_EMU
@@ -1415,8 +1425,10 @@ __device__ __forceinline__ void fq_emit16(uint32_t hi, uint32_t lo, uint32_t bad
     const uint32_t ok = ~o & 0xFFFFu;
     if (ok) {
 #pragma unroll
-        for (int j = 0; j < 16; j++)
-            if ((ok >> j) & 1u) sink(kmer_off_at<K>(hi, lo, j));
+        for (int j = 0; j < 16; j++) {
+            if constexpr (sink_has_add_if<Sink>::value) sink.add_if(kmer_off_at<K>(hi, lo, j), ok, 1u << j);
+            else if ((ok >> j) & 1u) sink(kmer_off_at<K>(hi, lo, j));
+        }
     }
 }
 
