@@ -154,6 +154,11 @@ def workload_name(genomes, bases, k, world):
             "BASELINE.json configs[%d]" % (genomes, bases, k, 1 if world == 1 else 2))
 
 
+# SMs left to the overlapped all-gather when N > 1 (measured on 8 B200: 8 CTAs move the 262 MB gather in about the time
+# of one counting step, 4 are too few; 2 GPUs exchange a quarter of that)
+NCCL_CTAS = int(os.environ.get("KF_BENCH_NCCL_CTAS", "0"))
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -183,12 +188,22 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
+    from kf2vecfsw_b200 import dist as kfdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    global NCCL_CTAS
+    if NCCL_CTAS <= 0:
+        NCCL_CTAS = 4 if world <= 2 else 8
     if world > 1:
+        # the all-gather of batch i runs beside the counting of batch i+1: NCCL gets at most NCCL_CTAS CTAs, and the
+        # counting kernels (one persistent CTA per SM, ~205 KB of shared memory each) are sized for the other SMs
+        os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
         dist.init_process_group("nccl", device_id=dev)
     engine.init(local_rank)
+    sms_used = engine.set_sm_limit(0)
+    if world > 1:
+        sms_used = engine.set_sm_limit(sms_used - NCCL_CTAS)
     k, G, NB = args.k, args.genomes, args.bases
     V = engine.vocab_size(k)
     threads = max(1, host_threads() // max(1, world))
@@ -201,14 +216,17 @@ def main():
     freq = torch.empty((G, V), dtype=torch.float64, device=dev)
     feat = torch.empty((G, V), dtype=torch.float32, device=dev)
     totals = torch.empty(G, dtype=torch.int64, device=dev)
-    gathered = torch.empty((world * G, V), dtype=torch.float32, device=dev) if world > 1 else None
+    # N > 1: the [N, V] backbone matrix is assembled on every GPU by an all-gather that runs while the next batch is
+    # being counted (two buffer pairs); every gather completes inside the timed region (drain before the end event)
+    og = kfdist.OverlappedGather(G, V, torch.float32, dev) if world > 1 else None
     kernel_ms = []
 
     def step(record=False):
         # everything is enqueued on torch's current stream: no host synchronisation inside a step
-        engine.count_device(arena, k=k, counts=counts, freq=freq, feat=feat, totals=totals)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, feat)   # assemble the backbone frequency matrix on every GPU
+        f = og.slot() if og else feat
+        engine.count_device(arena, k=k, counts=counts, freq=freq, feat=f, totals=totals)
+        if og:
+            og.submit()
         if record:
             kernel_ms.append(engine.last_count_kernel_ms())   # (waits for the library's events: only outside the timed region)
 
@@ -229,6 +247,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    if og:
+        og.drain()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -304,7 +324,9 @@ def main():
                        "genomes_per_gpu": G, "bases_per_genome": NB, "k": k, "file_bytes_per_gpu": int(file_bytes),
                        "l2_policy": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed" % (file_bytes / 1e9),
                        "parallelism": "genome-sharded, one process per GPU, no collective on the counting path"
-                                      + ("; NCCL all-gather of the [N,8192] fp32 matrix inside the step" if world > 1 else "")},
+                                      + ("; NCCL all-gather of the [N,8192] fp32 matrix of every step inside the timed region, the gather of "
+                                         "step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, counting kernels sized "
+                                         "for %d of the SMs)" % (NCCL_CTAS, sms_used) if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "count_fasta_lines_kernel<80,512> (+ width probe; the 60/70-column and generic launches "

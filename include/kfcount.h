@@ -112,6 +112,11 @@ int kf_last_file_status(const uint8_t *d_arena, const uint64_t *offsets, const u
                         int *status_out);
 /* Number of kernels kf_count_device launched in its last call (for bench.py's gpu_launches). */
 int kf_last_launch_count(void);
+/* Size the persistent counting kernels for n_sms SMs instead of all of them (0 = all): leaves SMs free for a kernel
+ * that runs beside them, e.g. the NCCL all-gather of the previous batch's rows (one CTA per SM with ~205 KB of shared
+ * memory cannot share an SM, and a CTA that has to wait for one delays the whole launch).  Returns the SM count in
+ * effect, or a negative error code.  (No reference counterpart: jellyfish -t p, main.py:309, is the nearest knob.) */
+int kf_set_sm_limit(int n_sms);
 /* Device time of the counting kernel(s) of the last kf_count_device / kf_count_buffers call, from CUDA
  * events recorded on the launching stream (waits for them).  Used for the roofline figure. */
 int kf_last_count_kernel_ms(float *ms);

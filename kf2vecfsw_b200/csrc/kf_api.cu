@@ -28,6 +28,7 @@ constexpr int part_bases(int k) { return k - 8; }      // leading bases that sel
 struct Ctx {
     int device = -1;
     int sm_count = 0;
+    int sm_all = 0;   // the device's SM count; sm_count = SMs the counting kernels are sized for (kf_set_sm_limit)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     bool ev_valid = false;
@@ -519,7 +520,7 @@ int kf_init(int device) {
     CK(cudaEventCreate(&g.ev_k1));
     CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&g.d_item_counter, sizeof(unsigned int)));
-    g.sm_count = prop.multiProcessorCount;
+    g.sm_count = g.sm_all = prop.multiProcessorCount;
     g.device = device;
     return KF_OK;
 }
@@ -542,6 +543,13 @@ int kf_shutdown(void) {
 int kf_device(void) { return g.device >= 0 ? g.device : KF_ERR_NO_DEVICE; }
 const char *kf_last_cuda_error(void) { return g.last_err.c_str(); }
 int kf_last_launch_count(void) { return g.last_launches; }
+int kf_set_sm_limit(int n_sms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (n_sms < 0) return KF_ERR_ARG;
+    g.sm_count = (n_sms == 0 || n_sms > g.sm_all) ? g.sm_all : n_sms;
+    return g.sm_count;
+}
 int kf_last_count_kernel_ms(float *ms) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g.device < 0) return KF_ERR_NO_DEVICE;

@@ -44,3 +44,43 @@ def all_gather_rows(local, parts: List[List[int]], group=None):
             idx = torch.tensor(p, dtype=torch.long, device=local.device)
             full[idx] = out[r * m: r * m + len(p)]
     return full
+
+
+class OverlappedGather:
+    """The all-gather of batch i runs while batch i + 1 is being counted: two (local, gathered) buffer pairs used in
+    turn; ``slot()`` hands out the next local block to fill (after waiting for the gather that last read it),
+    ``submit()`` starts its all-gather without blocking, ``drain()`` orders every outstanding gather before whatever the
+    caller enqueues next.  With NCCL the waits are stream dependencies (no host synchronisation); with gloo (CPU tests)
+    they block."""
+
+    def __init__(self, rows: int, cols: int, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.local = [torch.empty((rows, cols), dtype=dtype, device=device) for _ in range(2)]
+        self.full = [torch.empty((self.world * rows, cols), dtype=dtype, device=device) for _ in range(2)]
+        self.pending = [None, None]
+        self.i = 0
+
+    def slot(self):
+        b = self.i & 1
+        if self.pending[b] is not None:
+            self.pending[b].wait()
+            self.pending[b] = None
+        return self.local[b]
+
+    def submit(self):
+        """Starts the all-gather of the block last handed out by slot(); returns the [world * rows, cols] tensor it
+        fills (valid after drain(), or after the slot() call two batches later)."""
+        import torch.distributed as dist
+        b = self.i & 1
+        self.pending[b] = dist.all_gather_into_tensor(self.full[b], self.local[b], group=self.group, async_op=True)
+        self.i += 1
+        return self.full[b]
+
+    def drain(self):
+        for b in (0, 1):
+            if self.pending[b] is not None:
+                self.pending[b].wait()
+                self.pending[b] = None

@@ -81,6 +81,8 @@ def _load():
     L.kf_last_file_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p]
     L.kf_last_launch_count.restype = ctypes.c_int
+    L.kf_set_sm_limit.argtypes = [ctypes.c_int]
+    L.kf_set_sm_limit.restype = ctypes.c_int
     L.kf_last_count_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float)]
     L.kf_format_row.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_char_p,
                                 ctypes.c_size_t]
@@ -289,6 +291,15 @@ def last_file_status(arena: DeviceArena) -> np.ndarray:
                                        arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, status.ctypes.data),
            "kf_last_file_status")
     return status
+
+
+def set_sm_limit(n_sms: int) -> int:
+    """Sizes the persistent counting kernels for n_sms SMs (0 = all); returns the SM count in effect."""
+    _require_init()
+    rc = int(_load().kf_set_sm_limit(int(n_sms)))
+    if rc < 0:
+        raise KfError(rc, "kf_set_sm_limit")
+    return rc
 
 
 def last_launch_count() -> int:
