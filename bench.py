@@ -201,6 +201,7 @@ def main():
         os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
         dist.init_process_group("nccl", device_id=dev)
     engine.init(local_rank)
+    numa_node = engine.bind_host_to_gpu(local_rank) if world > 1 else None   # before any pinned host allocation
     sms_used = engine.set_sm_limit(0)
     if world > 1:
         sms_used = engine.set_sm_limit(sms_used - NCCL_CTAS)
@@ -291,7 +292,8 @@ def main():
         e2e = {"value": world * G * NB * args.steps / float(dt.item()) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(file_bytes), "d2h_bytes_per_step": int(G * V * 16 + G * 8),
                "ms_per_step": float(dt.item()) / args.steps * 1e3, "parity_ok": e2e_ok,
-               "api": "kf_count_buffers (C ABI, pinned host buffers in, counts+frequencies out)"}
+               "api": "kf_count_buffers (C ABI, pinned host buffers in, counts+frequencies out)",
+               "host_numa_node_rank0": numa_node}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -293,6 +293,33 @@ def last_file_status(arena: DeviceArena) -> np.ndarray:
     return status
 
 
+def bind_host_to_gpu(device: int) -> Optional[int]:
+    """Pins this process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), so
+    that the pinned host buffers it allocates afterwards, and the threads that fill them, are local to the GPU's PCIe
+    root: with one process per GPU on a two-socket box the host-to-device copies otherwise cross the socket link.
+    Returns the NUMA node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use or use == allowed:
+            return None
+        os.sched_setaffinity(0, use)
+        node = int(open(base + "/numa_node").read().strip())
+        return node
+    except Exception:
+        return None
+
+
 def set_sm_limit(n_sms: int) -> int:
     """Sizes the persistent counting kernels for n_sms SMs (0 = all); returns the SM count in effect."""
     _require_init()
