@@ -84,6 +84,16 @@ int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens, int n, int 
 int kf_count_files(const char *const *paths, int n, int k, uint32_t flags,
                    uint64_t *counts_out, double *freq_out, uint64_t *totals_out, int *status_out);
 
+/* The whole loop of get_frequencies (kf2vec/main.py:301-370: per file jellyfish count + dump, merge, pseudocount,
+ * normalise, write <sample>.kf) for n files, as a three-stage pipeline over batches of at most batch_bytes (0: 256 MiB):
+ * `threads` host threads (0: all) read batch b+1 into pinned memory while the GPU counts batch b and the threads format
+ * and write the rows of batch b-1.  out_paths[i] receives the row of in_paths[i] labelled samples[i] (text exactly as
+ * kf_write_kf); files whose status is not KF_OK get no output.  totals_out [n] (may be NULL); stage_seconds [4] (may be
+ * NULL): host time spent waiting for reads, in the GPU stage, waiting for writes, and in total. */
+int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, const char *const *samples, int n, int k,
+                   uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out,
+                   double *stage_seconds);
+
 /* ---- chunked-genome mode: one row per sliding window (get_chunks, main.py:813-881) -------------------------- */
 /* Replaces, per 10-kbp chunk, `seqkit sliding` + `seqkit split` + the jellyfish count/dump pair the reference runs
  * on every chunk file (main.py:824-838, 869-881).  seq is the linearised, N-collapsed, gap-stripped sequence of one

@@ -4,7 +4,16 @@
 #include "kf_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <queue>
+#include <thread>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -66,6 +75,10 @@ struct Ctx {
     unsigned long long *d_counts = nullptr; size_t counts_cap = 0;
     double *d_freq = nullptr; size_t freq_cap = 0;
     unsigned long long *d_totals = nullptr; size_t totals_cap = 0;
+    // kf_files_to_kf: two pinned input slabs and two pinned output blocks (grow-only)
+    uint8_t *h_slab[2] = {nullptr, nullptr}; size_t h_slab_cap[2] = {0, 0};
+    double *h_freq[2] = {nullptr, nullptr}; size_t h_freq_cap[2] = {0, 0};
+    unsigned long long *h_cnt[2] = {nullptr, nullptr}; size_t h_cnt_cap[2] = {0, 0};
     // plan cache
     std::vector<uint64_t> pc_offsets, pc_lens;
     std::vector<uint8_t> pc_formats;
@@ -720,6 +733,256 @@ int kf_count_files(const char *const *paths, int n, int k, uint32_t flags, uint6
     for (int i = 0; i < n; i++)
         if (io_fail[(size_t)i]) status_out[i] = KF_ERR_IO;
     return rc;
+}
+
+}  // extern "C"
+
+namespace kf {
+namespace {
+
+template <typename T>
+int ensure_pinned(T *&ptr, size_t &cap, size_t need_bytes) {
+    if (need_bytes <= cap) return KF_OK;
+    if (ptr) { CK(cudaFreeHost(ptr)); ptr = nullptr; cap = 0; }
+    if (cudaHostAlloc((void **)&ptr, need_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        g.last_err = "cudaHostAlloc failed";
+        return KF_ERR_NOMEM;
+    }
+    cap = need_bytes;
+    return KF_OK;
+}
+
+// Minimal worker pool of one kf_files_to_kf call: tasks are file reads and .kf writes.
+class Pool {
+public:
+    explicit Pool(int n) {
+        for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void push(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(mu_); q_.push(std::move(f)); pending_++; }
+        cv_.notify_one();
+    }
+    void wait_all() {
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop();
+            }
+            f();
+            { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_cv_.notify_all(); }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::queue<std::function<void()>> q_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+}  // namespace kf
+
+extern "C" {
+
+// Files on disk -> .kf files on disk (the whole of get_frequencies' loop, main.py:301-370), as a three-stage pipeline over
+// batches of files: worker threads read batch b+1 into a pinned slab (laid out as the device arena: 512-byte file starts,
+// NUL gaps) while the GPU counts batch b (ONE host-to-device copy of the slab, kernels, device-to-host copy of the rows)
+// and the workers format and write the .kf rows of batch b-1.
+int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, const char *const *samples, int n, int k,
+                   uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out, double *stage_seconds) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (!in_paths || !out_paths || !samples || !status_out || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
+    if (stage_seconds) for (int i = 0; i < 4; i++) stage_seconds[i] = 0.0;
+    if (n == 0) return KF_OK;
+    const double t_begin = now_s();
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = std::min(threads, 64);
+    if (batch_bytes == 0) batch_bytes = (size_t)256 << 20;
+    const int64_t V = kf_vocab_size(k);
+    const bool raw = (flags & KF_FLAG_RAW_CNT) != 0, pc = (flags & KF_FLAG_PSEUDOCOUNT) != 0;
+    const bool want_counts = raw && !pc;   // the reference prints integers only for raw rows with no missing k-mer
+
+    // sizes and batches (file order kept)
+    std::vector<uint64_t> fsize((size_t)n, 0);
+    for (int i = 0; i < n; i++) {
+        struct stat st;
+        status_out[i] = KF_OK;
+        if (!in_paths[i] || stat(in_paths[i], &st) != 0 || !S_ISREG(st.st_mode)) status_out[i] = KF_ERR_IO;
+        else fsize[(size_t)i] = (uint64_t)st.st_size;
+        if (totals_out) totals_out[i] = 0;
+    }
+    struct Batch { int i0, i1; uint64_t bytes; };
+    std::vector<Batch> batches;
+    {
+        int i0 = 0;
+        uint64_t cur = 0;
+        for (int i = 0; i < n; i++) {
+            const uint64_t padded = (fsize[(size_t)i] + CHUNK - 1) / CHUNK * CHUNK;
+            if (i > i0 && cur + padded > batch_bytes) { batches.push_back({i0, i, cur}); i0 = i; cur = 0; }
+            cur += padded;
+        }
+        batches.push_back({i0, n, cur});
+    }
+    const int nb = (int)batches.size();
+    std::vector<std::vector<uint64_t>> b_off((size_t)nb), b_len((size_t)nb);
+    std::vector<std::vector<uint8_t>> b_fmt((size_t)nb);
+    std::vector<std::atomic<int>> io_fail((size_t)n);
+    for (auto &a : io_fail) a.store(0);
+
+    kf::Pool pool(threads);
+    double t_read = 0, t_gpu = 0, t_write = 0;
+
+    auto issue_reads = [&](int b) -> int {
+        const Batch &B = batches[(size_t)b];
+        const int sl = b & 1;
+        int rc = ensure_pinned(g.h_slab[sl], g.h_slab_cap[sl], (size_t)B.bytes + KF_TAIL_PAD);
+        if (rc != KF_OK) return rc;
+        auto &off = b_off[(size_t)b];
+        auto &len = b_len[(size_t)b];
+        off.assign((size_t)(B.i1 - B.i0), 0);
+        len.assign((size_t)(B.i1 - B.i0), 0);
+        b_fmt[(size_t)b].assign((size_t)(B.i1 - B.i0), 0);
+        uint64_t o = 0;
+        for (int i = B.i0; i < B.i1; i++) {
+            off[(size_t)(i - B.i0)] = o;
+            len[(size_t)(i - B.i0)] = status_out[i] == KF_OK ? fsize[(size_t)i] : 0;
+            o += (fsize[(size_t)i] + CHUNK - 1) / CHUNK * CHUNK;
+        }
+        memset(g.h_slab[sl] + B.bytes, 0, KF_TAIL_PAD);
+        for (int i = B.i0; i < B.i1; i++) {
+            uint8_t *dst = g.h_slab[sl] + off[(size_t)(i - B.i0)];
+            const uint64_t L = len[(size_t)(i - B.i0)];
+            const uint64_t padded = (fsize[(size_t)i] + CHUNK - 1) / CHUNK * CHUNK;
+            const char *path = in_paths[i];
+            std::atomic<int> *fail = &io_fail[(size_t)i];
+            pool.push([dst, L, padded, path, fail] {
+                uint64_t got = 0;
+                if (L) {
+                    const int fd = open(path, O_RDONLY);
+                    if (fd < 0) fail->store(1);
+                    else {
+                        while (got < L) {
+                            const ssize_t r = pread(fd, dst + got, (size_t)std::min<uint64_t>(L - got, (uint64_t)64 << 20), (off_t)got);
+                            if (r <= 0) { fail->store(1); break; }
+                            got += (uint64_t)r;
+                        }
+                        close(fd);
+                    }
+                }
+                memset(dst + got, 0, (size_t)(padded - got));   // the gap up to the next file start must read as NUL
+            });
+        }
+        return KF_OK;
+    };
+
+    int rc_all = KF_OK;
+    {
+        const double t0 = now_s();
+        rc_all = issue_reads(0);
+        pool.wait_all();
+        t_read += now_s() - t0;
+    }
+    for (int b = 0; b < nb && rc_all == KF_OK; b++) {
+        const Batch &B = batches[(size_t)b];
+        const int sl = b & 1, nf = B.i1 - B.i0;
+        auto &off = b_off[(size_t)b];
+        auto &len = b_len[(size_t)b];
+        auto &fmt = b_fmt[(size_t)b];
+        // the reads of this batch are complete (waited for below / above): classify the files
+        for (int j = 0; j < nf; j++) {
+            const int i = B.i0 + j;
+            if (io_fail[(size_t)i].load()) { status_out[i] = KF_ERR_IO; len[(size_t)j] = 0; }
+            if (status_out[i] != KF_OK) { fmt[(size_t)j] = 0; len[(size_t)j] = 0; continue; }
+            if (len[(size_t)j] == 0) { status_out[i] = KF_ERR_EMPTY; fmt[(size_t)j] = 0; continue; }
+            fmt[(size_t)j] = g.h_slab[sl][off[(size_t)j]];
+            if (fmt[(size_t)j] != '>' && fmt[(size_t)j] != '@') { status_out[i] = KF_ERR_FORMAT; len[(size_t)j] = 0; }
+        }
+        // next batch's reads and the previous batch's writes run beside this batch's GPU work
+        const double t1 = now_s();
+        if (b + 1 < nb && (rc_all = issue_reads(b + 1)) != KF_OK) break;
+        const size_t arena_bytes = (size_t)B.bytes + KF_TAIL_PAD;
+        int rc;
+        if ((rc = ensure(g.d_arena, g.arena_cap, arena_bytes)) != KF_OK) { rc_all = rc; break; }
+        if ((rc = ensure(g.d_counts, g.counts_cap, (size_t)nf * V * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
+        if ((rc = ensure(g.d_freq, g.freq_cap, (size_t)nf * V * sizeof(double))) != KF_OK) { rc_all = rc; break; }
+        if ((rc = ensure(g.d_totals, g.totals_cap, (size_t)nf * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
+        if ((rc = ensure_pinned(g.h_freq[sl], g.h_freq_cap[sl], (size_t)nf * V * sizeof(double))) != KF_OK) { rc_all = rc; break; }
+        if (want_counts && (rc = ensure_pinned(g.h_cnt[sl], g.h_cnt_cap[sl], (size_t)nf * V * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
+        std::vector<unsigned long long> h_tot((size_t)nf, 0ull);
+        CK(cudaMemcpyAsync(g.d_arena, g.h_slab[sl], arena_bytes, cudaMemcpyHostToDevice, g.stream));
+        rc = count_device_locked(g.d_arena, arena_bytes, off.data(), len.data(), fmt.data(), nf, k, flags, g.d_counts, g.d_freq, nullptr,
+                                 g.d_totals, g.stream);
+        if (rc != KF_OK) { rc_all = rc; break; }
+        CK(cudaMemcpyAsync(g.h_freq[sl], g.d_freq, (size_t)nf * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        if (want_counts) CK(cudaMemcpyAsync(g.h_cnt[sl], g.d_counts, (size_t)nf * V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaMemcpyAsync(h_tot.data(), g.d_totals, (size_t)nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        if (g.fq_err_n > 0) {   // 4-line FASTQ layout check, as in kf_count_buffers
+            g.h_fq_err.resize((size_t)nf);
+            CK(cudaMemcpy(g.h_fq_err.data(), g.d_fq_err, (size_t)nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (int j = 0; j < nf; j++) {
+                const int i = B.i0 + j;
+                if (fmt[(size_t)j] != '@' || status_out[i] != KF_OK) continue;
+                const unsigned long long e = g.h_fq_err[(size_t)j];
+                if (e == ~0ull || e < off[(size_t)j] || e - off[(size_t)j] >= len[(size_t)j]) continue;
+                bool only_eol = true;
+                for (uint64_t p = e; p < off[(size_t)j] + len[(size_t)j] && only_eol; p++)
+                    only_eol = g.h_slab[sl][p] == '\n' || g.h_slab[sl][p] == '\r';
+                if (!only_eol) status_out[i] = KF_ERR_FASTQ;
+            }
+        }
+        const double t2 = now_s();
+        t_gpu += t2 - t1;
+        // everything queued before this point (writes of batch b-1, reads of batch b+1) must be done before the output
+        // block of batch b-1's parity is reused two batches on; simplest: drain the pool here
+        pool.wait_all();
+        const double t3 = now_s();
+        t_read += t3 - t2;
+        for (int j = 0; j < nf; j++) {
+            const int i = B.i0 + j;
+            if (totals_out) totals_out[i] = h_tot[(size_t)j];
+            if (status_out[i] != KF_OK) continue;
+            const double *row = g.h_freq[sl] + (size_t)j * V;
+            const unsigned long long *crow = want_counts ? g.h_cnt[sl] + (size_t)j * V : nullptr;
+            const char *outp = out_paths[i], *smp = samples[i];
+            int *st = &status_out[i];
+            pool.push([row, crow, outp, smp, st, V] {
+                int int_mode = 0;
+                if (crow) {
+                    int_mode = 1;
+                    for (int64_t v = 0; v < V; v++) if (crow[v] == 0) { int_mode = 0; break; }
+                }
+                const int w = kf_write_kf(outp, smp, row, V, int_mode, 0);
+                if (w != KF_OK) *st = w;
+            });
+        }
+    }
+    {
+        const double t0 = now_s();
+        pool.wait_all();
+        t_write += now_s() - t0;
+    }
+    if (stage_seconds) { stage_seconds[0] = t_read; stage_seconds[1] = t_gpu; stage_seconds[2] = t_write; stage_seconds[3] = now_s() - t_begin; }
+    return rc_all;
 }
 
 }  // extern "C"

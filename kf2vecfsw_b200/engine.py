@@ -320,6 +320,28 @@ def bind_host_to_gpu(device: int) -> Optional[int]:
         return None
 
 
+def files_to_kf(in_paths: Sequence[str], out_paths: Sequence[str], samples: Sequence[str], k: int = 7,
+                pseudocount: bool = False, raw_cnt: bool = False, threads: int = 0, batch_bytes: int = 0):
+    """Files on disk -> .kf files on disk through the pipelined C entry point (reads, GPU, writes overlapped).
+    Returns (status i32 [n], totals u64 [n], stage seconds [read wait, gpu, write wait, total])."""
+    _require_init()
+    L = _load()
+    n = len(in_paths)
+    assert len(out_paths) == n and len(samples) == n
+    enc = lambda xs: (ctypes.c_char_p * max(n, 1))(*[os.fsencode(x) for x in xs])
+    status = np.zeros(n, dtype=np.int32)
+    totals = np.zeros(n, dtype=np.uint64)
+    secs = np.zeros(4, dtype=np.float64)
+    L.kf_files_to_kf.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_files_to_kf.restype = ctypes.c_int
+    rc = L.kf_files_to_kf(enc(in_paths), enc(out_paths), enc(samples), n, k, _flags(pseudocount, raw_cnt), int(threads),
+                          int(batch_bytes), status.ctypes.data, totals.ctypes.data, secs.ctypes.data)
+    _check(rc, "kf_files_to_kf")
+    return status, totals, secs
+
+
 def set_sm_limit(n_sms: int) -> int:
     """Sizes the persistent counting kernels for n_sms SMs (0 = all); returns the SM count in effect."""
     _require_init()

@@ -20,7 +20,7 @@ from . import engine
 
 FORMATS = ['.fq', '.fastq', '.fa', '.fna', '.fasta']  # main.py:272
 DEFAULT_K = 7                                          # main.py:80
-BATCH_BYTES = 4 << 30                                  # host bytes staged per library call
+BATCH_BYTES = 256 << 20                                # host bytes staged per pipeline batch (two pinned slabs)
 
 
 def list_inputs(input_dir: str) -> Tuple[List[str], List[str]]:
@@ -65,24 +65,22 @@ def get_frequencies(args) -> None:
     paths = [os.path.join(args.input_dir, f) for f in files_names]
     V = engine.vocab_size(k)
 
-    for batch in _batches(paths):
-        bufs = [np.fromfile(paths[i], dtype=np.uint8) for i in batch]
-        counts, freq, totals, status = engine.count_buffers(bufs, k=k, pseudocount=pseudocount, raw_cnt=raw_cnt)
-        for j, i in enumerate(batch):
-            if status[j] != 0:
-                # The reference ignores jellyfish's exit code and then dies with IndexError at main.py:315;
-                # fail with the real cause instead of writing a bogus row.
-                raise engine.KfError(int(status[j]), "k-mer counting failed for {}".format(files_names[i]))
-            if pseudocount:
-                print('>>> Adding pseudocounts. Sample: {}'.format(files_names[i]))       # main.py:333
-            if not raw_cnt:
-                print('>>> Normalizing. Sample: {}'.format(files_names[i]))               # main.py:341
-            # pandas keeps the merged column int64 only when no vocabulary k-mer is missing (main.py:327-328):
-            # then str() prints "5", otherwise "5.0".
-            int_mode = raw_cnt and not pseudocount and bool(np.all(counts[j] > 0))
-            f3 = os.path.join(args.output_dir, "{}.{}".format(samples_names[i], "kf"))
-            engine.write_kf(f3, str(samples_names[i]), freq[j], int_mode=int_mode)
-        del bufs
+    # One pipelined library call: host threads read the next batch of files into pinned memory while the GPU counts the
+    # current one and the rows of the previous one are formatted and written (kf_files_to_kf).  args.p -- jellyfish's
+    # thread count in the reference (main.py:309) -- is the number of those host threads.
+    outs = [os.path.join(args.output_dir, "{}.{}".format(s, "kf")) for s in samples_names]
+    threads = int(getattr(args, 'p', 0) or 0)
+    status, totals, _ = engine.files_to_kf(paths, outs, [str(s) for s in samples_names], k=k, pseudocount=pseudocount,
+                                           raw_cnt=raw_cnt, threads=threads, batch_bytes=BATCH_BYTES)
+    for i in range(len(paths)):
+        if status[i] != 0:
+            # The reference ignores jellyfish's exit code and then dies with IndexError at main.py:315;
+            # fail with the real cause instead of writing a bogus row.
+            raise engine.KfError(int(status[i]), "k-mer counting failed for {}".format(files_names[i]))
+        if pseudocount:
+            print('>>> Adding pseudocounts. Sample: {}'.format(files_names[i]))       # main.py:333
+        if not raw_cnt:
+            print('>>> Normalizing. Sample: {}'.format(files_names[i]))               # main.py:341
 
     print('\n==> Done processing {}'.format(args.input_dir))
 

@@ -358,3 +358,37 @@ def test_partitioned_kernel_large_k(eng, k):
     assert int(r.max()) > 4_000_000
     counts, freq, totals, status = eng.count_buffers([data], k=k)
     assert np.array_equal(counts[0], r)
+
+
+@pytest.mark.gpu
+def test_files_to_kf_pipeline_matches_buffer_path(eng, toy_inputs, tmp_path):
+    """kf_files_to_kf (reads / GPU / writes pipelined over batches) writes byte-for-byte what count_buffers + write_kf
+    write, over several batches (tiny batch_bytes), FASTA and FASTQ, with unreadable / empty / non-sequence files
+    reported per file and skipped; -raw_cnt rows switch to integers only when no k-mer is missing."""
+    rng = random.Random(77)
+    data = {"a": toy_inputs["G000830275sub"], "b": rand_fastq(rng), "c": toy_inputs["G000402355sub"], "d": rand_fasta_grid(rng),
+            "e": b"", "f": b"not a sequence file\n", "g": eng.synth_fasta(3, 0, 400_000).tobytes()}
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir(); outd.mkdir()
+    names = sorted(data)
+    paths = []
+    for s in names:
+        p = ind / (s + ".fa")
+        p.write_bytes(data[s])
+        paths.append(str(p))
+    paths.append(str(ind / "missing.fa"))
+    names.append("missing")
+    for raw in (False, True):
+        outs = [str(outd / ("%s_%d.kf" % (s, raw))) for s in names]
+        status, totals, secs = eng.files_to_kf(paths, outs, names, k=7, raw_cnt=raw, threads=3, batch_bytes=600_000)
+        ok = [s for s in names if s not in ("e", "f", "missing")]
+        assert [int(status[names.index(s)]) for s in ok] == [0] * len(ok)
+        assert all(int(status[names.index(s)]) != 0 for s in ("e", "f", "missing"))
+        counts, freq, tot, st = eng.count_buffers([data[s] for s in ok], k=7, raw_cnt=raw)
+        for j, s in enumerate(ok):
+            ref = str(outd / "ref.kf")
+            eng.write_kf(ref, s, freq[j], int_mode=bool(raw and np.all(counts[j] > 0)))
+            assert open(outs[names.index(s)], "rb").read() == open(ref, "rb").read(), (s, raw)
+            assert int(totals[names.index(s)]) == int(tot[j])
+        for s in ("e", "f", "missing"):
+            assert not os.path.exists(outs[names.index(s)])
