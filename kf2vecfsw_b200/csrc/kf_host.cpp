@@ -12,6 +12,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 namespace kf {
 
@@ -243,19 +245,46 @@ int kf_write_kf_rows(const char *out_path, const char *labels, const double *row
     if (!out_path || !labels || !rows || n < 0 || V < 0) return KF_ERR_ARG;
     FILE *f = fopen(out_path, append ? "ab" : "wb");
     if (!f) return KF_ERR_IO;
-    std::vector<char> buf;
-    const char *lab = labels;
-    int rc = KF_OK;
-    for (int64_t i = 0; i < n && rc == KF_OK; i++) {
-        const size_t sl = strlen(lab);
-        buf.resize(sl + 2 + (size_t)V * 32 + 1);
-        const int64_t m = kf_format_row(lab, rows + (size_t)i * (size_t)V, V, int_modes ? int_modes[i] : 0, buf.data(), buf.size());
-        if (m < 0) rc = (int)m;
-        else if (fwrite(buf.data(), 1, (size_t)m, f) != (size_t)m) rc = KF_ERR_IO;
-        lab += sl + 1;
+    std::vector<const char *> lab((size_t)n);
+    {
+        const char *p = labels;
+        for (int64_t i = 0; i < n; i++) { lab[(size_t)i] = p; p += strlen(p) + 1; }
     }
-    if (fclose(f) != 0 && rc == KF_OK) rc = KF_ERR_IO;
-    return rc;
+    // rows are formatted by several threads in blocks of consecutive rows (a row is ~8,192 numbers), each block into its
+    // own buffer; the blocks are written in order
+    const int64_t BLOCK = 16;
+    const int64_t nblocks = (n + BLOCK - 1) / BLOCK;
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(nblocks, 16), (int64_t)std::thread::hardware_concurrency()));
+    std::vector<std::vector<char>> out((size_t)nblocks);
+    std::atomic<int64_t> next(0);
+    std::atomic<int> rc(KF_OK);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t b = next.fetch_add(1);
+            if (b >= nblocks) return;
+            std::vector<char> &buf = out[(size_t)b];
+            size_t used = 0;
+            for (int64_t i = b * BLOCK; i < std::min(n, (b + 1) * BLOCK); i++) {
+                const size_t need = strlen(lab[(size_t)i]) + 2 + (size_t)V * 32 + 1;
+                if (buf.size() < used + need) buf.resize(std::max(buf.size() * 2, used + need));
+                const int64_t m = kf_format_row(lab[(size_t)i], rows + (size_t)i * (size_t)V, V, int_modes ? int_modes[i] : 0, buf.data() + used, need);
+                if (m < 0) { rc.store((int)m); return; }
+                used += (size_t)m;
+            }
+            buf.resize(used);
+        }
+    };
+    if (T <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work);
+        for (auto &t : th) t.join();
+    }
+    int r = rc.load();
+    for (int64_t b = 0; b < nblocks && r == KF_OK; b++)
+        if (!out[(size_t)b].empty() && fwrite(out[(size_t)b].data(), 1, out[(size_t)b].size(), f) != out[(size_t)b].size()) r = KF_ERR_IO;
+    if (fclose(f) != 0 && r == KF_OK) r = KF_ERR_IO;
+    return r;
 }
 
 // ---- chunked-genome text preparation: main.py:730-753 ------------------------------------------------------------
