@@ -57,8 +57,10 @@ struct Ctx {
     // k = 8..10: (file, partition) work items of the partitioned shared-memory kernel
     int *d_file_t0 = nullptr; size_t ft0_cap = 0;
     uint32_t *d_items = nullptr; size_t items_cap = 0;
-    unsigned int *d_item_counter = nullptr;
-    int pc_items = 0;
+    unsigned int *d_item_counter = nullptr;   // [2]: pass A (or the only pass), pass B
+    int pc_items = 0;        // items of the text pass: (file, 0)
+    int pc_items_b = 0;      // items of the stream passes: (file, p >= 1), stored after the first pc_items
+    uint2 *d_stream = nullptr; size_t stream_cap = 0;   // decoded pieces of pass A: 8 bytes per 16 bytes of arena
     uint32_t pc_part_mode = 0;
     // FASTQ plan: 128 KiB tiles (32 lane ranges), layout-violation offsets
     Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
@@ -282,13 +284,28 @@ int launch_gmem(const uint8_t *d_arena, int grid, bool force_walker, uint32_t fi
         if (g.pc_items > 0 && !force_walker) {
             constexpr int PB = part_bases(K);
             constexpr size_t smem = PartSink<K, PB>::NWORDS * sizeof(uint32_t);
-            auto kern = count_fasta_part_kernel<K, PB, THREADS_PART>;
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CK(cudaMemsetAsync(g.d_item_counter, 0, sizeof(unsigned int), s));
-            kern<<<std::min(g.sm_count, g.pc_items), THREADS_PART, smem, s>>>(d_arena, g.d_tiles, g.d_file_t0, g.d_items, g.pc_items, fwd, file_base,
-                                                                             g.d_item_counter);
-            CK(cudaGetLastError());
-            g.last_launches++;
+            CK(cudaMemsetAsync(g.d_item_counter, 0, 2 * sizeof(unsigned int), s));
+            if constexpr (PB == 0) {
+                auto kern = count_fasta_part_kernel<K, PB, THREADS_PART, 0>;
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<std::min(g.sm_count, g.pc_items), THREADS_PART, smem, s>>>(d_arena, g.d_tiles, g.d_file_t0, g.d_items, g.pc_items, fwd,
+                                                                                 file_base, g.d_item_counter, nullptr);
+                CK(cudaGetLastError());
+                g.last_launches++;
+            } else {
+                // pass A parses the text once (partition 0 + the decoded stream), pass B counts the other partitions from it
+                auto ka = count_fasta_part_kernel<K, PB, THREADS_PART, 1>;
+                auto kb = count_fasta_part_kernel<K, PB, THREADS_PART, 2>;
+                CK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ka<<<std::min(g.sm_count, g.pc_items), THREADS_PART, smem, s>>>(d_arena, g.d_tiles, g.d_file_t0, g.d_items, g.pc_items, fwd, file_base,
+                                                                               g.d_item_counter, g.d_stream);
+                CK(cudaGetLastError());
+                kb<<<std::min(g.sm_count, g.pc_items_b), THREADS_PART, smem, s>>>(d_arena, g.d_tiles, g.d_file_t0, g.d_items + g.pc_items, g.pc_items_b, fwd,
+                                                                                 file_base, g.d_item_counter + 1, g.d_stream);
+                CK(cudaGetLastError());
+                g.last_launches += 2;
+            }
         }
     }
     const uint32_t *skip = (g.pc_items > 0 && !force_walker) ? g.d_file_P : nullptr;   // files taken by the partitioned kernel
@@ -381,20 +398,24 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 }
                 file_t0[f1] = (int)t;
             }
-            std::vector<uint32_t> items, taken((size_t)f1, 0u);
+            std::vector<uint32_t> items, items_b, taken((size_t)f1, 0u);
             const uint32_t P = 1u << (2 * part_bases(k));
             for (uint32_t f = f0; f < f1; f++) {
                 if (formats[f] != '>' || lens[f] == 0 || (lens[f] < PART_MIN_BYTES && part_mode != 2)) continue;
                 taken[f] = 1u;
-                for (uint32_t pp = 0; pp < P; pp++) items.push_back((f << 8) | pp);
+                items.push_back(f << 8);                                               // text pass: partition 0
+                for (uint32_t pp = 1; pp < P; pp++) items_b.push_back((f << 8) | pp);  // stream passes, a file's side by side
             }
-            if (f1 >= (1u << 24)) items.clear(), std::fill(taken.begin(), taken.end(), 0u);   // (file id must fit the item word)
+            if (f1 >= (1u << 24)) items.clear(), items_b.clear(), std::fill(taken.begin(), taken.end(), 0u);   // (file id must fit the item word)
+            g.pc_items_b = (int)items_b.size();
+            const size_t n_a = items.size();
+            items.insert(items.end(), items_b.begin(), items_b.end());
             if ((rc = ensure(g.d_file_t0, g.ft0_cap, file_t0.size() * sizeof(int))) != KF_OK) return rc;
             if ((rc = ensure(g.d_items, g.items_cap, (items.size() + 1) * sizeof(uint32_t))) != KF_OK) return rc;
             CK(cudaMemcpy(g.d_file_t0, file_t0.data(), file_t0.size() * sizeof(int), cudaMemcpyHostToDevice));
             if (!items.empty()) CK(cudaMemcpy(g.d_items, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(g.d_file_P, taken.data(), (size_t)f1 * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            g.pc_items = (int)items.size();
+            g.pc_items = (int)n_a;
         }
         if (smem_path) {
             std::vector<uint32_t> file_row, cta_first_rank;
@@ -414,6 +435,11 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     const size_t fwd_bytes = smem_path ? (size_t)g.pc_rows * NB * sizeof(unsigned long long) : (size_t)nf * NB * sizeof(uint32_t);
     if ((rc = ensure(g.d_fwd, g.fwd_cap, fwd_bytes)) != KF_OK) return rc;
     if (!smem_path) CK(cudaMemsetAsync(g.d_fwd, 0, fwd_bytes, s));   // (k <= 7: the probe kernel zeroes what needs it)
+    if (g.pc_items_b > 0) {
+        // decoded stream of the multi-pass path: one uint2 per 16-byte piece up to the batch's last file
+        const size_t end = (size_t)((offsets[f1 - 1] + lens[f1 - 1] + CHUNK - 1) / CHUNK + 2);
+        if ((rc = ensure(g.d_stream, g.stream_cap, end * 32 * sizeof(uint2))) != KF_OK) return rc;
+    }
     const bool force_walker = (flags & KF_FLAG_FORCE_WALKER) != 0;
     const bool use_lg = smem_path && k == 7 && !force_walker && !(flags & KF_FLAG_NO_LINEGRID);
     if (smem_path) {
@@ -532,7 +558,7 @@ int kf_init(int device) {
     CK(cudaEventCreate(&g.ev_k0));
     CK(cudaEventCreate(&g.ev_k1));
     CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&g.d_item_counter, sizeof(unsigned int)));
+    CK(cudaMalloc((void **)&g.d_item_counter, 2 * sizeof(unsigned int)));
     g.sm_count = g.sm_all = prop.multiProcessorCount;
     g.device = device;
     return KF_OK;

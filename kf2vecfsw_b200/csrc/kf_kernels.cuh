@@ -246,6 +246,9 @@ template <class S> struct sink_takes_window { static constexpr bool value = fals
 // What the rare paths (byte walker, out of line) count into: a by-value functor, so that the address of the sink proper
 // is never taken and its state stays in registers on the hot path.  Default: a copy of the sink.
 template <class S> __device__ __forceinline__ S sink_slow(const S &s) { return s; }
+// A sink may want to see EVERY lane of every chunk (record(chunk * 32 + lane, fast, hi, lo, n): fast = the lane's k-mers
+// go through window()/operator() of the fast path, otherwise through the rare paths or nowhere).
+template <class S> struct sink_records_lanes { static constexpr bool value = false; };
 template <int K, bool FORCE_WALKER, int PF, class Sink, class Src>
 __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, uint32_t c1, uint32_t file_c0, Sink &sink,
                                                     uint64_t own_lo = 0, uint64_t own_hi = ~0ull,
@@ -285,11 +288,12 @@ __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, 
                 const bool outside = pb + 16 <= own_lo || pb >= own_hi;
                 const bool cut = pb < own_lo || pb + 16 > own_hi;
                 const bool slow = FORCE_WALKER || slowflag || (nbw & 1u) || cut;
+                const uint32_t nb = nbw & ~3u;
+                uint32_t hi = cur.bits, lo = nb;
+                if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
+                if constexpr (sink_records_lanes<Sink>::value) sink.record((size_t)c * 32 + (size_t)lane, !outside && !slow, hi, lo, cur.n);
                 if (outside) {
                 } else if (!slow) {
-                    const uint32_t nb = nbw & ~3u;
-                    uint32_t hi = cur.bits, lo = nb;
-                    if (cur.n == 15) { hi |= nb >> 30; lo = nb << 2; }
                     if constexpr (sink_takes_window<Sink>::value) {
                         sink.window(hi, lo, cur.n);
                     } else {
@@ -515,6 +519,13 @@ struct PartSink {
     // sv: the k-mer (at least its low 2(K-PB) bits) on bits 2(K-PB):1
     __device__ __forceinline__ void add(uint32_t sv) { red_shared_add(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u); }
     uint32_t *s_slow;  // shared: REDs issued by the rare paths since the last drain
+    uint32_t *g_row;   // pass A of a multi-pass count: the file's row, for the rare paths' k-mers of OTHER partitions
+    uint2 *stream;     // pass A: every lane's decoded piece goes here for the passes over the other partitions
+    // stream entry: x = hi, y = lo with bit 0 = "not a fast lane" (nothing to count from the stream), bit 1 = 15 k-mers
+    // (lo's low two bits are never part of a k-mer: the last one, j = 15, ends at base 24 for K = 10)
+    __device__ __forceinline__ void record(size_t idx, bool fast, uint32_t hi, uint32_t lo, uint32_t n) const {
+        if (stream) stream[idx] = make_uint2(hi, (lo & ~3u) | (fast ? 0u : 1u) | (n == 15 ? 2u : 0u));
+    }
     // 0x55555555-style mask: bit 30 - 2j set iff base j of the window (bits 31-2j:30-2j) equals code c
     static __device__ __forceinline__ uint32_t match(uint32_t w, uint32_t c) {
         const uint32_t x = w ^ (c * 0x55555555u);
@@ -526,8 +537,8 @@ struct PartSink {
         if (PB == 2) t = match(hi, part >> 2) & match(__funnelshift_l(lo, hi, 2), part & 3u);
         if (n == 15) t &= ~1u;
         issued += (uint32_t)__popc(t);
-        // (walking the set bits of t instead -- one k-mer in 16 matches at k = 10 -- was measured slower: the divergent loop
-        //  costs more than 16 predicated-off REDs)
+        // (walking the set bits of t instead -- one k-mer in 16 matches at k = 10 -- was measured slower in the text pass and
+        //  in the stream passes: the divergent loop costs more than 16 predicated REDs)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const int r = 63 - 2 * K - 2 * j;   // k-mer j on bits 2K:1 of (hi:lo) >> r
@@ -538,21 +549,34 @@ struct PartSink {
     }
 };
 template <int K, int PB> struct sink_takes_window<PartSink<K, PB>> { static constexpr bool value = true; };
+template <int K, int PB> struct sink_records_lanes<PartSink<K, PB>> { static constexpr bool value = PB != 0; };
 template <int K, int PB>
 struct PartSlowSink {   // one k-mer at a time (rare paths): off = 4 * kmer
     uint32_t *hist;
     uint32_t base, part;
     uint32_t *s_slow;
+    uint32_t *g_row;
     __device__ __forceinline__ void operator()(uint32_t off) const {
         if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) {
             const uint32_t sv = off >> 1;
             red_shared_add(hist, base, sv & PartSink<K, PB>::AMASK, (sv & 2u) * 0x8000u + 1u);
             atomicAdd(s_slow, 1u);
+        } else if (g_row) {
+            atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g_row) + off), 1u);   // another partition's bin
         }
     }
 };
 template <int K, int PB> __device__ __forceinline__ PartSlowSink<K, PB> sink_slow(const PartSink<K, PB> &s) {
-    return PartSlowSink<K, PB>{s.hist, s.base, s.part, s.s_slow};
+    return PartSlowSink<K, PB>{s.hist, s.base, s.part, s.s_slow, s.g_row};
+}
+// exact recount of a stream entry's k-mers of one partition: global REDs
+template <int K, int PB>
+__device__ __forceinline__ void part_stream_recount(uint32_t hi, uint32_t lo, uint32_t n, uint32_t part, uint32_t *g_row) {
+    const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t kmer = (uint32_t)(w >> (64 - 2 * K - 2 * j)) & ((1u << (2 * K)) - 1u);
+        if (PB == 0 || (kmer >> (2 * (K - PB))) == part) atomicAdd(g_row + kmer, 1u);
+    }
 }
 
 template <int K, int PB>
@@ -567,11 +591,15 @@ struct PartGmemSink {   // exact recount of one partition after a wrapped half: 
 // items: (file, partition) pairs, the partitions of a file next to each other; CTAs take them from a global counter.
 // file_t0[f] .. file_t0[f + 1]: the file's tiles in `tiles` (consecutive); files with no tiles or with small == 1 are
 // left to the global-atomic kernel.  Rows are zero when the kernel starts.
-template <int K, int PB, int THREADS>
+// MODE 0: the only pass (one partition, k = 8).  MODE 1: pass A of a multi-pass count -- the text is parsed ONCE: the
+// item's partition is counted, every lane's decoded piece is written to `stream` (8 bytes per 16 bytes of text), and
+// the k-mers of the rare paths that belong to other partitions go straight to the row with global REDs.  MODE 2: pass B
+// -- the other partitions are counted from the stream (no parsing, half the bytes); launched after pass A.
+template <int K, int PB, int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ file_t0,
                         const uint32_t *__restrict__ items, int n_items, uint32_t *__restrict__ g_fwd32, uint32_t file_base,
-                        unsigned int *__restrict__ item_counter) {
+                        unsigned int *__restrict__ item_counter, uint2 *__restrict__ stream) {
     using S = PartSink<K, PB>;
     constexpr int NWARPS = THREADS / 32;
     constexpr size_t NB = (size_t)1 << (2 * K);
@@ -587,6 +615,8 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
     sink.base = smem_addr(hist);
     sink.issued = 0;
     sink.s_slow = &s_slow;
+    sink.g_row = nullptr;
+    sink.stream = MODE == 1 ? stream : nullptr;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = (int)atomicAdd(item_counter, 1u);
@@ -595,7 +625,9 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
         if (it >= n_items) break;
         const uint32_t file = items[it] >> 8, part = items[it] & 0xFFu;
         sink.part = part;
-        uint32_t *row = g_fwd32 + (size_t)(file - file_base) * NB + ((size_t)part << (2 * (K - PB)));
+        uint32_t *file_row = g_fwd32 + (size_t)(file - file_base) * NB;
+        uint32_t *row = file_row + ((size_t)part << (2 * (K - PB)));
+        if (MODE == 1) sink.g_row = file_row;
         const int t0 = file_t0[file], t1 = file_t0[file + 1];
         for (int ta = t0; ta < t1; ta += PART_FLUSH_TILES) {
             const int tb = ta + PART_FLUSH_TILES < t1 ? ta + PART_FLUSH_TILES : t1;
@@ -605,7 +637,25 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
                 const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
                 const uint32_t cend = T.first_chunk + T.n_chunks;
                 const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-                if (c0 < c1) fasta_process_range<K, false, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, sink);
+                if (MODE != 2) {
+                    if (c0 < c1) fasta_process_range<K, false, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, sink);
+                } else {
+                    // pass B: the lanes' decoded pieces, D chunks in flight (register ring, rotated at compile time)
+                    constexpr int D = 4;
+                    const uint2 *sp = stream + (size_t)c0 * 32 + lane;
+                    uint2 ring[D];
+#pragma unroll
+                    for (int i = 0; i < D; i++) ring[i] = c0 + i < c1 ? KF_LDCG(sp + (size_t)i * 32) : make_uint2(0u, 1u);
+                    for (uint32_t cg = c0; cg < c1; cg += D) {
+#pragma unroll
+                        for (int u = 0; u < D; u++) {
+                            const uint32_t c = cg + u;
+                            const uint2 v = ring[u];
+                            ring[u] = c + D < c1 ? KF_LDCG(sp + (size_t)(c + D - c0) * 32) : make_uint2(0u, 1u);
+                            if (!(v.y & 1u)) sink.window(v.x, v.y & ~3u, (v.y & 2u) ? 15u : 16u);   // (past c1: flagged entries)
+                        }
+                    }
+                }
             }
             // ---- drain: checksum, then add the interval's counts to the row ----
             unsigned long long iss = sink.issued;
@@ -648,7 +698,14 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
                     const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
                     const uint32_t cend = T.first_chunk + T.n_chunks;
                     const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
-                    if (c0 < c1) fasta_process_range<K, false, 2>(GlobalSrc{arena}, c0, c1, T.file_chunk0, gs);
+                    if (MODE != 2) {
+                        if (c0 < c1) fasta_process_range<K, false, 2>(GlobalSrc{arena}, c0, c1, T.file_chunk0, gs);
+                    } else {
+                        for (uint32_t c = c0; c < c1; ++c) {
+                            const uint2 v = KF_LDCG(stream + (size_t)c * 32 + lane);
+                            if (!(v.y & 1u)) part_stream_recount<K, PB>(v.x, v.y & ~3u, (v.y & 2u) ? 15u : 16u, part, gs.g);
+                        }
+                    }
                 }
                 __threadfence();
             }

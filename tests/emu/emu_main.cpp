@@ -101,14 +101,28 @@ int main(int argc, char **argv) {
         // partitioned shared-memory kernel + u32 fold, as kf_api.cu launches them for k = 8..10
         std::vector<int> file_t0(n + 1, 0);
         { size_t t = 0; for (int f = 0; f < n; f++) { file_t0[f] = (int)t; while (t < tiles.size() && tiles[t].file == (uint32_t)f) t++; } file_t0[n] = (int)t; }
-        const int PB = k - 3;   // k = 4: 4 partitions, k = 5: 16
-        std::vector<uint32_t> items;
-        for (int f = 0; f < n; f++) if (len[f] && arena[off[f]] == '>') for (uint32_t pp = 0; pp < (1u << (2 * PB)); pp++) items.push_back(((uint32_t)f << 8) | pp);
+        const int PB = k - 3;   // k = 3: one partition, k = 4: 4 partitions, k = 5: 16
+        // pass A: (file, 0) items parse the text once and write the decoded stream; pass B: (file, p >= 1) items count from it
+        std::vector<uint32_t> items_a, items_b;
+        for (int f = 0; f < n; f++) if (len[f] && arena[off[f]] == '>') {
+            items_a.push_back((uint32_t)f << 8);
+            for (uint32_t pp = 1; pp < (1u << (2 * PB)); pp++) items_b.push_back(((uint32_t)f << 8) | pp);
+        }
         std::vector<uint32_t> fwd32((size_t)n * NB, 0u);
-        unsigned int counter = 0;
-        if (k == 4) emu::launch(grid, threads == 512 ? 64 : threads, PartSink<4, 1>::NWORDS * 4, [&]() { if (threads == 32) count_fasta_part_kernel<4, 1, 32>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); else count_fasta_part_kernel<4, 1, 64>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); });
-        else if (k == 5) emu::launch(grid, threads == 512 ? 64 : threads, PartSink<5, 2>::NWORDS * 4, [&]() { if (threads == 32) count_fasta_part_kernel<5, 2, 32>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); else count_fasta_part_kernel<5, 2, 64>(arena.data(), tiles.data(), file_t0.data(), items.data(), (int)items.size(), fwd32.data(), 0u, &counter); });
-        else { fprintf(stderr, "partitioned emu: k = 4 or 5\n"); return 2; }
+        std::vector<uint2> stream(arena.size() / CHUNK * 32 + 64, uint2{0xDEADBEEFu, 0u});   // garbage that would be counted if read unwritten
+        unsigned int counter[2] = {0, 0};
+        const int thr = threads == 512 ? 64 : threads;
+#define RUN_PART(KK, PBB, TT, MODE, ITEMS, CNT) count_fasta_part_kernel<KK, PBB, TT, MODE>(arena.data(), tiles.data(), file_t0.data(), ITEMS.data(), (int)ITEMS.size(), fwd32.data(), 0u, CNT, stream.data())
+        if (k == 4) {
+            emu::launch(grid, thr, PartSink<4, 1>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(4, 1, 32, 1, items_a, &counter[0]); else RUN_PART(4, 1, 64, 1, items_a, &counter[0]); });
+            emu::launch(grid, thr, PartSink<4, 1>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(4, 1, 32, 2, items_b, &counter[1]); else RUN_PART(4, 1, 64, 2, items_b, &counter[1]); });
+        } else if (k == 5) {
+            emu::launch(grid, thr, PartSink<5, 2>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(5, 2, 32, 1, items_a, &counter[0]); else RUN_PART(5, 2, 64, 1, items_a, &counter[0]); });
+            emu::launch(grid, thr, PartSink<5, 2>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(5, 2, 32, 2, items_b, &counter[1]); else RUN_PART(5, 2, 64, 2, items_b, &counter[1]); });
+        } else if (k == 3) {   // one partition: the k = 8 shape (MODE 0)
+            emu::launch(grid, thr, PartSink<3, 0>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(3, 0, 32, 0, items_a, &counter[0]); else RUN_PART(3, 0, 64, 0, items_a, &counter[0]); });
+        }
+        else { fprintf(stderr, "partitioned emu: k = 3, 4 or 5\n"); return 2; }
         std::vector<uint32_t> canon; canonical_codes(k, canon);
         long long V = (long long)canon.size();
         std::vector<unsigned long long> counts((size_t)n * V), totals(n);

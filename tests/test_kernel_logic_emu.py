@@ -200,17 +200,17 @@ def test_emulated_partitioned_kernel_fuzz(tmp_path):
             p = str(tmp_path / ("p%d_%d.fa" % (s, i)))
             open(p, "wb").write(rand_fasta(rng) if rng.random() < 0.5 else rand_fasta_grid(rng))
             files.append(p)
-        k = rng.choice([4, 5])
+        k = rng.choice([3, 4, 5])   # one partition (the k = 8 shape) / text pass + stream passes over 3 / 15 partitions
         grid, thr, tile = rng.randint(1, 4), rng.choice([32, 64]), rng.choice([1, 3, 8, 64])
         res = run_emu(k, thr, grid, False, tile, files, mode=2)
         for f, (tot, counts, _) in zip(files, res):
             ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
             assert np.array_equal(counts, ref), (s, k, grid, thr, tile, f)
-    seq = "A" * 300000 + "ACGTTGCAAGGCTTAACCGGTTAA" * 500 + "N" * 50 + "C" * 160001
+    seq = "A" * 300000 + "ACGTTGCAAGGCTTAACCGGTTAA" * 500 + "N" * 50 + "C" * 160001 + "T" * 200000 + "ACGGT" * 1000 + "G" * 150000
     data = (">polyA\n" + "\n".join(seq[i:i + 80] for i in range(0, len(seq), 80)) + "\n").encode()
     p = str(tmp_path / "pa.fa")
     open(p, "wb").write(data)
-    for k in (4, 5):
+    for k in (3, 4, 5):   # halves wrap in the text pass (A, C: gray codes 0, 1 ...) and in the stream passes
         ref = o.canonical_counts_bytes(data, k)
         assert int(ref.max()) > 2 * 65535
         for grid, thr, tile in ((1, 64, 64), (3, 32, 8)):
