@@ -392,3 +392,36 @@ def test_files_to_kf_pipeline_matches_buffer_path(eng, toy_inputs, tmp_path):
             assert int(totals[names.index(s)]) == int(tot[j])
         for s in ("e", "f", "missing"):
             assert not os.path.exists(outs[names.index(s)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,G", [(8, 160), (9, 160), (10, 96)])
+def test_large_k_full_size_genomes_every_row_vs_c_oracle(eng, k, G):
+    """BASELINE.json configs[4] shape: 5 Mbp genomes at k = 8 / 9 / 10 through the device-arena path (text pass + stream
+    passes of the partitioned kernel, more work items than SMs): every row bit-exact against the multi-threaded C
+    oracle, totals from the run structure, and the canonical fold property sum(counts) = number of valid k-mers."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    NB = 5_000_000
+    threads = len(os.sched_getaffinity(0))
+    with ThreadPoolExecutor(threads) as ex:
+        gen = list(ex.map(lambda i: eng.synth_fasta(777, i, NB), range(G)))
+    arena = eng.DeviceArena(gen)
+    V = eng.vocab_size(k)
+    counts = torch.empty((G, V), dtype=torch.int64, device="cuda")
+    totals = torch.empty(G, dtype=torch.int64, device="cuda")
+    eng.count_device(arena, k=k, counts=counts, totals=totals)
+    torch.cuda.synchronize()
+    got = counts.cpu().numpy().astype(np.uint64)
+    ref, _, st = c_oracle.count_buffers_mt(gen, k, threads=threads, want_freq=False)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(totals.cpu().numpy().astype(np.uint64), ref.sum(axis=1))
+    sym = o.symbols_from_bytes(gen[G - 1].tobytes())
+    good = np.concatenate(([0], (sym >= 0).astype(np.int8), [0]))
+    d = np.diff(good)
+    runs = np.flatnonzero(d == -1) - np.flatnonzero(d == 1)
+    assert int(totals[G - 1]) == int(np.maximum(runs - (k - 1), 0).sum())
+    # a second call on the same layout (cached plan, reused stream and counters) gives the same matrix
+    eng.count_device(arena, k=k, counts=counts, totals=totals)
+    torch.cuda.synchronize()
+    assert np.array_equal(counts.cpu().numpy().astype(np.uint64), ref)
