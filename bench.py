@@ -195,16 +195,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     global NCCL_CTAS
     if NCCL_CTAS <= 0:
-        NCCL_CTAS = 4 if world <= 2 else 8
-    if world > 1:
+        NCCL_CTAS = 8
+    # measured: at 2 GPUs the 65 MB gather costs less (0.07 ms) than the SMs the overlap needs; from 4 GPUs on it pays
+    overlap = world >= 4 or (world > 1 and "KF_BENCH_NCCL_CTAS" in os.environ)
+    if overlap:
         # the all-gather of batch i runs beside the counting of batch i+1: NCCL gets at most NCCL_CTAS CTAs, and the
         # counting kernels (one persistent CTA per SM, ~205 KB of shared memory each) are sized for the other SMs
         os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     engine.init(local_rank)
     numa_node = engine.bind_host_to_gpu(local_rank) if world > 1 else None   # before any pinned host allocation
     sms_used = engine.set_sm_limit(0)
-    if world > 1:
+    if overlap:
         sms_used = engine.set_sm_limit(sms_used - NCCL_CTAS)
     k, G, NB = args.k, args.genomes, args.bases
     V = engine.vocab_size(k)
@@ -220,7 +223,8 @@ def main():
     totals = torch.empty(G, dtype=torch.int64, device=dev)
     # N > 1: the [N, V] backbone matrix is assembled on every GPU by an all-gather that runs while the next batch is
     # being counted (two buffer pairs); every gather completes inside the timed region (drain before the end event)
-    og = kfdist.OverlappedGather(G, V, torch.float32, dev) if world > 1 else None
+    og = kfdist.OverlappedGather(G, V, torch.float32, dev) if overlap else None
+    gathered = torch.empty((world * G, V), dtype=torch.float32, device=dev) if (world > 1 and not overlap) else None
     kernel_ms = []
 
     def step(record=False):
@@ -229,6 +233,8 @@ def main():
         engine.count_device(arena, k=k, counts=counts, freq=freq, feat=f, totals=totals)
         if og:
             og.submit()
+        elif gathered is not None:
+            dist.all_gather_into_tensor(gathered, f)
         if record:
             kernel_ms.append(engine.last_count_kernel_ms())   # (waits for the library's events: only outside the timed region)
 
@@ -361,9 +367,9 @@ def main():
                        "genomes_per_gpu": G, "bases_per_genome": NB, "k": k, "file_bytes_per_gpu": int(file_bytes),
                        "l2_policy": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed" % (file_bytes / 1e9),
                        "parallelism": "genome-sharded, one process per GPU, no collective on the counting path"
-                                      + ("; NCCL all-gather of the [N,8192] fp32 matrix of every step inside the timed region, the gather of "
-                                         "step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, counting kernels sized "
-                                         "for %d of the SMs)" % (NCCL_CTAS, sms_used) if world > 1 else "")},
+                                      + ("; NCCL all-gather of the [N,8192] fp32 matrix of every step inside the timed region" if world > 1 else "")
+                                      + (", the gather of step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, "
+                                         "counting kernels sized for %d of the SMs)" % (NCCL_CTAS, sms_used) if overlap else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "count_fasta_lines_kernel<80,512> (+ width probe; the 60/70-column and generic launches "
