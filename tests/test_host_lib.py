@@ -41,6 +41,11 @@ def test_no_device_is_an_error_not_a_fallback():
     assert L.kf_init(0) == -2
     with pytest.raises(engine.KfError):
         engine.count_buffers([b">a\nACGT\n"], k=3)
+    # the file pipeline and the SM limit refuse as well: nothing is read, counted or written without the device
+    assert L.kf_set_sm_limit(100) == -2
+    with pytest.raises(engine.KfError):
+        engine.files_to_kf(["/nonexistent.fa"], ["/tmp/never_written.kf"], ["x"], k=7)
+    assert not os.path.exists("/tmp/never_written.kf")
 
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
