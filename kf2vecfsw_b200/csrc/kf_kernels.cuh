@@ -1013,20 +1013,29 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
     uint32_t woff = 0;
     bool search = false;
     int strikes = 0;
+    // wleft: that many windows from B on are known to lie inside the current unit with a full window after them -- they
+    // take the short path below (no break analysis, no unit bookkeeping) as long as all 32 slots are on the grid
+    uint32_t wleft = 0;
+    auto set_wleft = [&](const LnUnit &u) {
+        wleft = (u.Ue > B && u.Ue - B >= 2ull * G::WIN) ? (uint32_t)((u.Ue - B) / (uint64_t)G::WIN) - 1u : 0u;
+    };
     auto start_unit = [&](const LnUnit &u) {
         search = u.Us > A;          // A itself is a line start; later units are found from the staged bytes
         base = search ? ((u.Us - 1) & ~15ull) : (u.Us & ~15ull);
         B = u.Us;
         woff = (uint32_t)(B - base);
         strikes = 0;
+        wleft = 0;
+        if (!search) set_wleft(u);
         KF_SYNCWARP();
         if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
     };
-    auto refetch = [&](uint64_t at) {   // window whose first line starts at `at`
+    auto refetch = [&](uint64_t at) {   // window whose first line starts at `at` (same unit)
         base = at & ~15ull;
         B = at;
         woff = (uint32_t)(at & 15u);
         search = false;
+        set_wleft(U);
         KF_SYNCWARP();
         if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
     };
@@ -1058,6 +1067,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             }
             woff = (uint32_t)(B - base);
             if ((uint64_t)(B - base) + G::NEED > (uint64_t)G::STAGE) { refetch(B); continue; }
+            set_wleft(U);
         }
         // ---- pull my line (+ look-ahead) into registers, byte-aligned ----
         const uint32_t o = woff + (uint32_t)lane * G::P;
@@ -1068,15 +1078,30 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         for (int i = 0; i <= G::NWA; i++) x[i] = sw[i];
 #pragma unroll
         for (int i = 0; i < G::NWA; i++) x[i] = __funnelshift_r(x[i], x[i + 1], ash);
+        const bool nl_byte = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au;   // my slot ends with a '\n'
+        const uint64_t curB = B;
+        uint32_t f = 32;
+        uint64_t gen_lo = 0, gen_hi = 0;   // exact generic region (empty when the window was clean)
+        if (wleft != 0 && __ballot_sync(FULL, nl_byte) == FULL) {
+            // ---- the common case: 32 slots on the grid, this window and the next one inside the unit (and so inside the
+            // file): the next window follows this one ----
+            wleft--;
+            strikes = 0;
+            B += (uint64_t)G::WIN;
+            base = B & ~15ull;
+            woff = (uint32_t)B & 15u;
+            KF_SYNCWARP();
+            if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
+        } else {
         // on the grid: my slot ends with a '\n' AND lies inside the file (a short last line + arena padding + the next
         // file's header can add up to exactly one slot -- profiles/r01: one k-mer in 5e9 counted across two files)
-        const bool nl_ok = ((x[LW / 4] >> (8 * (LW & 3))) & 0xFFu) == 0x0Au && B + (uint64_t)(lane + 1) * G::P <= F1;
+        const bool nl_ok = nl_byte && B + (uint64_t)(lane + 1) * G::P <= F1;
         // ---- who is on the grid: lines that start before the unit's end ----
         const uint64_t rem = U.Ue - B;                                  // > 0
         const uint32_t nact = rem >= (uint64_t)G::WIN ? 32u : (uint32_t)((rem + G::P - 1) / G::P);
         const bool active = (uint32_t)lane < nact;
         const unsigned bad = __ballot_sync(FULL, active && !nl_ok);
-        const uint32_t f = bad ? (uint32_t)(__ffs((int)bad) - 1) : nact;
+        f = bad ? (uint32_t)(__ffs((int)bad) - 1) : nact;
         // ---- where the next window is; get its copy going before the decode ----
         const uint64_t sf = B + (uint64_t)f * G::P;     // first byte not covered by lanes [0, f)
         uint64_t q = sf;                                // next line start to process on the grid
@@ -1117,10 +1142,8 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         } else {
             strikes = 0;
         }
-        const uint64_t curB = B;
-        uint64_t gen_lo = sf, gen_hi = fast_break ? sf : q;   // exact generic region (empty when the window was clean)
-        LnUnit Un = U;
-        bool have_n = true;
+        gen_lo = sf;
+        gen_hi = fast_break ? sf : q;
         if (q < U.Ue && strikes >= 4) {
             // this stretch is not on the grid (another width, blank lines ...): finish the unit generically
             gen_hi = fasta_line_start_at_or_after(gsrc, U.Ue, F0, F1, lane);
@@ -1128,8 +1151,9 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         }
         if (q < U.Ue) refetch(q);
         else {
-            have_n = claim(Un);
-            if (have_n) start_unit(Un);
+            have = claim(U);   // (nothing below looks at the unit that has just been finished)
+            if (have) start_unit(U);
+        }
         }
         // ---- decode + count the lanes on the grid ----
         KF_T(td0);
@@ -1189,8 +1213,6 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
 #ifdef KF_PIECE_TIMING
         if (gen_lo < gen_hi) { const long long tg1 = clock64(); KF_LADD(12, 1); KF_LADD(13, tg1 - tg0); }
 #endif
-        U = Un;
-        have = have_n;
     }
 #ifdef KF_PIECE_TIMING
     for (int i = 0; i < 7; i++) if (tacc[i]) KF_TADD(8 + i, tacc[i]);
