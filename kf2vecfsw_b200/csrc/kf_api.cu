@@ -32,7 +32,7 @@ constexpr uint32_t TILE_CHUNKS = 1024;                 // 512 KiB per tile: 64 c
 constexpr size_t GMEM_WS_LIMIT = (size_t)12 << 30;     // forward-count workspace cap for k >= 8
 constexpr int THREADS_PART = 1024;                     // partitioned kernel (k = 8..10): 1 CTA/SM, 128 KiB histogram, 64 regs/thread
 constexpr uint64_t PART_MIN_BYTES = 256 << 10;         // smaller files (chunked-mode windows ...) stay on global REDs
-constexpr int part_bases(int k) { return k - 8; }      // leading bases that select the partition: 4^(k-8) partitions
+constexpr int part_top_bits(int k) { return k == 8 ? 0 : k == 9 ? 3 : 5; }   // PartGeom: 1 / 3 / 11 partitions
 
 struct Ctx {
     int device = -1;
@@ -282,7 +282,7 @@ int launch_gmem(const uint8_t *d_arena, int grid, bool force_walker, uint32_t fi
     uint32_t *fwd = (uint32_t *)g.d_fwd;
     if constexpr (K >= 8 && K <= 10) {
         if (g.pc_items > 0 && !force_walker) {
-            constexpr int PB = part_bases(K);
+            constexpr int PB = part_top_bits(K);
             constexpr size_t smem = PartSink<K, PB>::NWORDS * sizeof(uint32_t);
             CK(cudaMemsetAsync(g.d_item_counter, 0, 2 * sizeof(unsigned int), s));
             if constexpr (PB == 0) {
@@ -399,7 +399,7 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 file_t0[f1] = (int)t;
             }
             std::vector<uint32_t> items, items_b, taken((size_t)f1, 0u);
-            const uint32_t P = 1u << (2 * part_bases(k));
+            const uint32_t P = k == 8 ? PartGeom<8, 0>::NPART : k == 9 ? PartGeom<9, 3>::NPART : PartGeom<10, 5>::NPART;
             for (uint32_t f = f0; f < f1; f++) {
                 if (formats[f] != '>' || lens[f] == 0 || (lens[f] < PART_MIN_BYTES && part_mode != 2)) continue;
                 taken[f] = 1u;

@@ -497,27 +497,49 @@ __device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32
 // k = 8..10: partitioned shared-memory histogram
 // ------------------------------------------------------------------------------------------------
 // 4^k counters do not fit in shared memory, and one RED per occurrence into an L2-resident row runs at the L2's atomic
-// rate (~0.1 Tbases/s).  Instead the k-mer space is cut by the k-mer's first PB bases into 4^PB partitions of
-// 4^(k-PB) = 65,536 bins, which fit as 32,768 words of two u16 halves; a work item is (file, partition): the CTA reads the
-// whole file (the partitions of a file run side by side on different SMs, so the re-reads are L2 hits mostly), counts
-// the k-mers of its partition and owns that part of the file's row outright -- plain read-add-write, no global atomics.
+// rate (~0.1 Tbases/s).  Instead the k-mer space is cut into partitions that fit in shared memory as u16 halves (PartGeom:
+// 65,536 bins at k = 8, 98,304 at k = 9 and 10); a work item is (file, partition): the CTA counts the k-mers of its
+// partition over the whole file and owns that part of the file's row outright -- plain read-add-write, no global atomics.
 //   word w of the histogram: low half = occurrences of bins 2w and 2w+1, high half = those of bin 2w+1 (one RED with
 //   addend 1 or 0x10001).  A half can wrap: the histogram is drained every PART_FLUSH_TILES tiles, and at every drain
 //   the sum of the low halves must equal the number of REDs issued; if not, the interval is recounted with global REDs.
 constexpr int PART_FLUSH_TILES = 8;
 
-template <int K, int PB>
-struct PartSink {
-    static_assert(PB >= 0 && PB <= 2 && K - PB <= 8 && K - PB >= 2, "partition geometry");
-    static constexpr uint32_t NBINS = 1u << (2 * (K - PB));
+// Partition geometry.  TB = 0: one partition of 4^K bins (k = 8).  TB > 0 (odd): the k-mer's top TB bits -- its first
+// TB/2 bases and the high code bit of the next -- number 2^TB "granules" of 4^K >> TB bins; a partition is three
+// consecutive granules (98,304 bins = 192 KB of u16 halves at k = 9, 10: three passes instead of four at k = 9, eleven
+// instead of sixteen at k = 10), the last one what is left.
+template <int K, int TB>
+struct PartGeom {
+    static_assert(TB == 0 || (TB % 2 == 1 && TB >= 3 && TB <= 5), "top bits");
+    static constexpr uint32_t GSH = 2 * K - TB;
+    static constexpr uint32_t GRAN = 1u << GSH;
+    static constexpr uint32_t NTOP = 1u << TB;
+    static constexpr uint32_t NBINS = TB ? 3u * GRAN : GRAN;          // bins of a full partition
+    static constexpr uint32_t NPART = TB ? (NTOP + 2u) / 3u : 1u;
     static constexpr uint32_t NWORDS = NBINS / 2;
-    static constexpr uint32_t AMASK = (NBINS << 1) - 4u;    // byte address of the word, taken from kmer << 1
+    static constexpr uint32_t AMASK = (TB ? 8u * GRAN : 2u * GRAN) - 4u;   // byte address of the word from 2 * (kmer - first bin)
+    static_assert(NBINS >= 8 && NWORDS * 4 <= 196608, "partition size");
+    static __host__ __device__ constexpr uint32_t first_bin(uint32_t p) { return TB ? 3u * p * GRAN : 0u; }
+    static __host__ __device__ constexpr uint32_t bins_of(uint32_t p) {
+        return TB ? ((1u << (2 * K)) - first_bin(p) < NBINS ? (1u << (2 * K)) - first_bin(p) : NBINS) : NBINS;
+    }
+    static __device__ __forceinline__ bool owns(uint32_t kmer, uint32_t p) { return TB == 0 || ((kmer >> GSH) - 3u * p) < 3u; }
+};
+
+template <int K, int TB>
+struct PartSink {
+    using G = PartGeom<K, TB>;
+    static constexpr uint32_t NWORDS = G::NWORDS;
     uint32_t *hist;
     uint32_t base;     // shared-window address of word 0
-    uint32_t part;     // the PB leading bases this CTA counts (gray codes, first base most significant)
+    uint32_t part;     // partition index
+    uint32_t lo2;      // 2 * first bin of the partition
     uint32_t issued;   // REDs issued by this thread since the last drain
-    // sv: the k-mer (at least its low 2(K-PB) bits) on bits 2(K-PB):1
-    __device__ __forceinline__ void add(uint32_t sv) { red_shared_add(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u); }
+    __device__ __forceinline__ void set_part(uint32_t p) { part = p; lo2 = 2u * G::first_bin(p); }
+    // sv: the k-mer on bits 2K:1 (anything above)
+    __device__ __forceinline__ uint32_t addr_of(uint32_t sv) const { return (TB ? sv - lo2 : sv) & G::AMASK; }
+    __device__ __forceinline__ void add(uint32_t sv) { red_shared_add(hist, base, addr_of(sv), (sv & 2u) * 0x8000u + 1u); }
     uint32_t *s_slow;  // shared: REDs issued by the rare paths since the last drain
     uint32_t *g_row;   // pass A of a multi-pass count: the file's row, for the rare paths' k-mers of OTHER partitions
     uint2 *stream;     // pass A: every lane's decoded piece goes here for the passes over the other partitions
@@ -526,44 +548,60 @@ struct PartSink {
     __device__ __forceinline__ void record(size_t idx, bool fast, uint32_t hi, uint32_t lo, uint32_t n) const {
         if (stream) stream[idx] = make_uint2(hi, (lo & ~3u) | (fast ? 0u : 1u) | (n == 15 ? 2u : 0u));
     }
-    // 0x55555555-style mask: bit 30 - 2j set iff base j of the window (bits 31-2j:30-2j) equals code c
-    static __device__ __forceinline__ uint32_t match(uint32_t w, uint32_t c) {
+    // 0x55555555-style masks over the 16 positions of a window: bit 30 - 2j belongs to position j
+    static __device__ __forceinline__ uint32_t match(uint32_t w, uint32_t c) {       // base j of w equals code c
         const uint32_t x = w ^ (c * 0x55555555u);
         return ~(x | (x >> 1)) & 0x55555555u;
     }
-    __device__ __forceinline__ void window(uint32_t hi, uint32_t lo, uint32_t n) {
+    // positions whose k-mer starts in one of this partition's granules
+    __device__ __forceinline__ uint32_t own_mask(uint32_t hi, uint32_t lo, uint32_t n) const {
         uint32_t t = 0x55555555u;
-        if (PB == 1) t = match(hi, part);
-        if (PB == 2) t = match(hi, part >> 2) & match(__funnelshift_l(lo, hi, 2), part & 3u);
+        if (TB) {
+            constexpr int NBASE = TB / 2;
+            uint32_t w[NBASE + 1];
+#pragma unroll
+            for (int b = 0; b <= NBASE; b++) w[b] = b == 0 ? hi : __funnelshift_l(lo, hi, 2 * b);
+            const uint32_t hb = (w[NBASE] >> 1) & 0x55555555u;   // high code bit of base j + NBASE
+            t = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < 3; q++) {
+                const uint32_t T = 3u * part + q;   // granule number: NBASE bases and one bit
+                uint32_t m = (T & 1u) ? hb : (~hb & 0x55555555u);
+#pragma unroll
+                for (int b = 0; b < NBASE; b++) m &= match(w[b], (T >> (TB - 2 - 2 * b)) & 3u);
+                if (T < G::NTOP) t |= m;
+            }
+        }
         if (n == 15) t &= ~1u;
+        if (n == 0) t = 0u;
+        return t;
+    }
+    __device__ __forceinline__ void window(uint32_t hi, uint32_t lo, uint32_t n) {
+        const uint32_t t = own_mask(hi, lo, n);
         issued += (uint32_t)__popc(t);
-        // (walking the set bits of t instead -- one k-mer in 16 matches at k = 10 -- was measured slower in the text pass and
-        //  in the stream passes: the divergent loop costs more than 16 predicated REDs)
+        // (walking the set bits of t instead was measured slower in the text pass and in the stream passes at four
+        //  partitions: the divergent loop costs more than 16 predicated REDs)
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             const int r = 63 - 2 * K - 2 * j;   // k-mer j on bits 2K:1 of (hi:lo) >> r
             const uint32_t sv = r >= 32 ? (hi >> (r - 32)) : __funnelshift_r(lo, hi, r);
-            if (PB == 0 && j < 15) add(sv);
-            else red_shared_add_if(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u, t, 1u << (30 - 2 * j));
+            if (TB == 0 && j < 15) add(sv);
+            else red_shared_add_if(hist, base, addr_of(sv), (sv & 2u) * 0x8000u + 1u, t, 1u << (30 - 2 * j));
         }
     }
-    // The same for sparse matches (16 partitions: one k-mer in 16 is ours): SLOTS straight-line "next set bit" slots, each
-    // one predicated RED, instead of 16 predicated positions; a lane with more matches (0.3 % at SLOTS = 4) finishes in a
-    // loop that the warp enters only then.  (A plain loop over the set bits was slower than the 16 positions.)
+    // The same for sparse matches (eleven partitions: one k-mer in ten is ours): SLOTS straight-line "next set bit"
+    // slots, each one predicated RED, instead of 16 predicated positions; a lane with more matches finishes in a loop
+    // that the warp enters only then.  Every lane of the warp must call it (ballot); n = 0: nothing to count.
     template <int SLOTS>
     __device__ __forceinline__ void window_slots(uint32_t hi, uint32_t lo, uint32_t n) {
-        uint32_t t = 0x55555555u;
-        if (PB == 1) t = match(hi, part);
-        if (PB == 2) t = match(hi, part >> 2) & match(__funnelshift_l(lo, hi, 2), part & 3u);
-        if (n == 15) t &= ~1u;
-        if (n == 0) t = 0u;   // (an entry with nothing to count: the lane still takes part in the ballot below)
+        uint32_t t = own_mask(hi, lo, n);
         issued += (uint32_t)__popc(t);
         auto take = [&](uint32_t have) {
             const uint32_t b = 31u - (uint32_t)__clz((int)(t | 1u));   // highest set bit = 30 - 2j (0 when t is empty)
             t &= ~(1u << b);
             const uint32_t r = 33u - 2u * K + b;                          // 63 - 2K - 2j
             const uint32_t sv = r >= 32u ? (hi >> (r - 32u)) : __funnelshift_r(lo, hi, r & 31u);
-            red_shared_add_if(hist, base, sv & AMASK, (sv & 2u) * 0x8000u + 1u, have, 1u);
+            red_shared_add_if(hist, base, addr_of(sv), (sv & 2u) * 0x8000u + 1u, have, 1u);
         };
 #pragma unroll
         for (int sidx = 0; sidx < SLOTS; sidx++) take(t != 0u ? 1u : 0u);
@@ -572,43 +610,43 @@ struct PartSink {
         }
     }
 };
-template <int K, int PB> struct sink_takes_window<PartSink<K, PB>> { static constexpr bool value = true; };
-template <int K, int PB> struct sink_records_lanes<PartSink<K, PB>> { static constexpr bool value = PB != 0; };
-template <int K, int PB>
+template <int K, int TB> struct sink_takes_window<PartSink<K, TB>> { static constexpr bool value = true; };
+template <int K, int TB> struct sink_records_lanes<PartSink<K, TB>> { static constexpr bool value = TB != 0; };
+template <int K, int TB>
 struct PartSlowSink {   // one k-mer at a time (rare paths): off = 4 * kmer
     uint32_t *hist;
-    uint32_t base, part;
+    uint32_t base, part, lo2;
     uint32_t *s_slow;
     uint32_t *g_row;
     __device__ __forceinline__ void operator()(uint32_t off) const {
-        if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) {
+        if (PartGeom<K, TB>::owns(off >> 2, part)) {
             const uint32_t sv = off >> 1;
-            red_shared_add(hist, base, sv & PartSink<K, PB>::AMASK, (sv & 2u) * 0x8000u + 1u);
+            red_shared_add(hist, base, (TB ? sv - lo2 : sv) & PartGeom<K, TB>::AMASK, (sv & 2u) * 0x8000u + 1u);
             atomicAdd(s_slow, 1u);
         } else if (g_row) {
             atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g_row) + off), 1u);   // another partition's bin
         }
     }
 };
-template <int K, int PB> __device__ __forceinline__ PartSlowSink<K, PB> sink_slow(const PartSink<K, PB> &s) {
-    return PartSlowSink<K, PB>{s.hist, s.base, s.part, s.s_slow, s.g_row};
+template <int K, int TB> __device__ __forceinline__ PartSlowSink<K, TB> sink_slow(const PartSink<K, TB> &s) {
+    return PartSlowSink<K, TB>{s.hist, s.base, s.part, s.lo2, s.s_slow, s.g_row};
 }
 // exact recount of a stream entry's k-mers of one partition: global REDs
-template <int K, int PB>
+template <int K, int TB>
 __device__ __forceinline__ void part_stream_recount(uint32_t hi, uint32_t lo, uint32_t n, uint32_t part, uint32_t *g_row) {
     const unsigned long long w = ((unsigned long long)hi << 32) | lo;
     for (uint32_t j = 0; j < n; j++) {
         const uint32_t kmer = (uint32_t)(w >> (64 - 2 * K - 2 * j)) & ((1u << (2 * K)) - 1u);
-        if (PB == 0 || (kmer >> (2 * (K - PB))) == part) atomicAdd(g_row + kmer, 1u);
+        if (PartGeom<K, TB>::owns(kmer, part)) atomicAdd(g_row + kmer, 1u);
     }
 }
 
-template <int K, int PB>
+template <int K, int TB>
 struct PartGmemSink {   // exact recount of one partition after a wrapped half: one global RED per occurrence
     uint32_t *g;        // the file's row
     uint32_t part;
     __device__ __forceinline__ void operator()(uint32_t off) const {
-        if (PB == 0 || (off >> (2 * (K - PB) + 2)) == part) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g) + off), 1u);
+        if (PartGeom<K, TB>::owns(off >> 2, part)) atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(g) + off), 1u);
     }
 };
 
@@ -619,12 +657,13 @@ struct PartGmemSink {   // exact recount of one partition after a wrapped half: 
 // item's partition is counted, every lane's decoded piece is written to `stream` (8 bytes per 16 bytes of text), and
 // the k-mers of the rare paths that belong to other partitions go straight to the row with global REDs.  MODE 2: pass B
 // -- the other partitions are counted from the stream (no parsing, half the bytes); launched after pass A.
-template <int K, int PB, int THREADS, int MODE>
+template <int K, int TB, int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ file_t0,
                         const uint32_t *__restrict__ items, int n_items, uint32_t *__restrict__ g_fwd32, uint32_t file_base,
                         unsigned int *__restrict__ item_counter, uint2 *__restrict__ stream) {
-    using S = PartSink<K, PB>;
+    using S = PartSink<K, TB>;
+    using PG = PartGeom<K, TB>;
     constexpr int NWARPS = THREADS / 32;
     constexpr size_t NB = (size_t)1 << (2 * K);
     KF_DYN_SMEM(uint32_t, hist);
@@ -648,9 +687,10 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
         const int it = s_item;
         if (it >= n_items) break;
         const uint32_t file = items[it] >> 8, part = items[it] & 0xFFu;
-        sink.part = part;
+        sink.set_part(part);
         uint32_t *file_row = g_fwd32 + (size_t)(file - file_base) * NB;
-        uint32_t *row = file_row + ((size_t)part << (2 * (K - PB)));
+        uint32_t *row = file_row + PG::first_bin(part);
+        const uint32_t nwords = PG::bins_of(part) / 2;   // (the last partition may be shorter)
         if (MODE == 1) sink.g_row = file_row;
         const int t0 = file_t0[file], t1 = file_t0[file + 1];
         for (int ta = t0; ta < t1; ta += PART_FLUSH_TILES) {
@@ -678,7 +718,7 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
                             ring[u] = c + D < c1 ? KF_LDCG(sp + (size_t)(c + D - c0) * 32) : make_uint2(0u, 1u);
                             // (past c1: flagged entries; every lane takes part in window_slots' ballot)
                             // (measured: 4 slots 19.0 ms vs 16 positions 23.4 ms at k = 10; 8 slots at k = 9 are slower than 16 positions)
-                            if (PB >= 2) sink.template window_slots<4>(v.x, (v.y & 1u) ? 0u : (v.y & ~3u), (v.y & 1u) ? 0u : ((v.y & 2u) ? 15u : 16u));
+                            if (TB >= 5) sink.template window_slots<5>(v.x, (v.y & 1u) ? 0u : (v.y & ~3u), (v.y & 1u) ? 0u : ((v.y & 2u) ? 15u : 16u));
                             else if (!(v.y & 1u)) sink.window(v.x, v.y & ~3u, (v.y & 2u) ? 15u : 16u);
                         }
                     }
@@ -703,7 +743,7 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
             for (uint32_t i = threadIdx.x; i < S::NWORDS; i += THREADS) {
                 const uint32_t w = hist[i];
                 hist[i] = 0;
-                if (ok && w) {
+                if (ok && w && i < nwords) {
                     uint2 *rp = reinterpret_cast<uint2 *>(row) + i;
                     uint2 v = KF_LDCG(rp);   // (not through L1: an exact recount adds to these bins with REDs)
                     v.x += (w & 0xFFFFu) - (w >> 16);
@@ -716,7 +756,7 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
                 // but this CTA's threads now share them: REDs)
                 __threadfence();
                 __syncthreads();
-                PartGmemSink<K, PB> gs;
+                PartGmemSink<K, TB> gs;
                 gs.g = g_fwd32 + (size_t)(file - file_base) * NB;
                 gs.part = part;
                 for (int t = ta; t < tb; ++t) {
@@ -730,7 +770,7 @@ count_fasta_part_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
                     } else {
                         for (uint32_t c = c0; c < c1; ++c) {
                             const uint2 v = KF_LDCG(stream + (size_t)c * 32 + lane);
-                            if (!(v.y & 1u)) part_stream_recount<K, PB>(v.x, v.y & ~3u, (v.y & 2u) ? 15u : 16u, part, gs.g);
+                            if (!(v.y & 1u)) part_stream_recount<K, TB>(v.x, v.y & ~3u, (v.y & 2u) ? 15u : 16u, part, gs.g);
                         }
                     }
                 }

@@ -101,12 +101,12 @@ int main(int argc, char **argv) {
         // partitioned shared-memory kernel + u32 fold, as kf_api.cu launches them for k = 8..10
         std::vector<int> file_t0(n + 1, 0);
         { size_t t = 0; for (int f = 0; f < n; f++) { file_t0[f] = (int)t; while (t < tiles.size() && tiles[t].file == (uint32_t)f) t++; } file_t0[n] = (int)t; }
-        const int PB = k - 3;   // k = 3: one partition, k = 4: 4 partitions, k = 5: 16
+        const int TBITS = k == 3 ? 0 : k == 4 ? 3 : 5;   // k = 3: one partition (the k = 8 shape), k = 4: 3 partitions of 96 bins, k = 5: 11
         // pass A: (file, 0) items parse the text once and write the decoded stream; pass B: (file, p >= 1) items count from it
         std::vector<uint32_t> items_a, items_b;
         for (int f = 0; f < n; f++) if (len[f] && arena[off[f]] == '>') {
             items_a.push_back((uint32_t)f << 8);
-            for (uint32_t pp = 1; pp < (1u << (2 * PB)); pp++) items_b.push_back(((uint32_t)f << 8) | pp);
+            for (uint32_t pp = 1; pp < (TBITS ? ((1u << TBITS) + 2) / 3 : 1u); pp++) items_b.push_back(((uint32_t)f << 8) | pp);
         }
         std::vector<uint32_t> fwd32((size_t)n * NB, 0u);
         std::vector<uint2> stream(arena.size() / CHUNK * 32 + 64, uint2{0xDEADBEEFu, 0u});   // garbage that would be counted if read unwritten
@@ -114,11 +114,11 @@ int main(int argc, char **argv) {
         const int thr = threads == 512 ? 64 : threads;
 #define RUN_PART(KK, PBB, TT, MODE, ITEMS, CNT) count_fasta_part_kernel<KK, PBB, TT, MODE>(arena.data(), tiles.data(), file_t0.data(), ITEMS.data(), (int)ITEMS.size(), fwd32.data(), 0u, CNT, stream.data())
         if (k == 4) {
-            emu::launch(grid, thr, PartSink<4, 1>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(4, 1, 32, 1, items_a, &counter[0]); else RUN_PART(4, 1, 64, 1, items_a, &counter[0]); });
-            emu::launch(grid, thr, PartSink<4, 1>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(4, 1, 32, 2, items_b, &counter[1]); else RUN_PART(4, 1, 64, 2, items_b, &counter[1]); });
+            emu::launch(grid, thr, PartSink<4, 3>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(4, 3, 32, 1, items_a, &counter[0]); else RUN_PART(4, 3, 64, 1, items_a, &counter[0]); });
+            emu::launch(grid, thr, PartSink<4, 3>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(4, 3, 32, 2, items_b, &counter[1]); else RUN_PART(4, 3, 64, 2, items_b, &counter[1]); });
         } else if (k == 5) {
-            emu::launch(grid, thr, PartSink<5, 2>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(5, 2, 32, 1, items_a, &counter[0]); else RUN_PART(5, 2, 64, 1, items_a, &counter[0]); });
-            emu::launch(grid, thr, PartSink<5, 2>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(5, 2, 32, 2, items_b, &counter[1]); else RUN_PART(5, 2, 64, 2, items_b, &counter[1]); });
+            emu::launch(grid, thr, PartSink<5, 5>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(5, 5, 32, 1, items_a, &counter[0]); else RUN_PART(5, 5, 64, 1, items_a, &counter[0]); });
+            emu::launch(grid, thr, PartSink<5, 5>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(5, 5, 32, 2, items_b, &counter[1]); else RUN_PART(5, 5, 64, 2, items_b, &counter[1]); });
         } else if (k == 3) {   // one partition: the k = 8 shape (MODE 0)
             emu::launch(grid, thr, PartSink<3, 0>::NWORDS * 4, [&]() { if (thr == 32) RUN_PART(3, 0, 32, 0, items_a, &counter[0]); else RUN_PART(3, 0, 64, 0, items_a, &counter[0]); });
         }
