@@ -314,6 +314,18 @@ int64_t kf_linearise_fasta(const uint8_t *data, size_t len, uint64_t min_len, ui
             const uint8_t *e = (const uint8_t *)memchr(data + p, '\n', len - p);
             const size_t le = e ? (size_t)(e - data) : len;
             if (w + (le - p) > seq_cap) return KF_ERR_ARG;
+            // most lines hold none of the bytes treated specially below: one vectorisable scan, then a plain copy
+            unsigned special = 0;
+            for (size_t i = p; i < le; i++) {
+                const uint8_t c = data[i];
+                special |= (unsigned)(c == 'N') | (unsigned)(c == 'n') | (unsigned)(c == '|') | (unsigned)(c == '\r') | (unsigned)(c == '-') |
+                           (unsigned)(c == '.') | (unsigned)(c == ' ');
+            }
+            if (!special) {
+                if (le > p) { memcpy(seq_out + w, data + p, le - p); w += le - p; in_run = false; }
+                p = e ? le + 1 : len;
+                continue;
+            }
             for (size_t i = p; i < le; i++) {
                 const uint8_t c = data[i];
                 if (c == 'N' || c == 'n' || c == '|') { if (!in_run) seq_out[w++] = 'N'; in_run = true; continue; }
