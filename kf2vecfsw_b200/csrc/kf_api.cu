@@ -60,7 +60,8 @@ struct Ctx {
     unsigned int *d_item_counter = nullptr;   // [2]: pass A (or the only pass), pass B
     int pc_items = 0;        // items of the text pass: (file, 0)
     int pc_items_b = 0;      // items of the stream passes: (file, p >= 1), stored after the first pc_items
-    uint2 *d_stream = nullptr; size_t stream_cap = 0;   // decoded pieces of pass A: 8 bytes per 16 bytes of arena
+    uint2 *d_stream = nullptr; size_t stream_cap = 0;
+    unsigned long long *d_fold_tot = nullptr; size_t fold_tot_cap = 0;   // per-file totals of the sliced fold   // decoded pieces of pass A: 8 bytes per 16 bytes of arena
     uint32_t pc_part_mode = 0;
     // FASTQ plan: 128 KiB tiles (32 lane ranges), layout-violation offsets
     Tile *d_fq_tiles = nullptr; size_t fq_tiles_cap = 0;
@@ -493,6 +494,18 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             fold_normalize_smem_kernel<unsigned long long><<<nf, FOLD_THREADS, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
                                                                                        use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
         }
+    } else if (V > (1 << 14)) {
+        // large vocabulary: counts + per-file total first, then the normalisation from the counts just written (the
+        // reverse-complement gather is a scattered read: done once); with few files the fold of a file is cut into
+        // slices so that every SM has work
+        const uint32_t S = std::max<uint32_t>(1u, std::min<uint32_t>(64u, (uint32_t)(2 * g.sm_count) / std::max(1u, nf)));
+        if ((rc = ensure(g.d_fold_tot, g.fold_tot_cap, (size_t)nf * sizeof(unsigned long long))) != KF_OK) return rc;
+        CK(cudaMemsetAsync(g.d_fold_tot, 0, (size_t)nf * sizeof(unsigned long long), s));
+        fold_counts_sliced_kernel<<<dim3(nf, S), 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, f0, d_counts, g.d_fold_tot);
+        CK(cudaGetLastError());
+        fold_norm_sliced_kernel<<<dim3(nf, S), 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, d_counts, d_freq, d_feat,
+                                                              d_totals, g.d_fold_tot);
+        g.last_launches++;
     } else
         fold_normalize_kernel<uint32_t><<<nf, 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, nullptr, nullptr,
                                                              d_counts, d_freq, d_feat, d_totals);

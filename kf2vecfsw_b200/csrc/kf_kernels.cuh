@@ -1912,4 +1912,65 @@ fold_normalize_kernel(const FwdT *__restrict__ g_fwd, const uint32_t *__restrict
     }
 }
 
+
+// Large k, few files: the fold of one file cut into gridDim.y slices of the vocabulary (one CTA per file leaves most
+// SMs idle when 4^k is large: k = 12 has 8.4 M canonical k-mers per file).  Two launches: canonical counts + per-file
+// total (u64 atomics: exact), then the normalisation.  Rows are the k >= 8 layout: one u32 row per file.
+__device__ __forceinline__ unsigned long long fold_canon_count(const uint32_t *__restrict__ g, uint32_t m, int k) {
+    const uint32_t r = revcomp_std(m, k);
+    unsigned long long c = g[std_to_gray(m)];
+    if (r != m) c += g[std_to_gray(r)];
+    return c;
+}
+__global__ void __launch_bounds__(1024)
+fold_counts_sliced_kernel(const uint32_t *__restrict__ g_fwd, const uint32_t *__restrict__ canon, int k, long long V, uint32_t file_base,
+                          unsigned long long *__restrict__ counts, unsigned long long *__restrict__ tot_ws) {
+    const size_t NB = (size_t)1 << (2 * k);
+    const uint32_t file = blockIdx.x;
+    const uint32_t *g = g_fwd + (size_t)file * NB;
+    const size_t orow = (size_t)(file + file_base) * (size_t)V;
+    const long long per = (V + gridDim.y - 1) / gridDim.y;
+    const long long i0 = (long long)blockIdx.y * per, i1 = i0 + per < V ? i0 + per : V;
+    unsigned long long local = 0;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const unsigned long long c = fold_canon_count(g, canon[i], k);
+        if (counts) counts[orow + i] = c;
+        local += c;
+    }
+    __shared__ unsigned long long red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (threadIdx.x == 0 && v) atomicAdd(tot_ws + file, v);
+    }
+}
+__global__ void __launch_bounds__(1024)
+fold_norm_sliced_kernel(const uint32_t *__restrict__ g_fwd, const uint32_t *__restrict__ canon, int k, long long V, uint32_t flags,
+                        uint32_t file_base, const unsigned long long *__restrict__ counts, double *__restrict__ freq,
+                        float *__restrict__ feat, unsigned long long *__restrict__ totals, const unsigned long long *__restrict__ tot_ws) {
+    const size_t NB = (size_t)1 << (2 * k);
+    const uint32_t file = blockIdx.x;
+    const uint32_t *g = g_fwd + (size_t)file * NB;
+    const size_t orow = (size_t)(file + file_base) * (size_t)V;
+    const unsigned long long total = tot_ws[file];
+    if (totals && blockIdx.y == 0 && threadIdx.x == 0) totals[file + file_base] = total;
+    if (!freq && !feat) return;
+    const bool pc = flags & 1u, raw = flags & 2u;
+    const double denom = (double)total + (pc ? 0.5 * (double)V : 0.0);
+    const long long per = (V + gridDim.y - 1) / gridDim.y;
+    const long long i0 = (long long)blockIdx.y * per, i1 = i0 + per < V ? i0 + per : V;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const unsigned long long c = counts ? counts[orow + i] : fold_canon_count(g, canon[i], k);
+        double v = (double)c + (pc ? 0.5 : 0.0);
+        if (!raw) v = v / denom;   // IEEE fp64 division: correctly rounded, bit-exact with numpy
+        if (freq) freq[orow + i] = v;
+        if (feat) feat[orow + i] = (float)(v * 1e4);   // train_classifier_model.py:149,323
+    }
+}
+
 }  // namespace kf
