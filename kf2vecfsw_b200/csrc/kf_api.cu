@@ -46,6 +46,7 @@ struct Ctx {
     Tile *d_tiles = nullptr; size_t tiles_cap = 0;
     int *d_cta_begin = nullptr; size_t cta_cap = 0;
     uint32_t *d_canon[KF_MAX_K + 1] = {nullptr};
+    uint32_t *d_rank[KF_MAX_K + 1] = {nullptr};    // k >= 8: column of canonical k-mer m (sorted alphabet), else 0xFFFFFFFF
     uint64_t *d_file_off = nullptr; size_t foff_cap = 0;
     uint64_t *d_file_len = nullptr; size_t flen_cap = 0;
     uint8_t *d_formats = nullptr; size_t fmt_cap = 0;
@@ -125,6 +126,13 @@ int ensure_canon(int k) {
     canonical_codes(k, c);
     CK(cudaMalloc((void **)&g.d_canon[k], c.size() * sizeof(uint32_t)));
     CK(cudaMemcpy(g.d_canon[k], c.data(), c.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (k >= 8) {
+        // inverse table for the tiled fold: column of every canonical k-mer, 0xFFFFFFFF for the other strand
+        std::vector<uint32_t> rank((size_t)1 << (2 * k), 0xFFFFFFFFu);
+        for (size_t i = 0; i < c.size(); i++) rank[c[i]] = (uint32_t)i;
+        CK(cudaMalloc((void **)&g.d_rank[k], rank.size() * sizeof(uint32_t)));
+        CK(cudaMemcpy(g.d_rank[k], rank.data(), rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     return KF_OK;
 }
 
@@ -501,7 +509,11 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         const uint32_t S = std::max<uint32_t>(1u, std::min<uint32_t>(64u, (uint32_t)(2 * g.sm_count) / std::max(1u, nf)));
         if ((rc = ensure(g.d_fold_tot, g.fold_tot_cap, (size_t)nf * sizeof(unsigned long long))) != KF_OK) return rc;
         CK(cudaMemsetAsync(g.d_fold_tot, 0, (size_t)nf * sizeof(unsigned long long), s));
-        fold_counts_sliced_kernel<<<dim3(nf, S), 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, f0, d_counts, g.d_fold_tot);
+        if (k >= 8 && !(flags & KF_FLAG_NO_LINEGRID))
+            fold_counts_tiled_kernel<<<dim3(nf, 1u << (2 * (k - 2 * FOLD_T))), 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_rank[k], k, V, f0, d_counts,
+                                                                                              g.d_fold_tot);
+        else
+            fold_counts_sliced_kernel<<<dim3(nf, S), 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, f0, d_counts, g.d_fold_tot);
         CK(cudaGetLastError());
         fold_norm_sliced_kernel<<<dim3(nf, S), 1024, 0, s>>>((const uint32_t *)g.d_fwd, g.d_canon[k], k, V, flags, f0, d_counts, d_freq, d_feat,
                                                               d_totals, g.d_fold_tot);

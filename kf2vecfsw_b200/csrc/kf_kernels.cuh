@@ -1973,4 +1973,57 @@ fold_norm_sliced_kernel(const uint32_t *__restrict__ g_fwd, const uint32_t *__re
     }
 }
 
+
+// The same first launch with both gathers coalesced (k >= 8).  A k-mer in the sorted alphabet is cut into its first three
+// bases a, the middle, and its last three bases b; a CTA takes one (file, middle) tile = 64 x 64 k-mers.  Forward bins of
+// consecutive b lie in one 64-entry block of the row; the reverse complement of (a, mid, b) is (rc b, rc mid, rc a), so
+// the reverse-complement bins of consecutive a lie in one 64-entry block as well: they are read with a fastest and
+// turned through shared memory.  rank[m] = column of canonical m, 0xFFFFFFFF for the other strand (table per k).
+constexpr int FOLD_T = 3;
+__global__ void __launch_bounds__(1024)
+fold_counts_tiled_kernel(const uint32_t *__restrict__ g_fwd, const uint32_t *__restrict__ rank, int k, long long V, uint32_t file_base,
+                         unsigned long long *__restrict__ counts, unsigned long long *__restrict__ tot_ws) {
+    constexpr int E = 1 << (2 * FOLD_T);   // 64
+    __shared__ uint32_t R[E][E + 1];
+    __shared__ unsigned long long red[32];
+    const size_t NB = (size_t)1 << (2 * k);
+    const uint32_t file = blockIdx.x;
+    const uint32_t mid = blockIdx.y;                  // the k - 6 middle bases
+    const uint32_t *g = g_fwd + (size_t)file * NB;
+    const size_t orow = (size_t)(file + file_base) * (size_t)V;
+    const int midbits = 2 * (k - 2 * FOLD_T);
+    const uint32_t lo = threadIdx.x & (E - 1), hi0 = threadIdx.x >> (2 * FOLD_T);   // 1024 threads: 16 rows of 64 per step
+    // reverse-complement bins, a fastest: thread (b = hi, a = lo) reads the bin of rc(a, mid, b) and stores it at R[a][b]
+#pragma unroll
+    for (int step = 0; step < E / 16; step++) {
+        const uint32_t b = hi0 + 16u * step, a = lo;
+        const uint32_t m = (a << (midbits + 2 * FOLD_T)) | (mid << (2 * FOLD_T)) | b;
+        R[a][b] = g[std_to_gray(revcomp_std(m, k))];
+    }
+    __syncthreads();
+    unsigned long long local = 0;
+#pragma unroll
+    for (int step = 0; step < E / 16; step++) {
+        const uint32_t a = hi0 + 16u * step, b = lo;
+        const uint32_t m = (a << (midbits + 2 * FOLD_T)) | (mid << (2 * FOLD_T)) | b;
+        const uint32_t col = rank[m];
+        if (col != 0xFFFFFFFFu) {
+            unsigned long long c = g[std_to_gray(m)];
+            if (revcomp_std(m, k) != m) c += R[a][b];
+            if (counts) counts[orow + col] = c;
+            local += c;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long v = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (threadIdx.x == 0 && v) atomicAdd(tot_ws + file, v);
+    }
+}
+
 }  // namespace kf
