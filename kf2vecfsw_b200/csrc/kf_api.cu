@@ -8,6 +8,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <queue>
 #include <thread>
@@ -550,7 +551,12 @@ int count_device_locked(const uint8_t *d_arena, size_t arena_bytes, const uint64
     const size_t NB = (size_t)1 << (2 * k);
     if (k <= KF_MAX_K_SMEM) return run_files(d_arena, offsets, lens, formats, 0, (uint32_t)n, k, flags, d_counts, d_freq, d_feat, d_totals, s);
     // large k: bound the dense forward-count workspace
-    size_t per = std::max<size_t>(1, GMEM_WS_LIMIT / (NB * sizeof(uint32_t)));
+    size_t ws_limit = GMEM_WS_LIMIT;
+    if (const char *e = getenv("KF_WS_LIMIT_BYTES")) {   // tests: exercise the file batching with a small workspace
+        const long long v = atoll(e);
+        if (v > 0) ws_limit = (size_t)v;
+    }
+    size_t per = std::max<size_t>(1, ws_limit / (NB * sizeof(uint32_t)));
     for (uint32_t f0 = 0; f0 < (uint32_t)n; f0 += (uint32_t)per) {
         uint32_t f1 = (uint32_t)std::min<size_t>((size_t)n, (size_t)f0 + per);
         int rc = run_files(d_arena, offsets, lens, formats, f0, f1, k, flags, d_counts, d_freq, d_feat, d_totals, s);

@@ -425,3 +425,22 @@ def test_large_k_full_size_genomes_every_row_vs_c_oracle(eng, k, G):
     eng.count_device(arena, k=k, counts=counts, totals=totals)
     torch.cuda.synchronize()
     assert np.array_equal(counts.cpu().numpy().astype(np.uint64), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [9, 10])
+def test_large_k_file_batching_over_a_small_workspace(eng, k, monkeypatch):
+    """k >= 8 rows live in a bounded workspace (12 GB): larger batches are run in groups of files.  With the workspace
+    squeezed to a few rows (KF_WS_LIMIT_BYTES) the groups hold 1-3 files: batch-global file ids in tiles and work
+    items, rows relative to the group's first file, the decoded stream indexed by arena chunk."""
+    rng = random.Random(99 + k)
+    bufs = [eng.synth_fasta(11, i, 400_000).tobytes() for i in range(4)] + [rand_fasta(rng), rand_fastq(rng), rand_fasta_grid(rng)] + \
+           [eng.synth_fasta(11, 9, 700_000).tobytes()]
+    ref = [o.canonical_counts_bytes(bytes(b), k) for b in bufs]
+    row_bytes = 4 << (2 * k)
+    for nrows in (1, 3):
+        monkeypatch.setenv("KF_WS_LIMIT_BYTES", str(nrows * row_bytes))
+        counts, freq, totals, status = eng.count_buffers(bufs, k=k)
+        for i in range(len(bufs)):
+            assert np.array_equal(counts[i], ref[i]), (k, nrows, i)
+    monkeypatch.delenv("KF_WS_LIMIT_BYTES")
