@@ -102,36 +102,56 @@ def get_chunks(args) -> None:
     files_names, samples_names = list_inputs(args.input_dir)
     log.info('\n==> Start processing samples. Time: {}\n'.format(stamp()))
 
-    for fname, sample in zip(files_names, samples_names):
-        log.info('\n==> Start processing. Sample: {}'.format(fname))
+    # Three stages run side by side on successive genomes: a helper thread reads and prepares genome i+1 (one C++ pass),
+    # this thread counts the windows of genome i on the GPU, another helper formats and writes the rows of genome i-1.
+    # (The library calls release the GIL; the log lines keep the reference's order.)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def prepare(fname, sample):
         with open(os.path.join(args.input_dir, fname), "rb") as f:
             data = f.read()
-        log.info('>>> Formatting to single line. Sample: {}'.format(fname))
-        log.info('>>> Replacing stretches of N. Sample: {}'.format(fname))
-        log.info('>>> Filtering contigs below threshold {}. Sample: {}'.format(str(CHUNK_SZ), fname))
-        seq, offs, lens, labels = plan_genome(sample, data)
-        if len(seq) == 0:
-            log.info('\n==> Excluded {}. No contigs above threshold length. Time: {}\n'.format(fname, stamp()))
-            continue
-        log.info('>>> Splitting into contigs. Sample: {}'.format(fname))
-        log.info('>>> Getting contig ids. Sample: {}'.format(fname))
-        log.info('>>> Computing contig statistics. Sample: {}'.format(fname))
-        if len(labels) < CHUNK_CNT_THR:
-            log.info('\n==> Excluded {}. {} chunks is too low. {} is required. Time: {}\n'.format(
-                fname, len(labels), CHUNK_CNT_THR, stamp()))
-            continue
-        log.info('\n==> Done chunk processing for {}. Time: {}\n'.format(fname, stamp()))
+        return plan_genome(sample, data)
 
-        counts, _, _ = engine.count_windows(seq, offs, lens, k=k)
-        log.info('\n==> Done computing k-mer frequences for {}. Time: {}\n'.format(fname, stamp()))
-
+    def write_rows(out_path, labels, counts):
         # get_frequencies(raw_cnt=True) rows (main.py:327-357): pandas keeps int64 only when no k-mer is missing
-        out_path = os.path.join(args.output_dir, "{}.{}".format(sample, "kf"))
         vals = counts.astype(np.float64)
         if pseudocount:
             vals += 0.5
         int_modes = np.zeros(len(labels), dtype=np.uint8) if pseudocount else (counts > 0).all(axis=1).astype(np.uint8)
         engine.write_kf_rows(out_path, labels, vals, int_modes=int_modes)
+
+    pairs = list(zip(files_names, samples_names))
+    with ThreadPoolExecutor(1) as prep_pool, ThreadPoolExecutor(1) as write_pool:
+        nxt = prep_pool.submit(prepare, *pairs[0]) if pairs else None
+        pending_write = None
+        for idx, (fname, sample) in enumerate(pairs):
+            log.info('\n==> Start processing. Sample: {}'.format(fname))
+            log.info('>>> Formatting to single line. Sample: {}'.format(fname))
+            log.info('>>> Replacing stretches of N. Sample: {}'.format(fname))
+            log.info('>>> Filtering contigs below threshold {}. Sample: {}'.format(str(CHUNK_SZ), fname))
+            seq, offs, lens, labels = nxt.result()
+            nxt = prep_pool.submit(prepare, *pairs[idx + 1]) if idx + 1 < len(pairs) else None
+            if len(seq) == 0:
+                log.info('\n==> Excluded {}. No contigs above threshold length. Time: {}\n'.format(fname, stamp()))
+                continue
+            log.info('>>> Splitting into contigs. Sample: {}'.format(fname))
+            log.info('>>> Getting contig ids. Sample: {}'.format(fname))
+            log.info('>>> Computing contig statistics. Sample: {}'.format(fname))
+            if len(labels) < CHUNK_CNT_THR:
+                log.info('\n==> Excluded {}. {} chunks is too low. {} is required. Time: {}\n'.format(
+                    fname, len(labels), CHUNK_CNT_THR, stamp()))
+                continue
+            log.info('\n==> Done chunk processing for {}. Time: {}\n'.format(fname, stamp()))
+
+            counts, _, _ = engine.count_windows(seq, offs, lens, k=k)
+            log.info('\n==> Done computing k-mer frequences for {}. Time: {}\n'.format(fname, stamp()))
+
+            if pending_write is not None:
+                pending_write.result()   # (errors of the previous write surface here)
+            out_path = os.path.join(args.output_dir, "{}.{}".format(sample, "kf"))
+            pending_write = write_pool.submit(write_rows, out_path, labels, counts)
+        if pending_write is not None:
+            pending_write.result()
 
     log.info('\n==> Done getting chunks. Time: {}\n'.format(stamp()))
     for h in (fh, sh):
