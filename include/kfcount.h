@@ -94,6 +94,12 @@ int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, co
                    uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out,
                    double *stage_seconds);
 
+/* Files on disk -> the [n, V] float32 feature matrix in DEVICE memory (row i for in_paths[i]: fp32(freq * 1e4), the
+ * tensor train_classifier_model.py:144-150,323 / classify.py:102-114 build from the .kf files), through the same
+ * pipelined reads and GPU stage, without the text round trip.  Rows of files whose status is not KF_OK are undefined. */
+int kf_files_to_device(const char *const *in_paths, int n, int k, uint32_t flags, int threads, size_t batch_bytes,
+                       float *d_feat_out, int *status_out, uint64_t *totals_out, double *stage_seconds);
+
 /* ---- chunked-genome mode: one row per sliding window (get_chunks, main.py:813-881) -------------------------- */
 /* Replaces, per 10-kbp chunk, `seqkit sliding` + `seqkit split` + the jellyfish count/dump pair the reference runs
  * on every chunk file (main.py:824-838, 869-881).  seq is the linearised, N-collapsed, gap-stripped sequence of one

@@ -863,11 +863,15 @@ extern "C" {
 // batches of files: worker threads read batch b+1 into a pinned slab (laid out as the device arena: 512-byte file starts,
 // NUL gaps) while the GPU counts batch b (ONE host-to-device copy of the slab, kernels, device-to-host copy of the rows)
 // and the workers format and write the .kf rows of batch b-1.
-int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, const char *const *samples, int n, int k,
-                   uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out, double *stage_seconds) {
+// out_paths / samples may be NULL (no .kf files: only d_feat_out); d_feat_out may be NULL (device float [n][V], the
+// trainers' matrix fp32(freq * 1e4), row i for in_paths[i]).
+static int files_pipeline(const char *const *in_paths, const char *const *out_paths, const char *const *samples, int n, int k,
+                          uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out, double *stage_seconds,
+                          float *d_feat_out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g.device < 0) return KF_ERR_NO_DEVICE;
-    if (!in_paths || !out_paths || !samples || !status_out || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
+    const bool write_kf = out_paths != nullptr;
+    if (!in_paths || (write_kf && !samples) || (!write_kf && !d_feat_out) || !status_out || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
     if (stage_seconds) for (int i = 0; i < 4; i++) stage_seconds[i] = 0.0;
     if (n == 0) return KF_OK;
     const double t_begin = now_s();
@@ -876,7 +880,7 @@ int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, co
     if (batch_bytes == 0) batch_bytes = (size_t)256 << 20;
     const int64_t V = kf_vocab_size(k);
     const bool raw = (flags & KF_FLAG_RAW_CNT) != 0, pc = (flags & KF_FLAG_PSEUDOCOUNT) != 0;
-    const bool want_counts = raw && !pc;   // the reference prints integers only for raw rows with no missing k-mer
+    const bool want_counts = write_kf && raw && !pc;   // the reference prints integers only for raw rows with no missing k-mer
 
     // sizes and batches (file order kept)
     std::vector<uint64_t> fsize((size_t)n, 0);
@@ -982,14 +986,14 @@ int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, co
         if ((rc = ensure(g.d_counts, g.counts_cap, (size_t)nf * V * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
         if ((rc = ensure(g.d_freq, g.freq_cap, (size_t)nf * V * sizeof(double))) != KF_OK) { rc_all = rc; break; }
         if ((rc = ensure(g.d_totals, g.totals_cap, (size_t)nf * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
-        if ((rc = ensure_pinned(g.h_freq[sl], g.h_freq_cap[sl], (size_t)nf * V * sizeof(double))) != KF_OK) { rc_all = rc; break; }
+        if (write_kf && (rc = ensure_pinned(g.h_freq[sl], g.h_freq_cap[sl], (size_t)nf * V * sizeof(double))) != KF_OK) { rc_all = rc; break; }
         if (want_counts && (rc = ensure_pinned(g.h_cnt[sl], g.h_cnt_cap[sl], (size_t)nf * V * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
         std::vector<unsigned long long> h_tot((size_t)nf, 0ull);
         CK(cudaMemcpyAsync(g.d_arena, g.h_slab[sl], arena_bytes, cudaMemcpyHostToDevice, g.stream));
-        rc = count_device_locked(g.d_arena, arena_bytes, off.data(), len.data(), fmt.data(), nf, k, flags, g.d_counts, g.d_freq, nullptr,
-                                 g.d_totals, g.stream);
+        rc = count_device_locked(g.d_arena, arena_bytes, off.data(), len.data(), fmt.data(), nf, k, flags, g.d_counts, write_kf ? g.d_freq : nullptr,
+                                 d_feat_out ? d_feat_out + (size_t)B.i0 * (size_t)V : nullptr, g.d_totals, g.stream);
         if (rc != KF_OK) { rc_all = rc; break; }
-        CK(cudaMemcpyAsync(g.h_freq[sl], g.d_freq, (size_t)nf * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        if (write_kf) CK(cudaMemcpyAsync(g.h_freq[sl], g.d_freq, (size_t)nf * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
         if (want_counts) CK(cudaMemcpyAsync(g.h_cnt[sl], g.d_counts, (size_t)nf * V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
         CK(cudaMemcpyAsync(h_tot.data(), g.d_totals, (size_t)nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
         CK(cudaStreamSynchronize(g.stream));
@@ -1017,7 +1021,7 @@ int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, co
         for (int j = 0; j < nf; j++) {
             const int i = B.i0 + j;
             if (totals_out) totals_out[i] = h_tot[(size_t)j];
-            if (status_out[i] != KF_OK) continue;
+            if (status_out[i] != KF_OK || !write_kf) continue;
             const double *row = g.h_freq[sl] + (size_t)j * V;
             const unsigned long long *crow = want_counts ? g.h_cnt[sl] + (size_t)j * V : nullptr;
             const char *outp = out_paths[i], *smp = samples[i];
@@ -1040,6 +1044,21 @@ int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, co
     }
     if (stage_seconds) { stage_seconds[0] = t_read; stage_seconds[1] = t_gpu; stage_seconds[2] = t_write; stage_seconds[3] = now_s() - t_begin; }
     return rc_all;
+}
+
+int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, const char *const *samples, int n, int k,
+                   uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out, double *stage_seconds) {
+    if (!out_paths) return KF_ERR_ARG;
+    return files_pipeline(in_paths, out_paths, samples, n, k, flags, threads, batch_bytes, status_out, totals_out, stage_seconds, nullptr);
+}
+
+// Files on disk -> the [n, V] float32 feature matrix in device memory (fp32(freq * 1e4): the tensor
+// train_classifier_model.py:144-150,323 builds from the .kf files), through the same read / GPU pipeline, without the
+// text round trip.  Rows of files whose status is not KF_OK are undefined.
+int kf_files_to_device(const char *const *in_paths, int n, int k, uint32_t flags, int threads, size_t batch_bytes, float *d_feat_out,
+                       int *status_out, uint64_t *totals_out, double *stage_seconds) {
+    if (!d_feat_out) return KF_ERR_ARG;
+    return files_pipeline(in_paths, nullptr, nullptr, n, k, flags, threads, batch_bytes, status_out, totals_out, stage_seconds, d_feat_out);
 }
 
 }  // extern "C"

@@ -342,6 +342,26 @@ def files_to_kf(in_paths: Sequence[str], out_paths: Sequence[str], samples: Sequ
     return status, totals, secs
 
 
+def files_to_device(in_paths: Sequence[str], feat, k: int = 7, pseudocount: bool = False, threads: int = 0, batch_bytes: int = 0):
+    """Files on disk -> rows of ``feat`` (torch.float32 CUDA tensor [n, V], contiguous) through the pipelined C entry
+    point.  Returns (status i32 [n], totals u64 [n], stage seconds)."""
+    _require_init()
+    L = _load()
+    n = len(in_paths)
+    assert feat.is_cuda and feat.is_contiguous() and tuple(feat.shape) == (n, vocab_size(k)) and str(feat.dtype) == "torch.float32"
+    paths = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(x) for x in in_paths])
+    status = np.zeros(n, dtype=np.int32)
+    totals = np.zeros(n, dtype=np.uint64)
+    secs = np.zeros(4, dtype=np.float64)
+    L.kf_files_to_device.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int,
+                                     ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_files_to_device.restype = ctypes.c_int
+    rc = L.kf_files_to_device(paths, n, k, _flags(pseudocount, False), int(threads), int(batch_bytes), ctypes.c_void_p(feat.data_ptr()),
+                              status.ctypes.data, totals.ctypes.data, secs.ctypes.data)
+    _check(rc, "kf_files_to_device")
+    return status, totals, secs
+
+
 def set_sm_limit(n_sms: int) -> int:
     """Sizes the persistent counting kernels for n_sms SMs (0 = all); returns the SM count in effect."""
     _require_init()

@@ -93,13 +93,13 @@ def frequency_matrix(input_dir: str, k: int = DEFAULT_K, pseudocount: bool = Fal
     files_names, samples_names = list_inputs(input_dir)
     paths = [os.path.join(input_dir, f) for f in files_names]
     V = engine.vocab_size(k)
-    engine.init()
-    rows = []
-    for batch in _batches(paths):
-        bufs = [np.fromfile(paths[i], dtype=np.uint8) for i in batch]
-        arena = engine.DeviceArena(bufs, device=device)
-        feat = torch.empty((arena.n, V), dtype=torch.float32, device=arena.device)
-        engine.count_device(arena, k=k, pseudocount=pseudocount, feat=feat)
-        rows.append(feat)
-    torch.cuda.synchronize()
-    return samples_names, (torch.cat(rows, 0) if rows else torch.empty((0, V), dtype=torch.float32))
+    dev_index = engine.init() if device is None else engine.init(torch.device(device).index or 0)
+    feat = torch.empty((len(paths), V), dtype=torch.float32, device=torch.device("cuda", dev_index))
+    if paths:
+        # pipelined reads (host threads, pinned slabs) + GPU stage; the rows never leave the device
+        status, _, _ = engine.files_to_device(paths, feat, k=k, pseudocount=pseudocount, batch_bytes=BATCH_BYTES)
+        for i in range(len(paths)):
+            if status[i] != 0:
+                raise engine.KfError(int(status[i]), "k-mer counting failed for {}".format(files_names[i]))
+        torch.cuda.synchronize(feat.device)
+    return samples_names, feat

@@ -444,3 +444,28 @@ def test_large_k_file_batching_over_a_small_workspace(eng, k, monkeypatch):
         for i in range(len(bufs)):
             assert np.array_equal(counts[i], ref[i]), (k, nrows, i)
     monkeypatch.delenv("KF_WS_LIMIT_BYTES")
+
+
+@pytest.mark.gpu
+def test_frequency_matrix_fast_path_equals_the_kf_round_trip(eng, toy_inputs, tmp_path):
+    """frequency_matrix (files -> [N, V] float32 on the device through kf_files_to_device: pipelined reads, no text) holds
+    exactly the tensor the trainers build from the .kf files: float32(float64 frequency * 1e4)
+    (train_classifier_model.py:144-150,323), in os.listdir order, over several pipeline batches."""
+    from kf2vecfsw_b200 import frequency_matrix, frequencies
+    ind = tmp_path / "in"
+    ind.mkdir()
+    data = {"a": toy_inputs["G000830275sub"], "b": toy_inputs["G000402355sub"], "c": eng.synth_fasta(5, 0, 500_000).tobytes(),
+            "d": eng.synth_fastq(5, 0, 100_000, 3_000, 150).tobytes()}
+    for s, b in data.items():
+        (ind / (s + (".fastq" if s == "d" else ".fna"))).write_bytes(b)
+    old = frequencies.BATCH_BYTES
+    frequencies.BATCH_BYTES = 700_000
+    try:
+        names, X = frequency_matrix(str(ind), k=7)
+    finally:
+        frequencies.BATCH_BYTES = old
+    assert sorted(names) == sorted(data)
+    counts, freq, totals, status = eng.count_buffers([data[n] for n in names], k=7)
+    want = (freq * 1e4).astype(np.float32)
+    assert X.dtype.__str__() == "torch.float32" and tuple(X.shape) == want.shape
+    assert np.array_equal(X.cpu().numpy(), want)
