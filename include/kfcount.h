@@ -136,6 +136,10 @@ int kf_set_sm_limit(int n_sms);
 /* Device time of the counting kernel(s) of the last kf_count_device / kf_count_buffers call, from CUDA
  * events recorded on the launching stream (waits for them).  Used for the roofline figure. */
 int kf_last_count_kernel_ms(float *ms);
+/* Durations (ms, CUDA events on the launching stream) of the counting kernels of the last n calls, oldest first, at most
+ * 64; returns how many were written.  Waits for those calls: meant to be read AFTER a timed loop, so that the loop itself
+ * runs without host synchronisation (bench.py: roofline.achieved over the timed region). */
+int kf_count_kernel_ms_history(float *ms_out, int n);
 
 /* ---- .kf writer: main.py:344-357 --------------------------------------------------------------- */
 /* Formats one row exactly as pandas `astype(str)` + ",".join does (Python repr of float64: shortest

@@ -40,8 +40,14 @@ struct Ctx {
     int sm_count = 0;
     int sm_all = 0;   // the device's SM count; sm_count = SMs the counting kernels are sized for (kf_set_sm_limit)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;   // ev_k0/ev_k1: the current call's pair of the ring below
     bool ev_valid = false;
+    // the counting kernels of the last EV_RING calls, timed on the launching stream (read back after the fact, so a
+    // timed loop needs no host synchronisation between its steps)
+    static constexpr int EV_RING = 64;
+    cudaEvent_t ring0[EV_RING] = {nullptr}, ring1[EV_RING] = {nullptr};
+    bool ring_valid[EV_RING] = {false};
+    long long n_calls = 0;
     // workspaces (grow-only)
     void *d_fwd = nullptr; size_t fwd_cap = 0;
     Tile *d_tiles = nullptr; size_t tiles_cap = 0;
@@ -540,7 +546,15 @@ int count_device_locked(const uint8_t *d_arena, size_t arena_bytes, const uint64
     if (prev_end + KF_TAIL_PAD > arena_bytes) return KF_ERR_LAYOUT;
     if ((prev_end + CHUNK - 1) / CHUNK + 2 >= 0xFFFFFFFFull) return KF_ERR_ARG;
     g.last_launches = 0;
+    if (g.ev_valid) g.ring_valid[(g.n_calls - 1 + Ctx::EV_RING) % Ctx::EV_RING] = true;   // (the previous call's pair was recorded)
     g.ev_valid = false;
+    {
+        const int slot = (int)(g.n_calls % Ctx::EV_RING);
+        g.n_calls++;
+        g.ring_valid[slot] = false;
+        g.ev_k0 = g.ring0[slot];
+        g.ev_k1 = g.ring1[slot];
+    }
     g.fq_err_n = 0;
     if (n == 0) return KF_OK;
     {
@@ -586,8 +600,9 @@ int kf_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
-    CK(cudaEventCreate(&g.ev_k0));
-    CK(cudaEventCreate(&g.ev_k1));
+    for (int i = 0; i < Ctx::EV_RING; i++) { CK(cudaEventCreate(&g.ring0[i])); CK(cudaEventCreate(&g.ring1[i])); }
+    g.ev_k0 = g.ring0[0];
+    g.ev_k1 = g.ring1[0];
     CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&g.d_item_counter, 2 * sizeof(unsigned int)));
     g.sm_count = g.sm_all = prop.multiProcessorCount;
@@ -605,7 +620,7 @@ int kf_shutdown(void) {
     cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_file_row); cudaFree(g.d_cta_first_rank); cudaFree(g.d_width_counts);
     for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
-    cudaEventDestroy(g.ev_k0); cudaEventDestroy(g.ev_k1);
+    for (int i = 0; i < Ctx::EV_RING; i++) { cudaEventDestroy(g.ring0[i]); cudaEventDestroy(g.ring1[i]); }
     g = Ctx();
     return KF_OK;
 }
@@ -627,6 +642,23 @@ int kf_last_count_kernel_ms(float *ms) {
     CK(cudaEventSynchronize(g.ev_k1));
     CK(cudaEventElapsedTime(ms, g.ev_k0, g.ev_k1));
     return KF_OK;
+}
+
+int kf_count_kernel_ms_history(float *ms_out, int n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.device < 0) return KF_ERR_NO_DEVICE;
+    if (!ms_out || n < 0) return KF_ERR_ARG;
+    if (g.ev_valid) g.ring_valid[(g.n_calls - 1 + Ctx::EV_RING) % Ctx::EV_RING] = true;
+    n = std::min<long long>(std::min<long long>(n, Ctx::EV_RING), g.n_calls);
+    int w = 0;
+    for (int i = n; i >= 1; i--) {   // oldest of the n first
+        const int slot = (int)((g.n_calls - i) % Ctx::EV_RING);
+        if (!g.ring_valid[slot]) continue;
+        CK(cudaEventSynchronize(g.ring1[slot]));
+        CK(cudaEventElapsedTime(ms_out + w, g.ring0[slot], g.ring1[slot]));
+        w++;
+    }
+    return w;
 }
 
 int kf_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *offsets, const uint64_t *lens,

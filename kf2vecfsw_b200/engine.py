@@ -362,6 +362,19 @@ def files_to_device(in_paths: Sequence[str], feat, k: int = 7, pseudocount: bool
     return status, totals, secs
 
 
+def count_kernel_ms_history(n: int) -> np.ndarray:
+    """Durations (ms) of the counting kernels of the last n calls (oldest first, at most 64); waits for them."""
+    _require_init()
+    L = _load()
+    out = np.zeros(max(n, 1), dtype=np.float32)
+    L.kf_count_kernel_ms_history.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.kf_count_kernel_ms_history.restype = ctypes.c_int
+    w = int(L.kf_count_kernel_ms_history(out.ctypes.data, int(n)))
+    if w < 0:
+        raise KfError(w, "kf_count_kernel_ms_history")
+    return out[:w]
+
+
 def set_sm_limit(n_sms: int) -> int:
     """Sizes the persistent counting kernels for n_sms SMs (0 = all); returns the SM count in effect."""
     _require_init()
