@@ -22,6 +22,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import kfsynth  # noqa: E402  (input generator: tools/libkfsynth.so, not the product library)
 
 METRIC = "Gbases/s k=7 k-mer frequency"
 UNIT = "Gbases/s"
@@ -54,7 +56,7 @@ def generate_genomes(engine, ids, n_bases, threads, pinned=True):
     """Synthetic 80-column FASTA genomes (kf_synth_fasta) written into one (pinned) host buffer."""
     import numpy as np
     import torch
-    sizes = [engine.synth_fasta_size(SEED, g, n_bases) for g in ids]
+    sizes = [kfsynth.synth_fasta_size(SEED, g, n_bases) for g in ids]
     offs = np.zeros(len(ids) + 1, dtype=np.int64)
     offs[1:] = np.cumsum(sizes)
     host = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=pinned)
@@ -62,7 +64,7 @@ def generate_genomes(engine, ids, n_bases, threads, pinned=True):
     views = [hnp[offs[i]:offs[i + 1]] for i in range(len(ids))]
 
     def work(i):
-        engine.synth_fasta(SEED, ids[i], n_bases, out=views[i])
+        kfsynth.synth_fasta(SEED, ids[i], n_bases, out=views[i])
 
     with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
         list(ex.map(work, range(len(ids))))
@@ -133,7 +135,7 @@ def cpu_reference_run(engine, n_bases, k, steps, warmup, budget_s_per_step=2.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     threads = host_threads()
-    probe = [engine.synth_fasta(SEED, 0, n_bases)]
+    probe = [kfsynth.synth_fasta(SEED, 0, n_bases)]
     t0 = time.perf_counter()
     c_oracle.count_buffers_mt(probe, k, 1)
     t1 = max(time.perf_counter() - t0, 1e-4)

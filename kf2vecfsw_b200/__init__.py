@@ -16,11 +16,10 @@ from .engine import (  # noqa: F401
     DeviceArena,
     format_row,
     init,
+    shutdown,
     last_count_kernel_ms,
     last_launch_count,
     lib_path,
-    synth_fasta,
-    synth_fastq,
     vocab,
     vocab_codes,
     vocab_size,

@@ -95,6 +95,14 @@ struct Ctx {
     std::vector<uint8_t> pc_formats;
     int pc_k = -1, pc_grid = 0, pc_ntiles = 0;
     uint32_t pc_f0 = 0, pc_f1 = 0;
+    // plan tables are staged in pinned memory (two blocks used in turn) and uploaded on the launching stream
+    uint8_t *h_stage[2] = {nullptr, nullptr}; size_t h_stage_cap[2] = {0, 0};
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    bool stage_pending[2] = {false, false};
+    int stage_next = 0;
+    cudaEvent_t ev_done = nullptr;          // recorded at the end of every run_files on its stream
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
     std::string last_err;
     int last_launches = 0;
 };
@@ -124,6 +132,19 @@ int ensure(T *&ptr, size_t &cap, size_t need_bytes) {
         if (e != cudaSuccess) { cudaGetLastError(); g.last_err = "cudaMalloc failed"; return KF_ERR_NOMEM; }
     }
     cap = want;
+    return KF_OK;
+}
+
+template <typename T>
+int ensure_pinned(T *&ptr, size_t &cap, size_t need_bytes) {
+    if (need_bytes <= cap) return KF_OK;
+    if (ptr) { CK(cudaFreeHost(ptr)); ptr = nullptr; cap = 0; }
+    if (cudaHostAlloc((void **)&ptr, need_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        g.last_err = "cudaHostAlloc failed";
+        return KF_ERR_NOMEM;
+    }
+    cap = need_bytes;
     return KF_OK;
 }
 
@@ -371,41 +392,21 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                std::equal(g.pc_lens.begin(), g.pc_lens.end(), lens + f0) &&
                std::equal(g.pc_formats.begin(), g.pc_formats.end(), formats + f0);
     if (!hit) {
-        std::vector<Tile> tiles;
-        std::vector<int> cta_begin;
-        build_plan(offsets, lens, formats, f0, f1, grid, tiles, cta_begin);
-        if ((rc = ensure(g.d_tiles, g.tiles_cap, (tiles.size() + 1) * sizeof(Tile))) != KF_OK) return rc;
-        if ((rc = ensure(g.d_cta_begin, g.cta_cap, cta_begin.size() * sizeof(int))) != KF_OK) return rc;
-        // the tables may still be read by kernels of a previous call on another stream
-        CK(cudaDeviceSynchronize());
-        if (!tiles.empty()) CK(cudaMemcpy(g.d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(g.d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-        // per-file tables are indexed by batch-global file id
-        if ((rc = ensure(g.d_file_off, g.foff_cap, (size_t)f1 * sizeof(uint64_t))) != KF_OK) return rc;
-        if ((rc = ensure(g.d_file_len, g.flen_cap, (size_t)f1 * sizeof(uint64_t))) != KF_OK) return rc;
-        if ((rc = ensure(g.d_formats, g.fmt_cap, (size_t)f1)) != KF_OK) return rc;
-        if ((rc = ensure(g.d_file_P, g.fP_cap, (size_t)f1 * sizeof(uint32_t))) != KF_OK) return rc;
-        CK(cudaMemcpy(g.d_file_off, offsets, (size_t)f1 * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(g.d_file_len, lens, (size_t)f1 * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(g.d_formats, formats, (size_t)f1, cudaMemcpyHostToDevice));
-        {
-            std::vector<Tile> fq_tiles;
-            std::vector<int> fq_cta_begin, fq_ftb;
-            build_fastq_plan(offsets, lens, formats, f0, f1, grid, fq_tiles, fq_cta_begin, fq_ftb);
-            g.pc_fq_ntiles = (int)fq_tiles.size();
-            g.pc_fq_nfiles = (int)fq_ftb.size() - 1;
-            if (g.pc_fq_ntiles > 0) {
-                if ((rc = ensure(g.d_fq_tiles, g.fq_tiles_cap, fq_tiles.size() * sizeof(Tile))) != KF_OK) return rc;
-                if ((rc = ensure(g.d_fq_cta_begin, g.fq_cta_cap, fq_cta_begin.size() * sizeof(int))) != KF_OK) return rc;
-                CK(cudaMemcpy(g.d_fq_tiles, fq_tiles.data(), fq_tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
-                CK(cudaMemcpy(g.d_fq_cta_begin, fq_cta_begin.data(), fq_cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-            }
-        }
+        // Not failure-atomic otherwise: the keys are dropped first and set again only after every upload was queued.
+        g.pc_k = -1;
         g.pc_items = 0;
+        g.pc_items_b = 0;
         g.pc_part_mode = part_mode;
+        // ---- phase 1: host tables ----
+        std::vector<Tile> tiles, fq_tiles;
+        std::vector<int> cta_begin, fq_cta_begin, fq_ftb, file_t0;
+        std::vector<uint32_t> items, taken, file_row, cta_first_rank;
+        build_plan(offsets, lens, formats, f0, f1, grid, tiles, cta_begin);
+        build_fastq_plan(offsets, lens, formats, f0, f1, grid, fq_tiles, fq_cta_begin, fq_ftb);
+        size_t n_items_a = 0, n_items_b = 0;
         if (k >= 8 && k <= 10 && part_mode != 0) {
             // (file, partition) items for FASTA files of at least PART_MIN_BYTES; file_P doubles as the "taken" flag
-            std::vector<int> file_t0((size_t)f1 + 1, 0);
+            file_t0.assign((size_t)f1 + 1, 0);
             {
                 size_t t = 0;
                 for (uint32_t f = 0; f < f1; f++) {
@@ -414,7 +415,8 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 }
                 file_t0[f1] = (int)t;
             }
-            std::vector<uint32_t> items, items_b, taken((size_t)f1, 0u);
+            std::vector<uint32_t> items_b;
+            taken.assign((size_t)f1, 0u);
             const uint32_t P = k == 8 ? PartGeom<8, 0>::NPART : k == 9 ? PartGeom<9, 3>::NPART : PartGeom<10, 5>::NPART;
             for (uint32_t f = f0; f < f1; f++) {
                 if (formats[f] != '>' || lens[f] == 0 || (lens[f] < PART_MIN_BYTES && part_mode != 2)) continue;
@@ -423,29 +425,83 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                 for (uint32_t pp = 1; pp < P; pp++) items_b.push_back((f << 8) | pp);  // stream passes, a file's side by side
             }
             if (f1 >= (1u << 24)) items.clear(), items_b.clear(), std::fill(taken.begin(), taken.end(), 0u);   // (file id must fit the item word)
-            g.pc_items_b = (int)items_b.size();
-            const size_t n_a = items.size();
+            n_items_a = items.size();
+            n_items_b = items_b.size();
             items.insert(items.end(), items_b.begin(), items_b.end());
+        }
+        if (smem_path) build_rows(tiles, cta_begin, grid, CTAS_PER_SM, f1, k == 7, file_row, cta_first_rank);
+        // ---- phase 2: device capacity ----
+        if ((rc = ensure(g.d_tiles, g.tiles_cap, (tiles.size() + 1) * sizeof(Tile))) != KF_OK) return rc;
+        if ((rc = ensure(g.d_cta_begin, g.cta_cap, cta_begin.size() * sizeof(int))) != KF_OK) return rc;
+        // per-file tables are indexed by batch-global file id
+        if ((rc = ensure(g.d_file_off, g.foff_cap, (size_t)f1 * sizeof(uint64_t))) != KF_OK) return rc;
+        if ((rc = ensure(g.d_file_len, g.flen_cap, (size_t)f1 * sizeof(uint64_t))) != KF_OK) return rc;
+        if ((rc = ensure(g.d_formats, g.fmt_cap, (size_t)f1)) != KF_OK) return rc;
+        if ((rc = ensure(g.d_file_P, g.fP_cap, (size_t)f1 * sizeof(uint32_t))) != KF_OK) return rc;
+        if (!fq_tiles.empty()) {
+            if ((rc = ensure(g.d_fq_tiles, g.fq_tiles_cap, fq_tiles.size() * sizeof(Tile))) != KF_OK) return rc;
+            if ((rc = ensure(g.d_fq_cta_begin, g.fq_cta_cap, fq_cta_begin.size() * sizeof(int))) != KF_OK) return rc;
+        }
+        if (!file_t0.empty()) {
             if ((rc = ensure(g.d_file_t0, g.ft0_cap, file_t0.size() * sizeof(int))) != KF_OK) return rc;
             if ((rc = ensure(g.d_items, g.items_cap, (items.size() + 1) * sizeof(uint32_t))) != KF_OK) return rc;
-            CK(cudaMemcpy(g.d_file_t0, file_t0.data(), file_t0.size() * sizeof(int), cudaMemcpyHostToDevice));
-            if (!items.empty()) CK(cudaMemcpy(g.d_items, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(g.d_file_P, taken.data(), (size_t)f1 * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            g.pc_items = (int)n_a;
         }
         if (smem_path) {
-            std::vector<uint32_t> file_row, cta_first_rank;
-            build_rows(tiles, cta_begin, grid, CTAS_PER_SM, f1, k == 7, file_row, cta_first_rank);
             if ((rc = ensure(g.d_file_row, g.frow_cap, file_row.size() * sizeof(uint32_t))) != KF_OK) return rc;
             if ((rc = ensure(g.d_cta_first_rank, g.cfr_cap, cta_first_rank.size() * sizeof(uint32_t))) != KF_OK) return rc;
-            CK(cudaMemcpy(g.d_file_row, file_row.data(), file_row.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(g.d_cta_first_rank, cta_first_rank.data(), cta_first_rank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-            g.pc_rows = file_row.back();
         }
-        g.pc_k = k; g.pc_grid = grid; g.pc_f0 = f0; g.pc_f1 = f1; g.pc_ntiles = (int)tiles.size();
+        // ---- phase 3: uploads, stream-ordered.  The tables are packed into a pinned staging block and copied with
+        // cudaMemcpyAsync on the launching stream, so the kernels queued behind them on that stream see them (a blocking
+        // cudaMemcpy from pageable memory may return before its DMA has landed and is not ordered against non-blocking
+        // streams).  A previous call's kernels on ANOTHER stream may still be reading the old tables: wait for them on
+        // the device, not on the host. ----
+        if (g.last_stream_valid && g.last_stream != s) CK(cudaStreamWaitEvent(s, g.ev_done, 0));
+        struct Up { void *dst; const void *src; size_t bytes; };
+        std::vector<Up> ups;
+        auto add = [&](void *dst, const void *src, size_t bytes) { if (bytes) ups.push_back({dst, src, bytes}); };
+        add(g.d_tiles, tiles.data(), tiles.size() * sizeof(Tile));
+        add(g.d_cta_begin, cta_begin.data(), cta_begin.size() * sizeof(int));
+        add(g.d_file_off, offsets, (size_t)f1 * sizeof(uint64_t));
+        add(g.d_file_len, lens, (size_t)f1 * sizeof(uint64_t));
+        add(g.d_formats, formats, (size_t)f1);
+        if (!fq_tiles.empty()) {
+            add(g.d_fq_tiles, fq_tiles.data(), fq_tiles.size() * sizeof(Tile));
+            add(g.d_fq_cta_begin, fq_cta_begin.data(), fq_cta_begin.size() * sizeof(int));
+        }
+        if (!file_t0.empty()) {
+            add(g.d_file_t0, file_t0.data(), file_t0.size() * sizeof(int));
+            add(g.d_items, items.data(), items.size() * sizeof(uint32_t));
+            add(g.d_file_P, taken.data(), (size_t)f1 * sizeof(uint32_t));
+        }
+        if (smem_path) {
+            add(g.d_file_row, file_row.data(), file_row.size() * sizeof(uint32_t));
+            add(g.d_cta_first_rank, cta_first_rank.data(), cta_first_rank.size() * sizeof(uint32_t));
+        }
+        size_t total = 0;
+        for (auto &u : ups) total += (u.bytes + 255) & ~(size_t)255;
+        const int sl = g.stage_next;
+        g.stage_next ^= 1;
+        if (g.stage_pending[sl]) { CK(cudaEventSynchronize(g.ev_stage[sl])); g.stage_pending[sl] = false; }
+        if (total + 256 > g.h_stage_cap[sl] &&
+            (rc = ensure_pinned(g.h_stage[sl], g.h_stage_cap[sl], std::max<size_t>(total + total / 2 + 256, (size_t)1 << 20))) != KF_OK) return rc;
+        size_t o = 0;
+        for (auto &u : ups) {
+            memcpy(g.h_stage[sl] + o, u.src, u.bytes);
+            CK(cudaMemcpyAsync(u.dst, g.h_stage[sl] + o, u.bytes, cudaMemcpyHostToDevice, s));
+            o += (u.bytes + 255) & ~(size_t)255;
+        }
+        CK(cudaEventRecord(g.ev_stage[sl], s));
+        g.stage_pending[sl] = true;
+        g.pc_fq_ntiles = (int)fq_tiles.size();
+        g.pc_fq_nfiles = (int)fq_ftb.size() - 1;
+        g.pc_items = (int)n_items_a;
+        g.pc_items_b = (int)n_items_b;
+        if (smem_path) g.pc_rows = file_row.back();
+        g.pc_grid = grid; g.pc_f0 = f0; g.pc_f1 = f1; g.pc_ntiles = (int)tiles.size();
         g.pc_offsets.assign(offsets + f0, offsets + f1);
         g.pc_lens.assign(lens + f0, lens + f1);
         g.pc_formats.assign(formats + f0, formats + f1);
+        g.pc_k = k;   // (last: the cache is valid only from here on)
     }
     // forward-count workspace: u64 rows (see build_rows) for k <= 7, one u32 row per file for k >= 8
     const size_t fwd_bytes = smem_path ? (size_t)g.pc_rows * NB * sizeof(unsigned long long) : (size_t)nf * NB * sizeof(uint32_t);
@@ -530,6 +586,9 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
                                                              d_counts, d_freq, d_feat, d_totals);
     CK(cudaGetLastError());
     g.last_launches++;
+    CK(cudaEventRecord(g.ev_done, s));
+    g.last_stream = s;
+    g.last_stream_valid = true;
     return KF_OK;
 }
 
@@ -600,6 +659,8 @@ int kf_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&g.ev_stage[i], cudaEventDisableTiming));
     for (int i = 0; i < Ctx::EV_RING; i++) { CK(cudaEventCreate(&g.ring0[i])); CK(cudaEventCreate(&g.ring1[i])); }
     g.ev_k0 = g.ring0[0];
     g.ev_k1 = g.ring1[0];
@@ -614,13 +675,22 @@ int kf_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g.device < 0) return KF_OK;
     cudaDeviceSynchronize();
-    cudaFree(g.d_fwd); cudaFree(g.d_tiles); cudaFree(g.d_cta_begin); cudaFree(g.d_arena);
-    cudaFree(g.d_counts); cudaFree(g.d_freq); cudaFree(g.d_totals); cudaFree(g.d_seq); cudaFree(g.d_win_off); cudaFree(g.d_win_len);
-    cudaFree(g.d_fq_tiles); cudaFree(g.d_fq_cta_begin); cudaFree(g.d_fq_err);
-    cudaFree(g.d_file_off); cudaFree(g.d_file_len); cudaFree(g.d_formats); cudaFree(g.d_file_P); cudaFree(g.d_file_row); cudaFree(g.d_cta_first_rank); cudaFree(g.d_width_counts);
-    for (auto &p : g.d_canon) { cudaFree(p); p = nullptr; }
-    cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy);
+    void *dev_ptrs[] = {g.d_fwd, g.d_tiles, g.d_cta_begin, g.d_arena, g.d_counts, g.d_freq, g.d_totals, g.d_seq, g.d_win_off, g.d_win_len,
+                        g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_err, g.d_file_off, g.d_file_len, g.d_formats, g.d_file_P, g.d_file_row,
+                        g.d_cta_first_rank, g.d_width_counts, g.d_file_t0, g.d_items, g.d_item_counter, g.d_stream, g.d_fold_tot};
+    for (void *p : dev_ptrs) if (p) cudaFree(p);
+    for (auto &p : g.d_canon) { if (p) cudaFree(p); p = nullptr; }
+    for (auto &p : g.d_rank) { if (p) cudaFree(p); p = nullptr; }
+    for (int i = 0; i < 2; i++) {
+        if (g.h_slab[i]) cudaFreeHost(g.h_slab[i]);
+        if (g.h_freq[i]) cudaFreeHost(g.h_freq[i]);
+        if (g.h_cnt[i]) cudaFreeHost(g.h_cnt[i]);
+        if (g.h_stage[i]) cudaFreeHost(g.h_stage[i]);
+        if (g.ev_stage[i]) cudaEventDestroy(g.ev_stage[i]);
+    }
+    cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy); cudaEventDestroy(g.ev_done);
     for (int i = 0; i < Ctx::EV_RING; i++) { cudaEventDestroy(g.ring0[i]); cudaEventDestroy(g.ring1[i]); }
+    cudaGetLastError();
     g = Ctx();
     return KF_OK;
 }
@@ -798,49 +868,10 @@ int kf_count_windows(const uint8_t *seq, size_t seq_len, const uint64_t *win_off
     return KF_OK;
 }
 
-int kf_count_files(const char *const *paths, int n, int k, uint32_t flags, uint64_t *counts_out, double *freq_out,
-                   uint64_t *totals_out, int *status_out) {
-    if (!paths || !status_out || n < 0) return KF_ERR_ARG;
-    if (g.device < 0) return KF_ERR_NO_DEVICE;
-    std::vector<std::vector<uint8_t>> data((size_t)n);
-    std::vector<const uint8_t *> bufs((size_t)n);
-    std::vector<size_t> lens((size_t)n);
-    std::vector<int> io_fail((size_t)n, 0);
-    for (int i = 0; i < n; i++) {
-        FILE *f = fopen(paths[i], "rb");
-        if (!f) { io_fail[(size_t)i] = 1; continue; }
-        fseek(f, 0, SEEK_END);
-        long sz = ftell(f);
-        fseek(f, 0, SEEK_SET);
-        data[(size_t)i].resize(sz > 0 ? (size_t)sz : 0);
-        if (sz > 0 && fread(data[(size_t)i].data(), 1, (size_t)sz, f) != (size_t)sz) io_fail[(size_t)i] = 1;
-        fclose(f);
-        bufs[(size_t)i] = data[(size_t)i].data();
-        lens[(size_t)i] = io_fail[(size_t)i] ? 0 : data[(size_t)i].size();
-    }
-    int rc = kf_count_buffers(bufs.data(), lens.data(), n, k, flags, counts_out, freq_out, totals_out, status_out);
-    for (int i = 0; i < n; i++)
-        if (io_fail[(size_t)i]) status_out[i] = KF_ERR_IO;
-    return rc;
-}
-
 }  // extern "C"
 
 namespace kf {
 namespace {
-
-template <typename T>
-int ensure_pinned(T *&ptr, size_t &cap, size_t need_bytes) {
-    if (need_bytes <= cap) return KF_OK;
-    if (ptr) { CK(cudaFreeHost(ptr)); ptr = nullptr; cap = 0; }
-    if (cudaHostAlloc((void **)&ptr, need_bytes, cudaHostAllocDefault) != cudaSuccess) {
-        cudaGetLastError();
-        g.last_err = "cudaHostAlloc failed";
-        return KF_ERR_NOMEM;
-    }
-    cap = need_bytes;
-    return KF_OK;
-}
 
 // Minimal worker pool of one kf_files_to_kf call: tasks are file reads and .kf writes.
 class Pool {
@@ -897,13 +928,14 @@ extern "C" {
 // and the workers format and write the .kf rows of batch b-1.
 // out_paths / samples may be NULL (no .kf files: only d_feat_out); d_feat_out may be NULL (device float [n][V], the
 // trainers' matrix fp32(freq * 1e4), row i for in_paths[i]).
+// counts_host / freq_host (kf_count_files): host [n][V] arrays that receive the rows (may be NULL).
 static int files_pipeline(const char *const *in_paths, const char *const *out_paths, const char *const *samples, int n, int k,
                           uint32_t flags, int threads, size_t batch_bytes, int *status_out, uint64_t *totals_out, double *stage_seconds,
-                          float *d_feat_out) {
+                          float *d_feat_out, uint64_t *counts_host = nullptr, double *freq_host = nullptr, bool host_rows = false) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g.device < 0) return KF_ERR_NO_DEVICE;
     const bool write_kf = out_paths != nullptr;
-    if (!in_paths || (write_kf && !samples) || (!write_kf && !d_feat_out) || !status_out || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
+    if (!in_paths || (write_kf && !samples) || (!write_kf && !d_feat_out && !host_rows) || !status_out || n < 0 || k < KF_MIN_K || k > KF_MAX_K) return KF_ERR_ARG;
     if (stage_seconds) for (int i = 0; i < 4; i++) stage_seconds[i] = 0.0;
     if (n == 0) return KF_OK;
     const double t_begin = now_s();
@@ -1007,7 +1039,13 @@ static int files_pipeline(const char *const *in_paths, const char *const *out_pa
             if (status_out[i] != KF_OK) { fmt[(size_t)j] = 0; len[(size_t)j] = 0; continue; }
             if (len[(size_t)j] == 0) { status_out[i] = KF_ERR_EMPTY; fmt[(size_t)j] = 0; continue; }
             fmt[(size_t)j] = g.h_slab[sl][off[(size_t)j]];
-            if (fmt[(size_t)j] != '>' && fmt[(size_t)j] != '@') { status_out[i] = KF_ERR_FORMAT; len[(size_t)j] = 0; }
+            if (fmt[(size_t)j] != '>' && fmt[(size_t)j] != '@') {
+                // rejected: its bytes are already in the slab -- blank its first bytes so that a preceding file that
+                // ends without a newline exactly on a 512-byte boundary cannot run on into them
+                status_out[i] = KF_ERR_FORMAT;
+                memset(g.h_slab[sl] + off[(size_t)j], 0, (size_t)std::min<uint64_t>(64, len[(size_t)j]));
+                len[(size_t)j] = 0;
+            }
         }
         // next batch's reads and the previous batch's writes run beside this batch's GPU work
         const double t1 = now_s();
@@ -1022,9 +1060,12 @@ static int files_pipeline(const char *const *in_paths, const char *const *out_pa
         if (want_counts && (rc = ensure_pinned(g.h_cnt[sl], g.h_cnt_cap[sl], (size_t)nf * V * sizeof(unsigned long long))) != KF_OK) { rc_all = rc; break; }
         std::vector<unsigned long long> h_tot((size_t)nf, 0ull);
         CK(cudaMemcpyAsync(g.d_arena, g.h_slab[sl], arena_bytes, cudaMemcpyHostToDevice, g.stream));
-        rc = count_device_locked(g.d_arena, arena_bytes, off.data(), len.data(), fmt.data(), nf, k, flags, g.d_counts, write_kf ? g.d_freq : nullptr,
+        rc = count_device_locked(g.d_arena, arena_bytes, off.data(), len.data(), fmt.data(), nf, k, flags, g.d_counts,
+                                 (write_kf || freq_host) ? g.d_freq : nullptr,
                                  d_feat_out ? d_feat_out + (size_t)B.i0 * (size_t)V : nullptr, g.d_totals, g.stream);
         if (rc != KF_OK) { rc_all = rc; break; }
+        if (counts_host) CK(cudaMemcpyAsync(counts_host + (size_t)B.i0 * (size_t)V, g.d_counts, (size_t)nf * V * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+        if (freq_host) CK(cudaMemcpyAsync(freq_host + (size_t)B.i0 * (size_t)V, g.d_freq, (size_t)nf * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
         if (write_kf) CK(cudaMemcpyAsync(g.h_freq[sl], g.d_freq, (size_t)nf * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
         if (want_counts) CK(cudaMemcpyAsync(g.h_cnt[sl], g.d_counts, (size_t)nf * V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
         CK(cudaMemcpyAsync(h_tot.data(), g.d_totals, (size_t)nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
@@ -1087,6 +1128,13 @@ int kf_files_to_kf(const char *const *in_paths, const char *const *out_paths, co
 // Files on disk -> the [n, V] float32 feature matrix in device memory (fp32(freq * 1e4): the tensor
 // train_classifier_model.py:144-150,323 builds from the .kf files), through the same read / GPU pipeline, without the
 // text round trip.  Rows of files whose status is not KF_OK are undefined.
+// The loop body of main.py:301-342 for n files with the rows returned in host arrays: the same pipelined reads (host
+// threads into pinned slabs, one H2D copy per batch) as kf_files_to_kf, no text.
+int kf_count_files(const char *const *paths, int n, int k, uint32_t flags, uint64_t *counts_out, double *freq_out,
+                   uint64_t *totals_out, int *status_out) {
+    return files_pipeline(paths, nullptr, nullptr, n, k, flags, 0, 0, status_out, totals_out, nullptr, nullptr, counts_out, freq_out, true);
+}
+
 int kf_files_to_device(const char *const *in_paths, int n, int k, uint32_t flags, int threads, size_t batch_bytes, float *d_feat_out,
                        int *status_out, uint64_t *totals_out, double *stage_seconds) {
     if (!d_feat_out) return KF_ERR_ARG;

@@ -1665,7 +1665,13 @@ __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ a
         if (pn >= F1) break;
         pos = pn + 1 + seqlen + 1;   // quality line: seqlen bytes and its '\n'
         after_jump = true;
-        if (pos >= X1) break;        // that record belongs to the next range
+        if (pos >= X1) {
+            // that record belongs to the next range, whose lane finds its start by itself: the jump is validated here
+            // (the skipped quality line must end right before pos, and a header must start there)
+            if (pos < F1 && (arena[pos - 1] != 0x0Au || arena[pos] != (uint8_t)'@')) atomicMin(fq_err, pos);
+            else if (pos == F1 && arena[pos - 1] != 0x0Au) atomicMin(fq_err, pos - 1);
+            break;
+        }
     }
 }
 

@@ -1,7 +1,7 @@
 """ctypes binding of libkfcount.so (include/kfcount.h) -- the host-side mirror of the C ABI.
 
 No CPU fallback lives here: if the shared library is missing or no sm_100 device is visible, compute
-calls raise ``KfError``.  Host-only helpers (vocabulary, .kf formatting, synthetic inputs) work without
+calls raise ``KfError``.  Host-only helpers (vocabulary, .kf formatting and parsing) work without
 a GPU because they are plain C++ inside the same library.
 """
 from __future__ import annotations
@@ -97,15 +97,6 @@ def _load():
     L.kf_parse_kf.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.kf_parse_kf.restype = ctypes.c_int64
-    L.kf_synth_fasta.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
-                                 ctypes.c_size_t]
-    L.kf_synth_fasta.restype = ctypes.c_int64
-    L.kf_synth_fasta_ex.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
-                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
-    L.kf_synth_fasta_ex.restype = ctypes.c_int64
-    L.kf_synth_fastq.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
-                                 ctypes.c_void_p, ctypes.c_size_t]
-    L.kf_synth_fastq.restype = ctypes.c_int64
     _LIB = L
     return L
 
@@ -132,6 +123,14 @@ def init(device: Optional[int] = None) -> int:
     _check(_load().kf_init(device), "kf_init(%d)" % device)
     _INIT_DEVICE = device
     return device
+
+
+def shutdown() -> None:
+    """Frees every device and pinned allocation of the library; ``init`` may be called again afterwards."""
+    global _INIT_DEVICE
+    if _INIT_DEVICE is not None:
+        _check(_load().kf_shutdown(), "kf_shutdown")
+        _INIT_DEVICE = None
 
 
 def _require_init():
@@ -251,7 +250,9 @@ class DeviceArena:
         self.formats = np.array([a[0] if a.size else 0 for a in arrs], dtype=np.uint8)
         self.tensor = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
         for a, off in zip(arrs, self.offsets):
-            if a.size:
+            # (a file the library rejects -- first byte neither '>' nor '@' -- is left as NUL bytes: a preceding file
+            #  that ends without a newline exactly on a 512-byte boundary must not run on into it)
+            if a.size and a[0] in (0x3E, 0x40):
                 src = torch.from_numpy(a) if a.flags.writeable else torch.frombuffer(memoryview(a), dtype=torch.uint8)
                 self.tensor[int(off): int(off) + a.size].copy_(src, non_blocking=True)
         torch.cuda.synchronize(self.device)
@@ -462,35 +463,3 @@ def parse_kf(text: bytes, V: int, want_rows: bool = True, want_feat: bool = Fals
         raise KfError(m if m < 0 else -5, "kf_parse_kf")
     labels = [text[int(o): int(o) + int(l)].decode() for o, l in zip(off, ln)]
     return labels, rows, feat
-
-
-# ---- synthetic inputs --------------------------------------------------------------------------------------
-def synth_fasta(seed: int, genome_id: int, n_bases: int, line_width: int = 80, out: Optional[np.ndarray] = None,
-                max_contigs: int = 50, n_runs: int = 10):
-    L = _load()
-    size = L.kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, max_contigs, n_runs, None, 0)
-    if size < 0:
-        raise KfError(int(size), "kf_synth_fasta")
-    if out is None:
-        out = np.empty(size, dtype=np.uint8)
-    n = L.kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, max_contigs, n_runs, out.ctypes.data, out.size)
-    if n < 0:
-        raise KfError(int(n), "kf_synth_fasta")
-    return out[:n]
-
-
-def synth_fasta_size(seed: int, genome_id: int, n_bases: int, line_width: int = 80, max_contigs: int = 50,
-                     n_runs: int = 10) -> int:
-    return int(_load().kf_synth_fasta_ex(seed, genome_id, n_bases, line_width, max_contigs, n_runs, None, 0))
-
-
-def synth_fastq(seed: int, sample_id: int, genome_len: int, n_reads: int, read_len: int = 150):
-    L = _load()
-    size = L.kf_synth_fastq(seed, sample_id, genome_len, n_reads, read_len, None, 0)
-    if size < 0:
-        raise KfError(int(size), "kf_synth_fastq")
-    out = np.empty(size, dtype=np.uint8)
-    n = L.kf_synth_fastq(seed, sample_id, genome_len, n_reads, read_len, out.ctypes.data, out.size)
-    if n < 0:
-        raise KfError(int(n), "kf_synth_fastq")
-    return out[:n]

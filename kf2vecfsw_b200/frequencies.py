@@ -31,20 +31,6 @@ def list_inputs(input_dir: str) -> Tuple[List[str], List[str]]:
     return files_names, samples_names
 
 
-def _batches(paths: List[str]) -> List[List[int]]:
-    out, cur, cur_bytes = [], [], 0
-    for i, p in enumerate(paths):
-        sz = os.path.getsize(p)
-        if cur and cur_bytes + sz > BATCH_BYTES:
-            out.append(cur)
-            cur, cur_bytes = [], 0
-        cur.append(i)
-        cur_bytes += sz
-    if cur:
-        out.append(cur)
-    return out
-
-
 def get_frequencies(args) -> None:
     """Reference: kf2vec/main.py:250-373."""
     print('\n==> Starting k-mer counting for {}\n'.format(args.input_dir))
@@ -59,7 +45,6 @@ def get_frequencies(args) -> None:
     k = getattr(args, 'k', DEFAULT_K)
     pseudocount = bool(getattr(args, 'pseudocount', False))
     raw_cnt = bool(getattr(args, 'raw_cnt', False))
-    # args.p (jellyfish -t) has no meaning here: the GPU path is not thread-parallel on the host.
 
     files_names, samples_names = list_inputs(args.input_dir)
     paths = [os.path.join(args.input_dir, f) for f in files_names]
@@ -72,6 +57,8 @@ def get_frequencies(args) -> None:
     threads = int(getattr(args, 'p', 0) or 0)
     status, totals, _ = engine.files_to_kf(paths, outs, [str(s) for s in samples_names], k=k, pseudocount=pseudocount,
                                            raw_cnt=raw_cnt, threads=threads, batch_bytes=BATCH_BYTES)
+    # The reference prints these lines while it works through the files (main.py:333,341); the files are counted in one
+    # pipelined call here, so the same lines, in the same order, follow it.
     for i in range(len(paths)):
         if status[i] != 0:
             # The reference ignores jellyfish's exit code and then dies with IndexError at main.py:315;

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import kf_oracle as o
+import kfsynth
 from kf2vecfsw_b200 import build as kfbuild
 from kf2vecfsw_b200 import engine
 
@@ -85,11 +86,11 @@ def test_write_kf(tmp_path):
 
 
 def test_synth_fasta_is_deterministic_and_well_formed():
-    a = engine.synth_fasta(1234, 7, 200000)
-    b = engine.synth_fasta(1234, 7, 200000)
-    c = engine.synth_fasta(1234, 8, 200000)
+    a = kfsynth.synth_fasta(1234, 7, 200000)
+    b = kfsynth.synth_fasta(1234, 7, 200000)
+    c = kfsynth.synth_fasta(1234, 8, 200000)
     assert a.tobytes() == b.tobytes() and a.tobytes() != c.tobytes()
-    assert a.size == engine.synth_fasta_size(1234, 7, 200000)
+    assert a.size == kfsynth.synth_fasta_size(1234, 7, 200000)
     recs = o.fasta_records(a.tobytes())
     assert 1 <= len(recs) <= 50
     seq = b"".join(s for _, s in recs)
@@ -100,7 +101,7 @@ def test_synth_fasta_is_deterministic_and_well_formed():
 
 
 def test_synth_fastq_is_four_line_and_hostile():
-    fq = engine.synth_fastq(99, 3, 50000, 2000, 150).tobytes()
+    fq = kfsynth.synth_fastq(99, 3, 50000, 2000, 150).tobytes()
     lines = fq.split(b"\n")
     assert lines[-1] == b"" and (len(lines) - 1) == 4 * 2000
     assert all(l.startswith(b"@g00003.") for l in lines[0:-1:4])

@@ -3,8 +3,10 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from kf2vecfsw_b200 import engine, chunks
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 engine.init(0)
-g = [engine.synth_fasta(20261018, i, 5_000_000).tobytes() for i in range(6)]
+g = [kfsynth.synth_fasta(20261018, i, 5_000_000).tobytes() for i in range(6)]
 for i, data in enumerate(g):
     t0 = time.perf_counter()
     seq, offs, lens, labels = chunks.plan_genome("g%d" % i, data)

@@ -3,12 +3,14 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from kf2vecfsw_b200 import engine
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 from concurrent.futures import ThreadPoolExecutor
 engine.init(0)
 n_samples = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 with ThreadPoolExecutor(8) as ex:
-    bufs = list(ex.map(lambda i: engine.synth_fastq(20261018, i, 5_000_000, n_reads, 150), range(n_samples)))
+    bufs = list(ex.map(lambda i: kfsynth.synth_fastq(20261018, i, 5_000_000, n_reads, 150), range(n_samples)))
 arena = engine.DeviceArena(bufs)
 for k in (7, 9):
     V = engine.vocab_size(k)
@@ -26,7 +28,7 @@ for k in (7, 9):
 del arena
 # chunked-genome mode: all 10-kbp windows of synthetic genomes
 from kf2vecfsw_b200 import chunks
-g = [engine.synth_fasta(20261018, i, 5_000_000).tobytes() for i in range(4)]
+g = [kfsynth.synth_fasta(20261018, i, 5_000_000).tobytes() for i in range(4)]
 t0 = time.perf_counter()
 nwin = 0
 for i, data in enumerate(g):

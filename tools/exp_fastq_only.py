@@ -2,10 +2,12 @@ import sys, os
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from kf2vecfsw_b200 import engine
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 from concurrent.futures import ThreadPoolExecutor
 engine.init(0)
 with ThreadPoolExecutor(8) as ex:
-    bufs = list(ex.map(lambda i: engine.synth_fastq(20261018, i, 5_000_000, 1_000_000, 150), range(8)))
+    bufs = list(ex.map(lambda i: kfsynth.synth_fastq(20261018, i, 5_000_000, 1_000_000, 150), range(8)))
 arena = engine.DeviceArena(bufs)
 counts = torch.empty((8, 8192), dtype=torch.int64, device="cuda")
 ms = []

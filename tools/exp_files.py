@@ -5,6 +5,8 @@ import json, os, shutil, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from concurrent.futures import ThreadPoolExecutor
 from kf2vecfsw_b200 import engine
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 400
 NB = 5_000_000
 engine.init(0)
@@ -13,7 +15,7 @@ ind, outd = os.path.join(root, "in"), os.path.join(root, "out")
 os.makedirs(ind); os.makedirs(outd)
 def gen(i):
     p = os.path.join(ind, "g%05d.fna" % i)
-    engine.synth_fasta(20261018, i, NB).tofile(p)
+    kfsynth.synth_fasta(20261018, i, NB).tofile(p)
     return p
 threads = len(os.sched_getaffinity(0))
 with ThreadPoolExecutor(threads) as ex:

@@ -3,12 +3,14 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from kf2vecfsw_b200 import engine
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 from concurrent.futures import ThreadPoolExecutor
 engine.init(0)
 V = 8192
 def run(tag, n, bases, mc, nr):
     with ThreadPoolExecutor(16) as ex:
-        bufs = list(ex.map(lambda i: engine.synth_fasta(1, i, bases, 80, None, mc, nr), range(n)))
+        bufs = list(ex.map(lambda i: kfsynth.synth_fasta(1, i, bases, 80, None, mc, nr), range(n)))
     arena = engine.DeviceArena(bufs)
     counts = torch.empty((n, V), dtype=torch.int64, device="cuda")
     ms = []

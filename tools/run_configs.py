@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np, torch
 from concurrent.futures import ThreadPoolExecutor
 from kf2vecfsw_b200 import engine, chunks
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 import c_oracle
 
 engine.init(0)
@@ -44,7 +46,7 @@ def emit(**kw):
 # ---- config 4: FASTQ query reads (150 bp, 30x of 5 Mbp, N-containing), 8 samples ----
 n_samples, n_reads = 8, 1_000_000
 with ThreadPoolExecutor(8) as ex:
-    fq = list(ex.map(lambda i: engine.synth_fastq(SEED, i, 5_000_000, n_reads, 150), range(n_samples)))
+    fq = list(ex.map(lambda i: kfsynth.synth_fastq(SEED, i, 5_000_000, n_reads, 150), range(n_samples)))
 arena = engine.DeviceArena(fq)
 bases = n_samples * n_reads * 150
 for k in (7,):
@@ -61,7 +63,7 @@ del arena
 # ---- config 5: large-k sweep on 5 Mbp genomes (whole-genome mode) ----
 G = 592   # 4 x 148: (file, partition) work items fill every SM the same number of times
 with ThreadPoolExecutor(16) as ex:
-    fa = list(ex.map(lambda i: engine.synth_fasta(SEED, i, 5_000_000), range(G)))
+    fa = list(ex.map(lambda i: kfsynth.synth_fasta(SEED, i, 5_000_000), range(G)))
 for k in (7, 8, 9, 10, 12):
     n = G if k <= 10 else 24
     arena = engine.DeviceArena(fa[:n])

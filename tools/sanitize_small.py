@@ -7,12 +7,14 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import numpy as np
 from kf2vecfsw_b200 import engine
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import kfsynth
 from fuzzgen import rand_fasta, rand_fasta_grid, rand_fastq
 import kf_oracle as o
 engine.init(0)
 rng = random.Random(5)
-bufs = [engine.synth_fasta(1, 0, 600_000).tobytes(), rand_fasta(rng), rand_fasta_grid(rng), rand_fastq(rng),
-        engine.synth_fastq(1, 0, 100_000, 2_000, 150).tobytes(), engine.synth_fasta(1, 1, 300_000).tobytes()]
+bufs = [kfsynth.synth_fasta(1, 0, 600_000).tobytes(), rand_fasta(rng), rand_fasta_grid(rng), rand_fastq(rng),
+        kfsynth.synth_fastq(1, 0, 100_000, 2_000, 150).tobytes(), kfsynth.synth_fasta(1, 1, 300_000).tobytes()]
 for k in (7, 8, 9, 10):
     for kw in ({}, {"part_all": True}):
         counts, freq, totals, status = engine.count_buffers(bufs, k=k, **kw)

@@ -1,5 +1,5 @@
 // ubench.cu -- developer micro-benchmarks for the counting kernel's design choices (not product code).
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I include -I kf2vecfsw_b200/csrc tools/ubench.cu -o tools/ubench
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I include -I kf2vecfsw_b200/csrc -I tools tools/ubench.cu kf2vecfsw_b200/csrc/kf_host.cpp tools/kf_synth.cpp -o tools/ubench
 // Run on a B200: tools/ubench [arena_MiB]
 //
 // Every variant streams the same synthetic 80-column FASTA arena (one record) and reports GB/s of file
@@ -7,6 +7,7 @@
 #define KF_PIECE_TIMING 1
 #include "kf_kernels.cuh"
 #include "kfcount.h"
+#include "kf_synth.h"
 #include <thread>
 
 #include <cstdio>
