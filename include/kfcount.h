@@ -36,6 +36,7 @@ extern "C" {
 #define KF_ERR_NOMEM (-7)        /* host or device allocation failed */
 #define KF_ERR_LAYOUT (-8)       /* device arena violates the layout contract of kf_count_device */
 #define KF_ERR_EMPTY (-9)        /* zero-length input (jellyfish fails on it; the reference then crashes) */
+#define KF_ERR_UNSUPPORTED (-10)  /* valid input that this entry point does not take (FASTQ in the sparse path) */
 
 /* flags (bit set) */
 #define KF_FLAG_PSEUDOCOUNT 1u   /* main.py:332-334  counts += 0.5 before normalising           */
@@ -47,6 +48,8 @@ extern "C" {
 /* limits */
 #define KF_MIN_K 1
 #define KF_MAX_K 12              /* dense canonical output up to k=12 (8,390,656 columns)        */
+#define KF_SPARSE_MIN_K 6        /* sparse (code, count) output: kf_sparse_*                     */
+#define KF_SPARSE_MAX_K 31       /* 2-bit codes in 64 bits; the reference's -k goes to 31 (main.py:81-82) */
 #define KF_MAX_K_SMEM 7          /* 4^k u32 bins privatised in shared memory up to here          */
 #define KF_CHUNK 512             /* arena alignment unit: one warp-load of 32 x 16 bytes         */
 #define KF_TAIL_PAD 4096         /* NUL bytes required after the last file of a device arena     */
@@ -140,6 +143,32 @@ int kf_last_count_kernel_ms(float *ms);
  * 64; returns how many were written.  Waits for those calls: meant to be read AFTER a timed loop, so that the loop itself
  * runs without host synchronisation (bench.py: roofline.achieved over the timed region). */
 int kf_count_kernel_ms_history(float *ms_out, int n);
+
+/* ---- sparse counting for large k: observed canonical k-mers only (get_kmers, main.py:135-172; jellyfish -k up to 31) ---- */
+/* Replaces `jellyfish count -m k -s 100M -C` + `jellyfish dump -c` (main.py:135-145, :308-319) where a dense row of 4^k bins
+ * is not sensible: per file, the OBSERVED canonical k-mers (2-bit codes A0 C1 G2 T3, first base most significant -- the
+ * order of kf_vocab_codes) with their counts, ascending by code (Jellyfish lists them in hash order).  Sort-and-run-length
+ * on the device: radix partition of the canonical codes by their leading bits, per-bucket sort in shared memory, run
+ * lengths.  KF_SPARSE_MIN_K <= k <= KF_SPARSE_MAX_K.  FASTA inputs; a FASTQ input gets status KF_ERR_UNSUPPORTED (use the
+ * dense entry points up to k = 12).  The result stays in device memory until the next kf_sparse_count* call or
+ * kf_sparse_release; n_distinct_out [n] = entries per file, totals_out [n] = valid k-mers per file (either may be NULL). */
+int kf_sparse_count(const uint8_t *const *bufs, const size_t *lens, int n, int k, uint64_t *n_distinct_out,
+                    uint64_t *totals_out, int *status_out);
+/* Same on a device-resident arena (layout contract of kf_count_device); enqueued on `stream` and synchronised before
+ * returning (the output size is only known then).  status_out may be NULL. */
+int kf_sparse_count_device(const uint8_t *d_arena, size_t arena_bytes, const uint64_t *offsets, const uint64_t *lens,
+                           const uint8_t *formats, int n, int k, uint64_t *n_distinct_out, uint64_t *totals_out,
+                           int *status_out, void *stream);
+/* Entries of the last result over all files, and the copy to host arrays: codes_out / counts_out [total] hold the files'
+ * entries back to back in file order, row_off_out [n + 1] where each file's begin (any may be NULL). */
+int64_t kf_sparse_total_entries(void);
+int kf_sparse_fetch(uint64_t *codes_out, uint32_t *counts_out, uint64_t *row_off_out);
+/* Device view of the last result: it is held as one chunk per internal sub-batch of files [file0, file1), whose entries
+ * are the global entries [first_entry, first_entry + n_entries). */
+int kf_sparse_chunk_count(void);
+int kf_sparse_chunk(int i, const uint64_t **d_codes, const uint32_t **d_counts, uint64_t *n_entries, uint64_t *first_entry,
+                    int *file0, int *file1);
+int kf_sparse_release(void);
 
 /* ---- .kf writer: main.py:344-357 --------------------------------------------------------------- */
 /* Formats one row exactly as pandas `astype(str)` + ",".join does (Python repr of float64: shortest

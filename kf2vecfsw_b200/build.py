@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "csrc", "kf_api.cu"), os.path.join(HERE, "csrc", "kf_host.cpp")]
-HEADERS = [os.path.join(HERE, "csrc", "kf_kernels.cuh"), os.path.join(ROOT, "include", "kfcount.h")]
+HEADERS = [os.path.join(HERE, "csrc", "kf_kernels.cuh"), os.path.join(HERE, "csrc", "kf_sparse.cuh"),
+           os.path.join(HERE, "csrc", "kf_sparse_host.inc"), os.path.join(ROOT, "include", "kfcount.h")]
 OUT = os.path.join(HERE, "libkfcount.so")
 
 NVCC_FLAGS = [

@@ -2,6 +2,7 @@
 // staging.  See include/kfcount.h for the contract and the reference lines each entry point replaces.
 #include "kfcount.h"
 #include "kf_kernels.cuh"
+#include "kf_sparse.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -109,6 +110,7 @@ struct Ctx {
 
 Ctx g;
 std::mutex g_mu;
+void sparse_free_all();   // kf_sparse_host.inc
 
 #define CK(call)                                                                                  \
     do {                                                                                          \
@@ -145,6 +147,30 @@ int ensure_pinned(T *&ptr, size_t &cap, size_t need_bytes) {
         return KF_ERR_NOMEM;
     }
     cap = need_bytes;
+    return KF_OK;
+}
+
+// Host tables -> device, stream-ordered: packed into a pinned staging block (two used in turn) and copied with
+// cudaMemcpyAsync on the launching stream, so the kernels queued behind them on that stream see them.  (A blocking
+// cudaMemcpy from pageable memory may return before its DMA has landed and is not ordered against non-blocking streams.)
+struct Up { void *dst; const void *src; size_t bytes; };
+int upload_tables(const std::vector<Up> &ups, cudaStream_t s) {
+    size_t total = 0;
+    for (auto &u : ups) total += (u.bytes + 255) & ~(size_t)255;
+    const int sl = g.stage_next;
+    g.stage_next ^= 1;
+    if (g.stage_pending[sl]) { CK(cudaEventSynchronize(g.ev_stage[sl])); g.stage_pending[sl] = false; }
+    int rc;
+    if (total + 256 > g.h_stage_cap[sl] &&
+        (rc = ensure_pinned(g.h_stage[sl], g.h_stage_cap[sl], std::max<size_t>(total + total / 2 + 256, (size_t)1 << 20))) != KF_OK) return rc;
+    size_t o = 0;
+    for (auto &u : ups) {
+        memcpy(g.h_stage[sl] + o, u.src, u.bytes);
+        CK(cudaMemcpyAsync(u.dst, g.h_stage[sl] + o, u.bytes, cudaMemcpyHostToDevice, s));
+        o += (u.bytes + 255) & ~(size_t)255;
+    }
+    CK(cudaEventRecord(g.ev_stage[sl], s));
+    g.stage_pending[sl] = true;
     return KF_OK;
 }
 
@@ -456,7 +482,6 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
         // streams).  A previous call's kernels on ANOTHER stream may still be reading the old tables: wait for them on
         // the device, not on the host. ----
         if (g.last_stream_valid && g.last_stream != s) CK(cudaStreamWaitEvent(s, g.ev_done, 0));
-        struct Up { void *dst; const void *src; size_t bytes; };
         std::vector<Up> ups;
         auto add = [&](void *dst, const void *src, size_t bytes) { if (bytes) ups.push_back({dst, src, bytes}); };
         add(g.d_tiles, tiles.data(), tiles.size() * sizeof(Tile));
@@ -477,21 +502,7 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             add(g.d_file_row, file_row.data(), file_row.size() * sizeof(uint32_t));
             add(g.d_cta_first_rank, cta_first_rank.data(), cta_first_rank.size() * sizeof(uint32_t));
         }
-        size_t total = 0;
-        for (auto &u : ups) total += (u.bytes + 255) & ~(size_t)255;
-        const int sl = g.stage_next;
-        g.stage_next ^= 1;
-        if (g.stage_pending[sl]) { CK(cudaEventSynchronize(g.ev_stage[sl])); g.stage_pending[sl] = false; }
-        if (total + 256 > g.h_stage_cap[sl] &&
-            (rc = ensure_pinned(g.h_stage[sl], g.h_stage_cap[sl], std::max<size_t>(total + total / 2 + 256, (size_t)1 << 20))) != KF_OK) return rc;
-        size_t o = 0;
-        for (auto &u : ups) {
-            memcpy(g.h_stage[sl] + o, u.src, u.bytes);
-            CK(cudaMemcpyAsync(u.dst, g.h_stage[sl] + o, u.bytes, cudaMemcpyHostToDevice, s));
-            o += (u.bytes + 255) & ~(size_t)255;
-        }
-        CK(cudaEventRecord(g.ev_stage[sl], s));
-        g.stage_pending[sl] = true;
+        if ((rc = upload_tables(ups, s)) != KF_OK) return rc;
         g.pc_fq_ntiles = (int)fq_tiles.size();
         g.pc_fq_nfiles = (int)fq_ftb.size() - 1;
         g.pc_items = (int)n_items_a;
@@ -675,6 +686,7 @@ int kf_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g.device < 0) return KF_OK;
     cudaDeviceSynchronize();
+    sparse_free_all();
     void *dev_ptrs[] = {g.d_fwd, g.d_tiles, g.d_cta_begin, g.d_arena, g.d_counts, g.d_freq, g.d_totals, g.d_seq, g.d_win_off, g.d_win_len,
                         g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_err, g.d_file_off, g.d_file_len, g.d_formats, g.d_file_P, g.d_file_row,
                         g.d_cta_first_rank, g.d_width_counts, g.d_file_t0, g.d_items, g.d_item_counter, g.d_stream, g.d_fold_tot};
@@ -1142,3 +1154,5 @@ int kf_files_to_device(const char *const *in_paths, int n, int k, uint32_t flags
 }
 
 }  // extern "C"
+
+#include "kf_sparse_host.inc"

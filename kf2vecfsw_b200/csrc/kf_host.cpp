@@ -104,6 +104,7 @@ const char *kf_strerror(int code) {
         case KF_ERR_NOMEM: return "out of memory";
         case KF_ERR_LAYOUT: return "device arena violates the layout contract";
         case KF_ERR_EMPTY: return "empty input";
+        case KF_ERR_UNSUPPORTED: return "input format not supported by this entry point";
         default: return "unknown error";
     }
 }

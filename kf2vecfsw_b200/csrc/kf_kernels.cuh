@@ -249,6 +249,9 @@ template <class S> __device__ __forceinline__ S sink_slow(const S &s) { return s
 // A sink may want to see EVERY lane of every chunk (record(chunk * 32 + lane, fast, hi, lo, n): fast = the lane's k-mers
 // go through window()/operator() of the fast path, otherwise through the rare paths or nowhere).
 template <class S> struct sink_records_lanes { static constexpr bool value = false; };
+// A sink may bring its own byte walker for the rare paths (walk(src, p0, p1, in_hdr, at_ls): same contract as
+// fasta_walk_lane) -- the sparse path's k-mers are canonical 64-bit codes with a run-time k.
+template <class S> struct sink_walks_itself { static constexpr bool value = false; };
 template <int K, bool FORCE_WALKER, int PF, class Sink, class Src>
 __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, uint32_t c1, uint32_t file_c0, Sink &sink,
                                                     uint64_t own_lo = 0, uint64_t own_hi = ~0ull,
@@ -302,9 +305,11 @@ __device__ __forceinline__ void fasta_process_range(const Src src, uint32_t c0, 
                         if (cur.n == 16) sink(kmer_off_at<K>(hi, lo, 15));
                     }
                 } else if (pb < own_lo) {
-                    fasta_walk_lane<K>(src, own_lo, pb + 16 < own_hi ? pb + 16 : own_hi, false, true, emit);
+                    if constexpr (sink_walks_itself<Sink>::value) sink.walk(src, own_lo, pb + 16 < own_hi ? pb + 16 : own_hi, false, true);
+                    else fasta_walk_lane<K>(src, own_lo, pb + 16 < own_hi ? pb + 16 : own_hi, false, true, emit);
                 } else {
-                    fasta_walk_lane<K>(src, pb, pb + 16 < own_hi ? pb + 16 : own_hi, (st & 1u) != 0, (st & 2u) != 0, emit);
+                    if constexpr (sink_walks_itself<Sink>::value) sink.walk(src, pb, pb + 16 < own_hi ? pb + 16 : own_hi, (st & 1u) != 0, (st & 2u) != 0);
+                    else fasta_walk_lane<K>(src, pb, pb + 16 < own_hi ? pb + 16 : own_hi, (st & 1u) != 0, (st & 2u) != 0, emit);
                 }
                 carry_hdr = (st & 4u) != 0;
                 cur = nxt;

@@ -1,0 +1,361 @@
+// kf_sparse.cuh -- sparse (sort-and-run-length) k-mer counting for large k (sm_100a).
+//
+// Replaces `jellyfish count -m k -C` + `jellyfish dump -c` (kf2vec/main.py:135-145, get_kmers; main.py:308-319) where a
+// dense row of 4^k bins is no longer sensible (k = 12: 64 MB per file; k up to 31 is what the reference's -k accepts,
+// main.py:81-82): the result is the list of OBSERVED canonical k-mers of every file with their counts, ascending by code
+// (A0 C1 G2 T3, first base most significant -- the vocabulary order of the dense path), which is what Jellyfish dumps
+// (in hash order).
+//
+// Pipeline over one batch of files (MSD radix partition by the code's leading bits, then per-bucket sort + run lengths):
+//   1. sparse_extract_kernel<0>  text -> canonical codes -> per-(file, bucket) histogram (shared memory, flushed per file)
+//   2. sparse_scan_buckets_kernel exclusive scan per file: where every bucket's keys go inside the file's key region
+//   3. sparse_extract_kernel<1>  the same parse again; every code is stored in its bucket (global cursor per bucket)
+//   4. sparse_sort_kernel        item = (file, run of buckets): each bucket sorted in shared memory (bitonic; in global
+//                                memory in place when it does not fit), distinct codes counted
+//   5. sparse_scan_items_kernel  exclusive scan of the distinct counts: where every item's output goes
+//   6. sparse_emit_kernel        run-length encode the item's (now globally sorted) key range into (code, count)
+// The parser is the dense path's (fasta_process_range): a k-mer is owned by the 16-byte lane that holds its first base,
+// so both passes enumerate exactly the same k-mers.  k <= 16: the lane's 32-base window yields forward and
+// reverse-complement codes with two shifts each; k >= 17: every lane runs the canonical byte walker.
+#pragma once
+#include "kf_kernels.cuh"
+
+namespace kf {
+
+constexpr int SP_BUCKET_BITS = 12;                  // leading bits of the 2k-bit canonical code that number the bucket
+constexpr uint32_t SP_BUCKETS = 1u << SP_BUCKET_BITS;
+constexpr int SP_MIN_K = 6;                         // (the code must have at least SP_BUCKET_BITS bits)
+constexpr int SP_MAX_K = 31;
+
+__device__ __forceinline__ uint64_t digit_reverse64(uint64_t x) {   // reverse the 32 two-bit digits
+    x = __brevll(x);
+    return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+}
+
+// What a counted canonical code does: MODE 0 bumps the bucket histogram in shared memory, MODE 1 stores the code in its
+// bucket of the file's key region.
+template <int MODE, typename KT>
+struct SparseEmit {
+    uint32_t *hist;       // MODE 0: shared, SP_BUCKETS bins
+    uint32_t *cursor;     // MODE 1: global, SP_BUCKETS cursors of the current file (offsets inside its key region)
+    KT *keys;             // MODE 1: the current file's key region
+    uint32_t shift;       // 2k - SP_BUCKET_BITS
+    __device__ __forceinline__ void operator()(uint64_t canon) const {
+        const uint32_t b = (uint32_t)(canon >> shift);
+        if (MODE == 0) atomicAdd(hist + b, 1u);
+        else keys[atomicAdd(cursor + b, 1u)] = (KT)canon;
+    }
+};
+
+// Canonical byte walker, run-time k (1..31): counts every k-mer whose first base lies in [p0, p1); (in_hdr, at_ls) is the
+// line state at p0.  Same contract as fasta_walk_lane.  Codes in the sorted alphabet A0 C1 G2 T3.
+template <class Src, class Emit>
+__device__ KF_NOINLINE void fasta_walk_lane_canon(const Src src, uint64_t p0, uint64_t p1, bool in_hdr, bool at_ls, int k, Emit emit) {
+    const uint64_t mask = (1ull << (2 * k)) - 1ull;
+    const int rsh = 2 * (k - 1);
+    uint64_t F = 0, R = 0;
+    int run = 0, owned = 0;
+    uint64_t p = p0;
+    for (;;) {
+        const bool own = p < p1;
+        if (!own && (owned == 0 || run - k + 1 >= owned)) break;
+        const uint32_t c = src.byte(p);
+        p++;
+        if (in_hdr) {
+            if (c == 0x0Au) { in_hdr = false; at_ls = true; }
+            run = 0; owned = 0;
+            continue;
+        }
+        if (c == 0x0Au) { at_ls = true; continue; }
+        if (at_ls && c == (uint32_t)'>') { in_hdr = true; at_ls = false; run = 0; owned = 0; continue; }
+        at_ls = false;
+        if (!is_base(c)) { run = 0; owned = 0; continue; }
+        const uint32_t gcode = (c >> 1) & 3u;
+        const uint64_t sc = (uint64_t)(gcode ^ (gcode >> 1));   // A0 C1 T2 G3 -> A0 C1 G2 T3
+        F = ((F << 2) | sc) & mask;
+        R = (R >> 2) | ((3ull - sc) << rsh);
+        run++;
+        if (own) owned++;
+        if (run >= k && run - k < owned) emit(F < R ? F : R);
+    }
+}
+
+template <int MODE, typename KT>
+struct SparseSink {
+    SparseEmit<MODE, KT> e;
+    int k;
+    // fast lanes (k <= 16): the k-mers that start at bases 0..n-1 of the 32-base window hi:lo (gray codes, first base in
+    // hi bits 31:30)
+    __device__ __forceinline__ void window(uint32_t hi, uint32_t lo, uint32_t n) const {
+        const uint32_t hs = hi ^ ((hi >> 1) & 0x55555555u), ls = lo ^ ((lo >> 1) & 0x55555555u);   // sorted alphabet
+        const uint64_t w = ((uint64_t)hs << 32) | ls;
+        const uint64_t rcw = digit_reverse64(~w);       // digit d (from the top) = complement of base 31 - d
+        const uint64_t mask = (1ull << (2 * k)) - 1ull;
+        const int s0 = 64 - 2 * k;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (j < 15 || n == 16) {
+                const uint64_t F = (w >> (s0 - 2 * j)) & mask;
+                const uint64_t R = (rcw >> (2 * j)) & mask;
+                e(F < R ? F : R);
+            }
+        }
+    }
+    template <class Src>
+    __device__ __forceinline__ void walk(const Src src, uint64_t p0, uint64_t p1, bool in_hdr, bool at_ls) const {
+        fasta_walk_lane_canon(src, p0, p1, in_hdr, at_ls, k, e);
+    }
+    __device__ __forceinline__ void operator()(uint32_t) const {}   // (never reached: walk() takes the rare paths)
+};
+template <int MODE, typename KT> struct sink_takes_window<SparseSink<MODE, KT>> { static constexpr bool value = true; };
+template <int MODE, typename KT> struct sink_walks_itself<SparseSink<MODE, KT>> { static constexpr bool value = true; };
+
+// Passes 1 and 3.  Persistent: CTA b owns tiles [cta_begin[b], cta_begin[b+1]) of the FASTA plan (dense path's tiles).
+// file ids in the tiles are batch-global; file_base = first file of this sub-batch; tables below are relative to it.
+//   MODE 0: g_hist [nf][SP_BUCKETS] += the CTA's shared-memory histogram, at every file change
+//   MODE 1: keys + kbase[f] = file f's key region, g_cursor [nf][SP_BUCKETS] = next free slot of every bucket
+template <int MODE, typename KT, bool WALK_ALL, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
+sparse_extract_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin, int k,
+                      uint32_t file_base, uint32_t *__restrict__ g_hist, uint32_t *__restrict__ g_cursor, KT *__restrict__ keys,
+                      const uint64_t *__restrict__ kbase) {
+    __shared__ uint32_t hist[MODE == 0 ? SP_BUCKETS : 1];
+    constexpr int NWARPS = THREADS / 32;
+    const int warp = threadIdx.x >> 5;
+    if (MODE == 0) {
+        for (uint32_t i = threadIdx.x; i < SP_BUCKETS; i += THREADS) hist[i] = 0;
+        __syncthreads();
+    }
+    int cur_file = -1;
+    auto flush = [&](int file) {
+        if (MODE != 0) return;
+        __syncthreads();
+        uint32_t *gh = g_hist + (size_t)(file - (int)file_base) * SP_BUCKETS;
+        for (uint32_t i = threadIdx.x; i < SP_BUCKETS; i += THREADS) {
+            const uint32_t v = hist[i];
+            if (v) { atomicAdd(gh + i, v); hist[i] = 0; }
+        }
+        __syncthreads();
+    };
+    SparseSink<MODE, KT> sink;
+    sink.k = k;
+    sink.e.hist = hist;
+    sink.e.shift = (uint32_t)(2 * k - SP_BUCKET_BITS);
+    sink.e.cursor = nullptr;
+    sink.e.keys = nullptr;
+    const int t1 = cta_begin[blockIdx.x + 1];
+    for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
+        const Tile T = tiles[t];
+        if ((int)T.file != cur_file) {
+            if (cur_file >= 0) flush(cur_file);
+            cur_file = (int)T.file;
+            if (MODE == 1) {
+                sink.e.cursor = g_cursor + (size_t)(T.file - file_base) * SP_BUCKETS;
+                sink.e.keys = keys + kbase[T.file - file_base];
+            }
+        }
+        const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
+        const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
+        const uint32_t cend = T.first_chunk + T.n_chunks;
+        const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
+        if (c0 < c1) fasta_process_range<12, WALK_ALL, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, sink);
+    }
+    if (cur_file >= 0) flush(cur_file);
+}
+
+// Pass 2: one CTA per file.  boff [nf][SP_BUCKETS + 1] = exclusive scan of the file's bucket counts (last = total),
+// cursor [nf][SP_BUCKETS] = the same (pass 3 advances it), totals [file_base + f] = the file's valid k-mers.
+__global__ void __launch_bounds__(1024)
+sparse_scan_buckets_kernel(const uint32_t *__restrict__ g_hist, uint32_t *__restrict__ boff, uint32_t *__restrict__ cursor,
+                           unsigned long long *__restrict__ totals, uint32_t file_base) {
+    static_assert(SP_BUCKETS == 4096, "four buckets per thread");
+    __shared__ uint32_t wsum[32];
+    const uint32_t f = blockIdx.x;
+    const uint32_t *h = g_hist + (size_t)f * SP_BUCKETS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4 v = reinterpret_cast<const uint4 *>(h)[threadIdx.x];
+    const uint32_t mine = v.x + v.y + v.z + v.w;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t ex = wsum[warp] + inc - mine;
+    const uint4 o4 = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+    uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
+    bo[4 * threadIdx.x] = o4.x; bo[4 * threadIdx.x + 1] = o4.y; bo[4 * threadIdx.x + 2] = o4.z; bo[4 * threadIdx.x + 3] = o4.w;
+    reinterpret_cast<uint4 *>(cursor + (size_t)f * SP_BUCKETS)[threadIdx.x] = o4;
+    if (threadIdx.x == 1023) {
+        bo[SP_BUCKETS] = ex + mine;
+        if (totals) totals[file_base + f] = (unsigned long long)(ex + mine);
+    }
+}
+
+// ---- bitonic sorting network, all merges ascending (first step of a merge mirrors, the others are strides): with that
+// shape, elements beyond n behave as +infinity without being stored, so any n works in place. ----
+template <typename KT>
+__device__ __forceinline__ void bitonic_sort(KT *a, uint32_t n, uint32_t npad, int tid, int nthreads) {
+    const uint32_t pairs = npad >> 1;
+    for (uint32_t lk = 1; (1u << lk) <= npad; lk++) {          // merge blocks of K2 = 2^lk
+        const uint32_t lh = lk - 1, hmask = (1u << lh) - 1u;
+        for (uint32_t t = (uint32_t)tid; t < pairs; t += (uint32_t)nthreads) {
+            const uint32_t blk = t >> lh, off = t & hmask;
+            const uint32_t i = (blk << lk) + off, j = (blk << lk) + ((1u << lk) - 1u - off);
+            if (j < n) { const KT x = a[i], y = a[j]; if (x > y) { a[i] = y; a[j] = x; } }
+        }
+        __syncthreads();
+        for (int lj = (int)lk - 2; lj >= 0; lj--) {              // strides J = 2^lj
+            const uint32_t jmask = (1u << lj) - 1u;
+            for (uint32_t t = (uint32_t)tid; t < pairs; t += (uint32_t)nthreads) {
+                const uint32_t i = ((t >> lj) << (lj + 1)) + (t & jmask), j = i + (1u << lj);
+                if (j < n) { const KT x = a[i], y = a[j]; if (x > y) { a[i] = y; a[j] = x; } }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Pass 4.  item = blockIdx.x = file * S + segment; the segment's SP_BUCKETS / S buckets are sorted one after the other.
+// nd [item] = number of distinct codes in the item's key range.
+template <typename KT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sparse_sort_kernel(KT *__restrict__ keys, const uint64_t *__restrict__ kbase, const uint32_t *__restrict__ boff, uint32_t S,
+                   uint32_t *__restrict__ nd) {
+    KF_DYN_SMEM(unsigned long long, sp_smem);
+    KT *buf = reinterpret_cast<KT *>(sp_smem);
+    constexpr uint32_t CAP = 65536 / sizeof(KT);
+    __shared__ uint32_t s_heads[THREADS / 32];
+    const uint32_t item = blockIdx.x, f = item / S, seg = item - f * S;
+    const uint32_t per = SP_BUCKETS / S, b0 = seg * per;
+    const uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
+    KT *fk = keys + kbase[f];
+    uint32_t heads = 0;   // per thread
+    for (uint32_t b = b0; b < b0 + per; b++) {
+        const uint32_t s = bo[b], n = bo[b + 1] - s;
+        if (n == 0) continue;
+        KT *gk = fk + s;
+        if (n <= CAP) {
+            uint32_t npad = 32;
+            while (npad < n) npad <<= 1;
+            for (uint32_t i = threadIdx.x; i < npad; i += THREADS) buf[i] = i < n ? gk[i] : (KT)~(KT)0;
+            __syncthreads();
+            if (n > 1) bitonic_sort<KT>(buf, npad, npad, (int)threadIdx.x, THREADS);
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+                const KT x = buf[i];
+                gk[i] = x;
+                heads += (i == 0 || buf[i - 1] != x) ? 1u : 0u;
+            }
+            __syncthreads();
+        } else {
+            // does not fit: the same network on global memory (one CTA: __syncthreads orders its global accesses)
+            uint32_t npad = 1u << (32 - __clz((int)(n - 1)));
+            if (npad < n) npad = 0x80000000u;   // (n > 2^31 cannot happen: a file holds fewer than 2^32 bytes per bucket scan)
+            bitonic_sort<KT>(gk, n, npad, (int)threadIdx.x, THREADS);
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) heads += (i == 0 || gk[i - 1] != gk[i]) ? 1u : 0u;
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) heads += __shfl_xor_sync(FULL, heads, o);
+    if ((threadIdx.x & 31) == 0) s_heads[threadIdx.x >> 5] = heads;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < THREADS / 32; w++) t += s_heads[w];
+        nd[item] = t;
+    }
+}
+
+// Pass 5: one CTA.  ooff [n_items + 1] = exclusive scan of nd (64-bit).
+__global__ void __launch_bounds__(1024)
+sparse_scan_items_kernel(const uint32_t *__restrict__ nd, unsigned long long *__restrict__ ooff, uint32_t n_items) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n_items; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const unsigned long long mine = i < n_items ? nd[i] : 0ull;
+        unsigned long long inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+            wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long base = s_base;
+        if (i < n_items) ooff[i] = base + wsum[warp] + inc - mine;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base = base + wsum[31] + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ooff[n_items] = s_base;
+}
+
+// Pass 6.  The item's key range is sorted (bucket after bucket, and the bucket number is the code's leading bits): its
+// runs of equal codes become (code, count) entries at out_base + ooff[item] ...
+template <typename KT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+sparse_emit_kernel(const KT *__restrict__ keys, const uint64_t *__restrict__ kbase, const uint32_t *__restrict__ boff, uint32_t S,
+                   const unsigned long long *__restrict__ ooff, unsigned long long *__restrict__ codes_out, uint32_t *__restrict__ counts_out) {
+    __shared__ uint32_t s_idx[THREADS];
+    __shared__ unsigned long long s_key[THREADS];
+    __shared__ uint32_t wsum[THREADS / 32];
+    __shared__ uint32_t s_h;
+    const uint32_t item = blockIdx.x, f = item / S, seg = item - f * S;
+    const uint32_t per = SP_BUCKETS / S;
+    const uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
+    const uint32_t r0 = bo[seg * per], r1 = bo[(seg + 1) * per];
+    if (r0 == r1) return;
+    const KT *fk = keys + kbase[f];
+    unsigned long long cur = ooff[item];      // next output slot
+    bool pending = false;                     // an open run: (pend_key, pend_start)
+    unsigned long long pend_key = 0;
+    uint32_t pend_start = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t t0 = r0; t0 < r1; t0 += THREADS) {
+        const uint32_t i = t0 + threadIdx.x;
+        const bool valid = i < r1;
+        const KT key = valid ? fk[i] : (KT)0;
+        const bool head = valid && (i == r0 || fk[i - 1] != key);
+        const unsigned bal = __ballot_sync(FULL, head);
+        if (lane == 0) wsum[warp] = (uint32_t)__popc(bal);
+        __syncthreads();
+        uint32_t before = 0, h = 0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; w++) { const uint32_t c = wsum[w]; if (w < warp) before += c; h += c; }
+        if (head) {
+            const uint32_t pos = before + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            s_idx[pos] = i;
+            s_key[pos] = (unsigned long long)key;
+        }
+        __syncthreads();
+        if (h > 0) {
+            const uint32_t first = s_idx[0];
+            if (pending && threadIdx.x == 0) { codes_out[cur] = pend_key; counts_out[cur] = first - pend_start; }
+            const unsigned long long base = cur + (pending ? 1ull : 0ull);
+            for (uint32_t j = threadIdx.x; j + 1 < h; j += THREADS) { codes_out[base + j] = s_key[j]; counts_out[base + j] = s_idx[j + 1] - s_idx[j]; }
+            cur = base + (h - 1);
+            pending = true;
+            pend_key = s_key[h - 1];
+            pend_start = s_idx[h - 1];
+        }
+        __syncthreads();
+    }
+    if (pending && threadIdx.x == 0) { codes_out[cur] = pend_key; counts_out[cur] = r1 - pend_start; }
+}
+
+}  // namespace kf

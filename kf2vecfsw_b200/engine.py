@@ -20,6 +20,8 @@ KF_TAIL_PAD = 4096
 KF_FLAG_NO_LINEGRID = 8
 KF_FLAG_PART_ALL = 16
 KF_MAX_K = 12
+KF_SPARSE_MIN_K = 6
+KF_SPARSE_MAX_K = 31
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -81,6 +83,15 @@ def _load():
     L.kf_last_file_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_void_p]
     L.kf_last_launch_count.restype = ctypes.c_int
+    L.kf_sparse_count.argtypes = [c_u8pp, ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_sparse_count_device.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p]
+    L.kf_sparse_total_entries.restype = ctypes.c_int64
+    L.kf_sparse_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_sparse_chunk.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p]
     L.kf_set_sm_limit.argtypes = [ctypes.c_int]
     L.kf_set_sm_limit.restype = ctypes.c_int
     L.kf_last_count_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float)]
@@ -228,6 +239,81 @@ def count_windows(seq, win_off, win_len, k: int = 7, pseudocount: bool = False, 
                                     freq.ctypes.data if freq is not None else None, totals.ctypes.data),
            "kf_count_windows")
     return counts, freq, totals
+
+
+# ---- sparse counting (large k): observed canonical k-mers only -------------------------------------------
+def _sparse_fetch(n: int):
+    L = _load()
+    total = int(L.kf_sparse_total_entries())
+    codes = np.empty(total, dtype=np.uint64)
+    counts = np.empty(total, dtype=np.uint32)
+    row_off = np.zeros(n + 1, dtype=np.uint64)
+    _check(L.kf_sparse_fetch(codes.ctypes.data, counts.ctypes.data, row_off.ctypes.data), "kf_sparse_fetch")
+    return codes, counts, row_off
+
+
+def sparse_count(bufs: Sequence, k: int, fetch: bool = True):
+    """Sort-and-run-length counting of host buffers (FASTA), KF_SPARSE_MIN_K <= k <= KF_SPARSE_MAX_K: what
+    ``jellyfish count -C`` + ``jellyfish dump -c`` list (main.py:135-145), ascending by 2-bit code (A0 C1 G2 T3, first
+    base most significant).  Returns (codes u64 [E], counts u32 [E], row_off u64 [n+1], totals u64 [n], status i32 [n]);
+    file i's entries are [row_off[i], row_off[i+1]).  With fetch=False the entries stay on the device
+    (``sparse_chunks``) and codes/counts are None."""
+    _require_init()
+    L = _load()
+    n = len(bufs)
+    arrs = [_as_u8(b) for b in bufs]
+    ptrs = (ctypes.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (ctypes.c_size_t * max(n, 1))(*[a.size for a in arrs])
+    nd = np.zeros(n, dtype=np.uint64)
+    totals = np.zeros(n, dtype=np.uint64)
+    status = np.zeros(n, dtype=np.int32)
+    _check(L.kf_sparse_count(ptrs, lens, n, k, nd.ctypes.data, totals.ctypes.data, status.ctypes.data), "kf_sparse_count")
+    if not fetch:
+        row_off = np.zeros(n + 1, dtype=np.uint64)
+        row_off[1:] = np.cumsum(nd)
+        return None, None, row_off, totals, status
+    codes, counts, row_off = _sparse_fetch(n)
+    return codes, counts, row_off, totals, status
+
+
+def sparse_count_device(arena: "DeviceArena", k: int, stream=None, fetch: bool = True):
+    """The same on a device-resident arena.  Synchronises ``stream`` (the output size is only known then)."""
+    import torch
+    _require_init()
+    L = _load()
+    if stream is None:
+        stream = torch.cuda.current_stream(arena.device)
+    handle = stream.cuda_stream if stream.cuda_stream != 0 else 1
+    nd = np.zeros(arena.n, dtype=np.uint64)
+    totals = np.zeros(arena.n, dtype=np.uint64)
+    status = np.zeros(arena.n, dtype=np.int32)
+    _check(L.kf_sparse_count_device(ctypes.c_void_p(arena.tensor.data_ptr()), arena.nbytes, arena.offsets.ctypes.data,
+                                    arena.lens.ctypes.data, arena.formats.ctypes.data, arena.n, k, nd.ctypes.data,
+                                    totals.ctypes.data, status.ctypes.data, ctypes.c_void_p(handle)), "kf_sparse_count_device")
+    if not fetch:
+        row_off = np.zeros(arena.n + 1, dtype=np.uint64)
+        row_off[1:] = np.cumsum(nd)
+        return None, None, row_off, totals, status
+    codes, counts, row_off = _sparse_fetch(arena.n)
+    return codes, counts, row_off, totals, status
+
+
+def sparse_chunks():
+    """Device view of the last sparse result: [(codes_ptr, counts_ptr, n_entries, first_entry, file0, file1), ...]."""
+    L = _load()
+    out = []
+    for i in range(int(L.kf_sparse_chunk_count())):
+        pc, pn = ctypes.c_void_p(), ctypes.c_void_p()
+        ne, fe = ctypes.c_uint64(), ctypes.c_uint64()
+        f0, f1 = ctypes.c_int(), ctypes.c_int()
+        _check(L.kf_sparse_chunk(i, ctypes.byref(pc), ctypes.byref(pn), ctypes.byref(ne), ctypes.byref(fe), ctypes.byref(f0),
+                                 ctypes.byref(f1)), "kf_sparse_chunk")
+        out.append((pc.value, pn.value, int(ne.value), int(fe.value), f0.value, f1.value))
+    return out
+
+
+def sparse_release() -> None:
+    _check(_load().kf_sparse_release(), "kf_sparse_release")
 
 
 # ---- counting: device-resident arena ------------------------------------------------------------------

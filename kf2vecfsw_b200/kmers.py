@@ -31,22 +31,58 @@ def kmer_matrix(counts: np.ndarray, k: int) -> np.ndarray:
     return mat
 
 
+def kmer_matrix_sparse(codes: np.ndarray, counts: np.ndarray, k: int) -> np.ndarray:
+    """Observed canonical k-mers (2-bit codes A0 C1 G2 T3, first base most significant) + counts -> N x (k+1) float32."""
+    mat = np.empty((codes.size, k + 1), dtype=np.float32)
+    c = codes.astype(np.uint64)
+    for j in range(k):
+        mat[:, j] = _STD_TO_FSW[((c >> np.uint64(2 * (k - 1 - j))) & np.uint64(3)).astype(np.intp)]
+    cnt = counts.astype(np.float32)
+    mat[:, k] = cnt / np.sum(cnt)
+    return mat
+
+
+_BATCH_BYTES = 1 << 30   # files are counted in batches of about this many input bytes (one sparse call each)
+
+
+def kmer_matrices(paths, k: int):
+    """Yields (path, matrix | None, status) per file.  k >= 6 goes through the sparse sort-and-run-length path
+    (``kf_sparse_count``: any k up to 31, the reference's -k range, main.py:81-82), smaller k through the dense rows."""
+    paths = list(paths)
+    i = 0
+    while i < len(paths):
+        j, nbytes = i, 0
+        while j < len(paths) and (j == i or nbytes + os.path.getsize(paths[j]) <= _BATCH_BYTES):
+            nbytes += os.path.getsize(paths[j])
+            j += 1
+        bufs = [np.fromfile(p, dtype=np.uint8) for p in paths[i:j]]
+        if k >= engine.KF_SPARSE_MIN_K:
+            codes, counts, row_off, _, status = engine.sparse_count(bufs, k)
+            for t, p in enumerate(paths[i:j]):
+                a, b = int(row_off[t]), int(row_off[t + 1])
+                yield p, (kmer_matrix_sparse(codes[a:b], counts[a:b], k) if b > a else None), int(status[t])
+            engine.sparse_release()
+        else:
+            cnt, _, _, status = engine.count_buffers(bufs, k=k, want_freq=False)
+            for t, p in enumerate(paths[i:j]):
+                yield p, (kmer_matrix(cnt[t], k) if cnt[t].any() else None), int(status[t])
+        i = j
+
+
 def get_kmers(args) -> None:
-    """Reference: kf2vec/main.py:112-184."""
+    """Reference: kf2vec/main.py:112-184 (same files, prints and .npy layout; rows in sorted instead of hash order)."""
     if not os.path.exists(args.output_dir):
         os.makedirs(args.output_dir)
     fasta_files = glob.glob(os.path.join(args.input_dir, "*.fna"))
-    for fna_path in fasta_files:
+    for fna_path, final_matrix, status in kmer_matrices(fasta_files, args.k):
         base_name = os.path.basename(fna_path).replace(".fna", "")
         print(f"--- Processing {base_name} ---")
-        counts, _, _, status = engine.count_buffers([np.fromfile(fna_path, dtype=np.uint8)], k=args.k, want_freq=False)
-        if status[0] != 0:
-            print(f"Error running k-mer counting on {fna_path}: {engine.KfError(int(status[0]))}")
+        if status not in (0, -9):   # (an empty file: Jellyfish reports no k-mers, the reference warns and goes on)
+            print(f"Error running k-mer counting on {fna_path}: {engine.KfError(status)}")
             continue
-        if not counts[0].any():
+        if final_matrix is None:
             print(f"Warning: No valid ATCG k-mers found in {base_name}")
             continue
-        final_matrix = kmer_matrix(counts[0], args.k)
         output_path = os.path.join(args.output_dir, f"{base_name}_k{args.k}.npy")
         np.save(output_path, final_matrix)
         print(f"Saved: {output_path} (Shape: {final_matrix.shape})")

@@ -25,6 +25,8 @@ def lib():
                                        ctypes.c_void_p, ctypes.c_void_p]
         L.kfo_count_buffers_mt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.kfo_count_sparse.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = L
     return _LIB
 
@@ -56,3 +58,17 @@ def count_buffers_mt(bufs, k: int, threads: int, want_freq: bool = True):
     if rc != 0:
         raise ValueError("kfo_count_buffers_mt failed: %d" % rc)
     return counts, freq, status
+
+
+def count_sparse(data, k: int):
+    """Observed canonical k-mers of one file, ascending: (codes u64 [nd], counts u64 [nd], total valid k-mers); k <= 31."""
+    L = lib()
+    data = bytes(data) if not isinstance(data, (bytes, bytearray)) else data
+    cap = max(len(data), 1)
+    codes = np.zeros(cap, dtype=np.uint64)
+    counts = np.zeros(cap, dtype=np.uint64)
+    nd, tot = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    rc = L.kfo_count_sparse(data, len(data), k, codes.ctypes.data, counts.ctypes.data, cap, ctypes.byref(nd), ctypes.byref(tot))
+    if rc != 0:
+        raise ValueError("kfo_count_sparse failed: %d" % rc)
+    return codes[:nd.value].copy(), counts[:nd.value].copy(), int(tot.value)

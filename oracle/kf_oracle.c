@@ -48,7 +48,9 @@ typedef struct {
     uint64_t mask;
     uint64_t f, r;
     int filled;
-    uint64_t *dense; /* [4^k], indexed by canonical code */
+    uint64_t *dense; /* [4^k], indexed by canonical code (NULL in list mode) */
+    uint64_t *list;  /* list mode (sparse counting, any k <= 31): every canonical occurrence appended */
+    size_t nlist;
 } roller_t;
 
 static inline void roll_reset(roller_t *R) { R->filled = 0; }
@@ -59,7 +61,11 @@ static inline void roll_push(roller_t *R, unsigned char c) {
     R->f = ((R->f << 2) | (uint64_t)code) & R->mask;
     R->r = (R->r >> 2) | ((uint64_t)(3 - code) << (2 * (R->k - 1)));
     if (R->filled < R->k) R->filled++;
-    if (R->filled == R->k) R->dense[R->f < R->r ? R->f : R->r]++;
+    if (R->filled == R->k) {
+        const uint64_t c = R->f < R->r ? R->f : R->r;
+        if (R->dense) R->dense[c]++;
+        else R->list[R->nlist++] = c;
+    }
 }
 
 static size_t skip_newlines(const uint8_t *d, size_t n, size_t p) {
@@ -127,6 +133,7 @@ int kfo_count_buffer(const uint8_t *data, size_t n, int k, uint64_t *canon_count
     uint64_t nb = 1ull << (2 * k);
     roller_t R;
     R.k = k; R.mask = nb - 1; R.f = R.r = 0; R.filled = 0;
+    R.list = NULL; R.nlist = 0;
     R.dense = (uint64_t *)calloc(nb, sizeof(uint64_t));
     if (!R.dense) return KFO_ERR_ARG;
     if (data[0] == '>') walk_fasta(data, n, &R);
@@ -138,6 +145,42 @@ int kfo_count_buffer(const uint8_t *data, size_t n, int k, uint64_t *canon_count
     }
     if (total) *total = t;
     free(R.dense);
+    return KFO_OK;
+}
+
+/* Sparse counting for any k <= 31: what `jellyfish count -C` + `jellyfish dump -c` list (kf2vec/main.py:135-145, get_kmers):
+ * the OBSERVED canonical k-mers with their counts -- here in ascending code order (A0 C1 G2 T3, first base most
+ * significant; Jellyfish lists them in hash order).  codes_out / counts_out hold up to cap entries; *n_distinct gets the
+ * number found (the arrays are filled only when it fits), *total the number of valid k-mers. */
+static int cmp_u64(const void *a, const void *b) {
+    const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+int kfo_count_sparse(const uint8_t *data, size_t n, int k, uint64_t *codes_out, uint64_t *counts_out, size_t cap,
+                     uint64_t *n_distinct, uint64_t *total) {
+    init_codes();
+    if (k < 1 || k > 31) return KFO_ERR_ARG;
+    if (n == 0) return KFO_ERR_FORMAT;
+    roller_t R;
+    R.k = k; R.mask = (1ull << (2 * k)) - 1; R.f = R.r = 0; R.filled = 0;
+    R.dense = NULL; R.nlist = 0;
+    R.list = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    if (!R.list) return KFO_ERR_ARG;
+    if (data[0] == '>') walk_fasta(data, n, &R);
+    else if (data[0] == '@') walk_fastq(data, n, &R);
+    else { free(R.list); return KFO_ERR_FORMAT; }
+    qsort(R.list, R.nlist, sizeof(uint64_t), cmp_u64);
+    uint64_t nd = 0;
+    for (size_t i = 0; i < R.nlist;) {
+        size_t j = i + 1;
+        while (j < R.nlist && R.list[j] == R.list[i]) j++;
+        if (nd < cap) { codes_out[nd] = R.list[i]; counts_out[nd] = (uint64_t)(j - i); }
+        nd++;
+        i = j;
+    }
+    if (n_distinct) *n_distinct = nd;
+    if (total) *total = (uint64_t)R.nlist;
+    free(R.list);
     return KFO_OK;
 }
 

@@ -197,6 +197,48 @@ def canonical_counts_bytes(data: bytes, k: int) -> np.ndarray:
     return fold_canonical(forward_counts(symbols_from_bytes(data), k), k)
 
 
+def sparse_counts_bytes(data: bytes, k: int):
+    """Observed canonical k-mers only, ascending by code (A0 C1 G2 T3, first base most significant), any k <= 31: what
+    `jellyfish count -C` + `jellyfish dump -c` list (kf2vec/main.py:135-145), in sorted instead of hash order.
+    Returns (codes uint64 [nd], counts uint64 [nd], total valid k-mers)."""
+    assert 1 <= k <= 31
+    sym = symbols_from_bytes(data)
+    if sym.size < k:
+        return np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64), 0
+    s = sym.astype(np.int64)
+    m = s.size - k + 1
+    fwd = np.zeros(m, dtype=np.uint64)
+    rc = np.zeros(m, dtype=np.uint64)
+    bad = np.zeros(m, dtype=bool)
+    for j in range(k):
+        sl = s[j: j + m]
+        bad |= sl < 0
+        c = (sl & 3).astype(np.uint64)
+        fwd = (fwd << np.uint64(2)) | c
+        rc |= (np.uint64(3) - c) << np.uint64(2 * j)
+    canon = np.minimum(fwd, rc)[~bad]
+    codes, counts = np.unique(canon, return_counts=True)
+    return codes.astype(np.uint64), counts.astype(np.uint64), int(canon.size)
+
+
+_FSW_BASE = np.array([0, 2, 3, 1], dtype=np.float32)   # code A0 C1 G2 T3 -> base_map A0 T1 C2 G3 (main.py:118)
+
+
+def kmer_matrix(data: bytes, k: int):
+    """get_kmers' N x (k+1) float32 matrix (kf2vec/main.py:147-172) for one file: k base codes (A0 T1 C2 G3) and
+    float32(count) / float32 sum of the counts.  Rows in ascending code order (the reference: Jellyfish hash order;
+    the float32 sum therefore agrees to rounding only).  None when no valid k-mer exists (main.py:158-160)."""
+    codes, counts, _ = sparse_counts_bytes(data, k)
+    if codes.size == 0:
+        return None
+    mat = np.empty((codes.size, k + 1), dtype=np.float32)
+    for j in range(k):
+        mat[:, j] = _FSW_BASE[((codes >> np.uint64(2 * (k - 1 - j))) & np.uint64(3)).astype(np.int64)]
+    c32 = counts.astype(np.float32)
+    mat[:, k] = c32 / np.sum(c32)
+    return mat
+
+
 def canonical_counts_slow(data: bytes, k: int) -> np.ndarray:
     """Pure-Python cross-check that rolls forward and reverse-complement mers like Jellyfish."""
     sym = symbols_from_bytes(data)

@@ -96,6 +96,9 @@ inline uint32_t __brev(uint32_t x) {
     for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i);
     return r;
 }
+inline unsigned long long __brevll(unsigned long long x) {
+    return ((unsigned long long)__brev((uint32_t)x) << 32) | __brev((uint32_t)(x >> 32));
+}
 inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
     sh &= 31;
     return sh ? (hi << sh) | (lo >> (32 - sh)) : hi;

@@ -4,6 +4,7 @@
 //   usage: emu_main <k> <threads_per_cta> <grid> <force_walker 0|1> <tile_chunks> <use_linegrid 0|1> file...
 #include "cuda_emu.h"
 #include "../../kf2vecfsw_b200/csrc/kf_kernels.cuh"
+#include "../../kf2vecfsw_b200/csrc/kf_sparse.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -96,6 +97,45 @@ int main(int argc, char **argv) {
         }
     }
     while (cta < grid) { cta++; cta_begin[cta] = (int)tiles.size(); }
+    if (mode == 3) {
+        // sparse sort-and-run-length path, the launch sequence of kf_sparse_host.inc:sparse_run_batch (one sub-batch)
+        const int thr = threads == 512 ? 64 : threads;
+        std::vector<uint64_t> kbase(n + 1, 0);
+        for (int f = 0; f < n; f++) kbase[f + 1] = kbase[f] + ((len[f] && arena[off[f]] == '>') ? len[f] : 0);
+        uint32_t S = 1;
+        while (S < SP_BUCKETS / 8 && (uint64_t)n * S < 16) S <<= 1;
+        const uint32_t n_items = (uint32_t)n * S;
+        std::vector<uint32_t> hist((size_t)n * SP_BUCKETS, 0u), boff((size_t)n * (SP_BUCKETS + 1), 0u), cursor((size_t)n * SP_BUCKETS, 0u), nd(n_items, 0u);
+        std::vector<unsigned long long> ooff(n_items + 1, 0ull), totals(n, 0ull);
+        auto body = [&](auto kt) {
+            using KT = decltype(kt);
+            std::vector<KT> keys(kbase[n] + 16, (KT)0x5A5A5A5A5A5A5A5Aull);
+            auto extract = [&](auto modec) {
+                constexpr int M = decltype(modec)::value;
+                emu::launch(grid, thr, 0, [&]() {
+                    if (k > 16) { if (thr == 32) sparse_extract_kernel<M, KT, true, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data());
+                                  else sparse_extract_kernel<M, KT, true, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data()); }
+                    else { if (thr == 32) sparse_extract_kernel<M, KT, false, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data());
+                           else sparse_extract_kernel<M, KT, false, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data()); }
+                });
+            };
+            extract(std::integral_constant<int, 0>());
+            emu::launch(n, 1024, 0, [&]() { sparse_scan_buckets_kernel(hist.data(), boff.data(), cursor.data(), totals.data(), 0u); });
+            extract(std::integral_constant<int, 1>());
+            emu::launch(n_items, 64, 65536, [&]() { sparse_sort_kernel<KT, 64>(keys.data(), kbase.data(), boff.data(), S, nd.data()); });
+            emu::launch(1, 1024, 0, [&]() { sparse_scan_items_kernel(nd.data(), ooff.data(), n_items); });
+            std::vector<unsigned long long> codes(ooff[n_items] + 1, 0ull);
+            std::vector<uint32_t> cnts(ooff[n_items] + 1, 0u);
+            emu::launch(n_items, 64, 0, [&]() { sparse_emit_kernel<KT, 64>(keys.data(), kbase.data(), boff.data(), S, ooff.data(), codes.data(), cnts.data()); });
+            for (int f = 0; f < n; f++) {
+                printf("%llu", totals[f]);
+                for (unsigned long long e = ooff[(size_t)f * S]; e < ooff[(size_t)(f + 1) * S]; e++) printf(" %llu:%u", codes[e], cnts[e]);
+                printf("\nF\n");
+            }
+        };
+        if (k <= 16) body((uint32_t)0); else body((unsigned long long)0);
+        return 0;
+    }
     size_t NB = (size_t)1 << (2 * k);
     if (mode == 2) {
         // partitioned shared-memory kernel + u32 fold, as kf_api.cu launches them for k = 8..10

@@ -216,3 +216,33 @@ def test_emulated_partitioned_kernel_fuzz(tmp_path):
         for grid, thr, tile in ((1, 64, 64), (3, 32, 8)):
             tot, counts, _ = run_emu(k, thr, grid, False, tile, [p], mode=2)[0]
             assert np.array_equal(counts, ref), (k, grid, thr, tile)
+
+
+def run_emu_sparse(k, threads, grid, tile_chunks, files):
+    out = subprocess.run([BIN, str(k), str(threads), str(grid), "0", str(tile_chunks), "3"] + files,
+                         capture_output=True, text=True, check=True).stdout.strip("\n").split("\n")
+    res = []
+    for i in range(len(files)):
+        parts = out[2 * i].split()
+        ent = [p.split(":") for p in parts[1:]]
+        res.append((int(parts[0]), np.array([int(c) for c, _ in ent], dtype=np.uint64), np.array([int(n) for _, n in ent], dtype=np.uint64)))
+    return res
+
+
+def test_emulated_sparse_sort_rle_fuzz(tmp_path):
+    """The sparse (sort-and-run-length) path for large k: two extraction passes (bucket histogram, bucket scatter),
+    per-bucket bitonic sort, run-length emit -- against the NumPy oracle's observed canonical k-mers, k = 6 .. 31
+    (32-bit keys up to k = 16 with the window fast path, 64-bit keys through the canonical byte walker above)."""
+    for s, k in zip(range(900, 905), (6, 12, 16, 17, 31)):   # (the 1,024-thread scans make an emulated run take ~20 s)
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 2)):
+            p = str(tmp_path / ("sp%d_%d.fa" % (s, i)))
+            open(p, "wb").write(rand_fasta(rng) if rng.random() < 0.5 else rand_fasta_grid(rng))
+            files.append(p)
+        grid, thr, tile = rng.randint(1, 3), rng.choice([32, 64]), rng.choice([1, 3, 64])
+        res = run_emu_sparse(k, thr, grid, tile, files)
+        for f, (tot, codes, counts) in zip(files, res):
+            rc, rn, rt = o.sparse_counts_bytes(open(f, "rb").read(), k)
+            assert tot == rt, (s, k, f)
+            assert np.array_equal(codes, rc) and np.array_equal(counts, rn), (s, k, grid, thr, tile, f)
