@@ -469,3 +469,108 @@ def test_frequency_matrix_fast_path_equals_the_kf_round_trip(eng, toy_inputs, tm
     want = (freq * 1e4).astype(np.float32)
     assert X.dtype.__str__() == "torch.float32" and tuple(X.shape) == want.shape
     assert np.array_equal(X.cpu().numpy(), want)
+
+
+# ---- round 2: k = 11 / 12 on the dense path, the sparse (sort-and-run-length) path up to k = 31, get_kmers ----
+@pytest.mark.parametrize("k", [11, 12])
+def test_dense_k11_k12_vs_c_oracle(eng, toy_inputs, k):
+    """The ABI's dense rows at k = 11 and 12 (4^k global bins, 2,098,176 / 8,390,656 canonical columns): toy inputs and
+    fuzz files against the C oracle's rolling canonical counter."""
+    rng = random.Random(1100 + k)
+    bufs = [toy_inputs["G000830275sub"], toy_inputs["G000402355sub"], rand_fasta(rng), rand_fasta_grid(rng), rand_fastq(rng)]
+    counts, freq, totals, status = eng.count_buffers(bufs, k=k)
+    assert (status == 0).all(), status
+    for i, b in enumerate(bufs):
+        ref = c_oracle.count_buffer(bytes(b), k)
+        assert np.array_equal(counts[i], ref), (k, i)
+        assert int(totals[i]) == int(ref.sum())
+        if ref.sum() > 0:
+            assert np.array_equal(freq[i], ref.astype(np.float64) / np.float64(ref.sum()))
+
+
+def check_sparse(eng, bufs, k, **kw):
+    codes, counts, row_off, totals, status = eng.sparse_count(bufs, k, **kw)
+    assert row_off[0] == 0 and int(row_off[-1]) == codes.size == counts.size
+    for i, b in enumerate(bufs):
+        b = bytes(b)
+        if len(b) == 0:
+            assert status[i] == -9 and row_off[i] == row_off[i + 1]
+            continue
+        if b[:1] != b">":
+            assert status[i] == (-10 if b[:1] == b"@" else -5) and row_off[i] == row_off[i + 1]
+            continue
+        assert status[i] == 0
+        rc, rn, rt = c_oracle.count_sparse(b, k)
+        a, e = int(row_off[i]), int(row_off[i + 1])
+        assert int(totals[i]) == rt, (k, i)
+        assert np.array_equal(codes[a:e], rc), (k, i, e - a, rc.size)
+        assert np.array_equal(counts[a:e].astype(np.uint64), rn), (k, i)
+    return codes, counts, row_off
+
+
+@pytest.mark.parametrize("k", [6, 7, 11, 12, 15, 16, 17, 21, 31])
+def test_sparse_counts_vs_c_oracle(eng, toy_inputs, k):
+    """kf_sparse_count: observed canonical k-mers, ascending by code, against the C oracle (sort + run lengths of the
+    rolling canonical mers): toy genomes, fuzz files (N runs, lower case, IUPAC, CRLF, blank lines, ragged widths),
+    an empty buffer, a FASTQ buffer (KF_ERR_UNSUPPORTED) and a non-sequence buffer (KF_ERR_FORMAT)."""
+    rng = random.Random(2000 + k)
+    bufs = [toy_inputs["G000830275sub"], b"", toy_inputs["G000402355sub"], rand_fastq(rng), b"hello\n", toy_inputs["G000830295"]]
+    bufs += [rand_fasta(rng) for _ in range(6)] + [rand_fasta_grid(rng) for _ in range(4)]
+    check_sparse(eng, bufs, k)
+    eng.sparse_release()
+
+
+def test_sparse_equals_dense_at_k12_and_sub_batches(eng, toy_inputs, monkeypatch):
+    """Two independent device paths at k = 12: the non-zero columns of the dense row (global REDs + fold) are the sparse
+    path's entries; and several sub-batches (KF_SPARSE_BATCH_BYTES) give the same result as one."""
+    names = ["G000830275sub", "G000402355sub", "G000830295"]
+    bufs = [toy_inputs[s] for s in names]
+    codes, counts, row_off = check_sparse(eng, bufs, 12)
+    dense, _, _, status = eng.count_buffers(bufs, k=12, want_freq=False)
+    vc = eng.vocab_codes(12).astype(np.uint64)
+    for i in range(len(bufs)):
+        nz = np.flatnonzero(dense[i])
+        a, e = int(row_off[i]), int(row_off[i + 1])
+        assert np.array_equal(vc[nz], codes[a:e]) and np.array_equal(dense[i][nz], counts[a:e].astype(np.uint64))
+    monkeypatch.setenv("KF_SPARSE_BATCH_BYTES", "300000")
+    c2, n2, r2, _, _ = eng.sparse_count(bufs, 12)
+    assert len(eng.sparse_chunks()) >= 2
+    assert np.array_equal(c2, codes) and np.array_equal(n2, counts) and np.array_equal(r2, row_off)
+    eng.sparse_release()
+
+
+def test_sparse_synthetic_genomes_k21_and_skewed_buckets(eng):
+    """5 Mbp synthetic genomes at k = 21 (64-bit keys) and k = 12, plus a low-complexity file whose k-mers crowd a few
+    buckets (poly-A / short repeats: one bucket far larger than shared memory -> the in-place global sort)."""
+    import kfsynth
+    bufs = [kfsynth.synth_fasta(7, i, 5_000_000) for i in range(3)]
+    seq = "A" * 400000 + "ACGTTGCA" * 30000 + "N" * 7 + "AAAAAAAAAAAAC" * 20000
+    bufs.append(np.frombuffer((">low\n" + "\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + "\n").encode(), dtype=np.uint8))
+    for k in (12, 21):
+        check_sparse(eng, bufs, k)
+    eng.sparse_release()
+
+
+def test_get_kmers_end_to_end(eng, toy_inputs, tmp_path, capsys):
+    """The FSW fork's get_kmers (main.py:112-184) on top of the sparse path: the .npy of every *.fna holds exactly the
+    observed canonical k-mers as k base codes (A0 T1 C2 G3) + float32 normalised counts.  The reference lists rows in
+    Jellyfish's hash order; the set of rows is what is defined (train_model_set.py:192-204 embeds it as a set)."""
+    from kf2vecfsw_b200 import get_kmers
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir()
+    names = ["G000830275sub", "G000402355sub"]
+    for s in names:
+        (ind / (s + ".fna")).write_bytes(toy_inputs[s])
+    (ind / "noseq.fna").write_bytes(b">only_n\nNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN\n")
+    (ind / "ignored.fa").write_bytes(toy_inputs[names[0]])          # get_kmers globs *.fna only (main.py:123)
+    for k in (4, 7, 12, 21):
+        get_kmers(argparse.Namespace(input_dir=str(ind), output_dir=str(outd), k=k))
+        for s in names:
+            got = np.load(outd / ("%s_k%d.npy" % (s, k)))
+            ref = o.kmer_matrix(toy_inputs[s], k)
+            assert got.dtype == np.float32 and got.shape == ref.shape == (ref.shape[0], k + 1)
+            assert np.array_equal(got, ref), (s, k)                 # same row order here (ascending), so plain equality
+            assert abs(float(got[:, k].sum()) - 1.0) < 1e-3
+        assert not (outd / ("noseq_k%d.npy" % k)).exists() and not (outd / ("ignored_k%d.npy" % k)).exists()
+    out = capsys.readouterr().out
+    assert "--- Processing G000830275sub ---" in out and "Warning: No valid ATCG k-mers found in noseq" in out and "Saved: " in out
