@@ -40,6 +40,7 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     int sm_all = 0;   // the device's SM count; sm_count = SMs the counting kernels are sized for (kf_set_sm_limit)
+    uint32_t smem_base = 0;   // shared-window address of dynamic shared memory (kf_smem_base_probe_kernel)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;   // ev_k0/ev_k1: the current call's pair of the ring below
     bool ev_valid = false;
@@ -309,18 +310,27 @@ int launch_fastq_k(int k, const uint8_t *d_arena, int grid, uint32_t file_base, 
     }
 }
 
-template <int LW>
-int launch_linegrid(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
+constexpr uint32_t LG_SMEM_BASE = 0x400;   // where dynamic shared memory begins on sm_100 (checked once: kf_init)
+
+template <int LW, uint32_t BASE>
+int launch_linegrid_b(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
     using G = LineGeom<LW>;
     constexpr int NW = THREADS_LG / 32;
     const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
-    auto kern = count_fasta_lines_kernel<LW, THREADS_LG>;
+    auto kern = count_fasta_lines_kernel<LW, THREADS_LG, BASE>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
                                                              (unsigned long long *)g.d_fwd, g.d_file_row, g.d_cta_first_rank, CTAS_PER_SM,
                                                              g.d_width_counts);
     CK(cudaGetLastError());
     return KF_OK;
+}
+// The pair histogram's REDs carry its shared-window address as an immediate when it is where sm_100 puts it (kf_init
+// asked the device); otherwise the variant that adds the base per RED runs.
+template <int LW>
+int launch_linegrid(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
+    return g.smem_base == LG_SMEM_BASE ? launch_linegrid_b<LW, LG_SMEM_BASE>(d_arena, grid_generic, s)
+                                       : launch_linegrid_b<LW, 0u>(d_arena, grid_generic, s);
 }
 
 template <int K>
@@ -678,6 +688,17 @@ int kf_init(int device) {
     CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&g.d_item_counter, 2 * sizeof(unsigned int)));
     g.sm_count = g.sm_all = prop.multiProcessorCount;
+    {
+        uint32_t *d_b = nullptr, h_b = 0;
+        CK(cudaMalloc((void **)&d_b, sizeof(uint32_t)));
+        CK(cudaFuncSetAttribute(kf_smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kf_smem_base_probe_kernel<<<1, 512, 200 * 1024, g.stream>>>(d_b);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h_b, d_b, sizeof(uint32_t), cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaFree(d_b));
+        g.smem_base = h_b;
+    }
     g.device = device;
     return KF_OK;
 }

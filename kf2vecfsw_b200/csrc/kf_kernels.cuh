@@ -458,6 +458,8 @@ __device__ inline void stage_wait(uint64_t *, uint32_t) { KF_SYNCWARP(); }
 __device__ inline uint32_t smem_addr(const void *) { return 0; }
 __device__ inline void red_shared_add(uint32_t *hist, uint32_t, uint32_t off, uint32_t v) { atomicAdd(hist + (off >> 2), v); }
 __device__ inline void red_shared_add_if(uint32_t *hist, uint32_t, uint32_t off, uint32_t v, uint32_t t, uint32_t bit) { if (t & bit) atomicAdd(hist + (off >> 2), v); }
+template <uint32_t BASE> __device__ inline void red_shared_add_imm(uint32_t *hist, uint32_t, uint32_t off, uint32_t v) { atomicAdd(hist + (off >> 2), v); }
+__device__ inline uint32_t opaque_one() { return gridDim.y; }
 #else
 #define KF_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #define KF_SYNCWARP() __syncwarp()
@@ -496,6 +498,17 @@ __device__ __forceinline__ void red_shared_add_if(uint32_t *, uint32_t base, uin
 __device__ __forceinline__ void red_shared_add(uint32_t *, uint32_t base, uint32_t off, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + off), "r"(v) : "memory");
 }
+// The same with the histogram's shared-window address as an IMMEDIATE of the instruction (BASE != 0), saving the add per
+// RED; BASE == 0: address = base + off as above.  The caller has checked that the histogram really sits at BASE.
+template <uint32_t BASE>
+__device__ __forceinline__ void red_shared_add_imm(uint32_t *, uint32_t base, uint32_t off, uint32_t v) {
+    if (BASE != 0) asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(off), "r"(v), "n"(BASE) : "memory");
+    else asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + off), "r"(v) : "memory");
+}
+// the constant 1 in a register the compiler cannot see through (every launch of this library is one-dimensional, so
+// gridDim.y == 1): (x & IMM) | one is then ONE LOP3 -- an instruction takes one immediate; with two literal constants
+// the compiler emits two
+__device__ __forceinline__ uint32_t opaque_one() { return gridDim.y; }
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -939,18 +952,29 @@ __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::
     return (acc4 & 0x10101010u) | (accC & 0xC8C8C8C8u);
 }
 
-// Count the NPAIR 8-mers ("pairs" of 7-mers) of one decoded line into the pair histogram.
+// Count the NPAIR 8-mers ("pairs" of 7-mers) of one decoded line into the pair histogram.  The 8-mer v (16 bits, first base
+// in bits 1:0) is cut out on bits 16:1 of sv: word = v >> 1 (byte address sv & 0x1FFFC); v's lowest bit picks the addend,
+// 1 (low half: every pair of the word) or 0x20001 (the high half counts the odd pairs, TWICE) -- and that bit is found on
+// bit 17 of the register cut out for the pair four places earlier, so a pair costs three ALU instructions and the RED:
+// funnel shift, two LOP3 (`one` is an opaque register holding 1).  Why word = v >> 1 and not v & 0x7FFF: the bank of a word
+// is its low five index bits; the low bit of a base code says G/C, and on a genome that is not 50 % GC a bank index with
+// three such bits (v bits 4:0) costs 3.9 wavefronts per RED against 3.8 with two (v bits 5:1) -- measured, and the kernel's
+// time follows the shared-memory wavefronts.
 template <int LW>
-__device__ __forceinline__ void ln_count_pairs(const uint32_t (&PK)[LineGeom<LW>::NPK + 1], uint32_t *hist16, uint32_t hbase) {
+__device__ __forceinline__ uint32_t ln_stream32(const uint32_t (&PK)[LineGeom<LW>::NPK + 1], int s) {   // stream bits s .. s+31
+    const int q = s >> 5, r = s & 31;
+    return r == 0 ? PK[q] : __funnelshift_r(PK[q], PK[q + 1], r);
+}
+template <int LW, uint32_t BASE>
+__device__ __forceinline__ void ln_count_pairs(const uint32_t (&PK)[LineGeom<LW>::NPK + 1], uint32_t *hist16, uint32_t hbase, uint32_t one) {
     using G = LineGeom<LW>;
+    uint32_t sv[G::NPAIR];
+#pragma unroll
+    for (int i = 0; i < G::NPAIR; i++) sv[i] = i == 0 ? (PK[0] << 1) : ln_stream32<LW>(PK, 4 * i - 1);
 #pragma unroll
     for (int i = 0; i < G::NPAIR; i++) {
-        const int r = (4 * i) & 31, q = (4 * i) >> 5;
-        uint32_t sv;   // the 8-mer v = bases 2i..2i+7 on bits 16:1
-        if (r == 0) sv = (q == 0) ? (PK[0] << 1) : __funnelshift_r(PK[q - 1], PK[q], 31);
-        else if (r - 1 + 17 <= 32) sv = PK[q] >> (r - 1);
-        else sv = __funnelshift_r(PK[q], PK[q + 1], r - 1);
-        red_shared_add(hist16, hbase, sv & 0x1FFFCu, (sv & 2u) * 0x8000u + 1u);
+        const uint32_t par = i >= 4 ? sv[i - 4] : (PK[0] << (17 - 4 * i));   // bit 17 = stream bit 4i = v's lowest bit
+        red_shared_add_imm<BASE>(hist16, hbase, sv[i] & 0x1FFFCu, (par & 0x20000u) | one);
     }
 }
 
@@ -998,7 +1022,7 @@ struct LnUnit {      // a claimed byte range of the current file piece
 
 // One warp: claim units of the piece [A, Xe) of file [F0, F1) until none is left.  A is a line start.
 // s_cursor: shared byte cursor relative to A.  Returns the number of pairs issued through npairs.
-template <int LW>
+template <int LW, uint32_t BASE>
 __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ arena, const uint64_t A, const uint64_t Xe,
                                                  const uint64_t F0, const uint64_t F1, uint8_t *buf, uint32_t *wscr,
                                                  uint64_t *bar, uint32_t &par, uint32_t *s_cursor, const uint32_t nwarps, uint32_t *hist16,
@@ -1007,6 +1031,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
     constexpr int K = 7;
     const int lane = threadIdx.x & 31;
     const uint32_t hbase = smem_addr(hist16);
+    const uint32_t one = opaque_one();
     const GlobalSrc gsrc{arena};
     auto emit = [&](uint32_t xk) { gs(xk << 2); };
     if (A >= Xe) return;
@@ -1210,7 +1235,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             uint32_t PK[G::NPK + 1];
             const uint32_t anyV = ln_decode<LW>(x, PK);
             if (anyV == 0) {
-                ln_count_pairs<LW>(PK, hist16, hbase);
+                ln_count_pairs<LW, BASE>(PK, hist16, hbase, one);
                 npairs += G::NPAIR;
             } else {
                 dirty = true;
@@ -1265,7 +1290,9 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
 }
 
 
-template <int LW, int THREADS>
+// BASE: shared-window address of the pair histogram (= start of the dynamic shared memory: the kernel has no static
+// shared memory) as a compile-time constant, or 0 when it is not known -- the host asks kf_smem_base_probe_kernel once.
+template <int LW, int THREADS, uint32_t BASE>
 __global__ void __launch_bounds__(THREADS, 1)
 count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
                          const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
@@ -1279,6 +1306,9 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     constexpr int NB7 = 16384;
     KF_DYN_SMEM(uint32_t, smem);
     constexpr int NSWORDS = NB7 / 2;
+#ifndef KF_EMU
+    if (BASE != 0 && smem_addr(smem) != BASE) __trap();   // (the immediate-address REDs would land elsewhere: fail loudly)
+#endif
     uint32_t *hist16 = smem;               // pairs: 65,536 8-mer bins, two u16 halves per word
     uint32_t *single16 = smem + NWORDS;    // rare paths: 16,384 7-mer bins, two u16 halves per word
     uint8_t *stage_base = reinterpret_cast<uint8_t *>(single16 + NSWORDS);
@@ -1311,17 +1341,20 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         if (lane == 0) s_part[warp] = np;
         KF_T(tw0);
         __syncthreads();
-        uint32_t low = 0, sing = 0;
-        for (int i = threadIdx.x; i < NWORDS; i += THREADS) low += hist16[i] & 0xFFFFu;
+        uint32_t low = 0, sing = 0, big = 0;
+        for (int i = threadIdx.x; i < NWORDS; i += THREADS) { const uint32_t v = hist16[i]; low += v & 0xFFFFu; big |= v; }
         for (int i = threadIdx.x; i < NSWORDS; i += THREADS) { const uint32_t v = single16[i]; sing += (v & 0xFFFFu) + (v >> 16); }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { low += __shfl_xor_sync(FULL, low, o); sing += __shfl_xor_sync(FULL, sing, o); }
-        if (lane == 0) { s_part[NWARPS + warp] = low; s_part[2 * NWARPS + warp] = sing; }
+        for (int o = 16; o > 0; o >>= 1) { low += __shfl_xor_sync(FULL, low, o); sing += __shfl_xor_sync(FULL, sing, o); big |= __shfl_xor_sync(FULL, big, o); }
+        // a word whose low half reached 32,768 may have a wrapped high half (it counts twice): reported through the
+        // checksum by making it fail
+        if (lane == 0) { s_part[NWARPS + warp] = (big & 0x8000u) ? 0xFFFFFFFFu : low; s_part[2 * NWARPS + warp] = sing; }
         __syncthreads();
         unsigned long long tp = 0, tl = 0, ts = 0;
+        bool half_ok = true;
 #pragma unroll
-        for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; ts += s_part[2 * NWARPS + w]; }
-        const bool ok = tp == tl && ts == (unsigned long long)*s_nsingle;
+        for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; ts += s_part[2 * NWARPS + w]; half_ok = half_ok && s_part[NWARPS + w] != 0xFFFFFFFFu; }
+        const bool ok = half_ok && tp == tl && ts == (unsigned long long)*s_nsingle;
         // every CTA that holds a piece of the file owns one row of it (file_row[file] + its rank among those CTAs; the
         // fold kernel sums the rows), so the row is WRITTEN, every bin, with plain 16-byte stores: no global atomics.
         // Only the first file of a CTA's tile range can have begun in an earlier CTA: its rank comes from the host.
@@ -1334,7 +1367,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
 #endif
         // xk: 7-mer with its digits reversed (first base in bits 1:0) -- the orientation of both histograms and of this
         // file's rows in g_fwd (the fold kernel undoes it).  xk is the first 7-mer of the 8-mers xk + a*16384 (word
-        // a*8192 + (xk >> 1); odd xk in the high half, even xk = low - high) and the second 7-mer of the 8-mers
+        // a*8192 + (xk >> 1); odd xk: half of the high half, even xk: low - high / 2) and the second 7-mer of the 8-mers
         // 4xk .. 4xk+3 (words 2xk, 2xk+1: sum of the low halves).  One thread: xk = 2j and 2j+1.
 #pragma unroll 4
         for (int j = threadIdx.x; j < NB7 / 2; j += THREADS) {
@@ -1347,8 +1380,8 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
 #pragma unroll
                 for (int a = 0; a < 4; a++) {
                     const uint32_t w = hist16[a * 8192 + j];
-                    c0 += (w & 0xFFFFu) - (w >> 16);
-                    c1 += w >> 16;
+                    c0 += (w & 0xFFFFu) - (w >> 17);
+                    c1 += w >> 17;
                 }
             }
             reinterpret_cast<ulonglong2 *>(g)[j] = make_ulonglong2(c0, c1);
@@ -1417,7 +1450,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         SingleSink gs;
         gs.h = single16;
         gs.n = s_nsingle;
-        ln_process_piece<LW>(arena, A, Xe, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
+        ln_process_piece<LW, BASE>(arena, A, Xe, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
         KF_T(ta2);
         KF_TADD(0, ta2 - ta1);
         t = te;
@@ -1427,6 +1460,15 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     if (threadIdx.x == 0) atomicAdd(&g_piece_timing[4], (unsigned long long)(clock64() - tk0));
 #endif
 }
+
+#ifndef KF_EMU
+// Shared-window address at which the dynamic shared memory of a kernel WITHOUT static shared memory begins, under the
+// launch conditions of this process (0x400 on sm_100: the first KiB is the system's; debuggers / sanitizers may differ).
+__global__ void kf_smem_base_probe_kernel(uint32_t *out) {
+    KF_DYN_SMEM(uint32_t, probe_smem);
+    if (threadIdx.x == 0) *out = smem_addr(probe_smem);
+}
+#endif
 
 // byte-mask helpers (also used by the FASTQ kernels below)
 __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every byte of v that is non-zero

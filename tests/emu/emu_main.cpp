@@ -52,7 +52,7 @@ static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const s
     constexpr int NW = THREADS / 32;
     size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
     emu::launch(grid, THREADS, smem, [&]() {
-        count_fasta_lines_kernel<LW, THREADS>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
+        count_fasta_lines_kernel<LW, THREADS, 0u>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
     });
 }
 

@@ -10,6 +10,7 @@ import pytest
 
 import kf_oracle as o
 import c_oracle
+import kfsynth
 from fuzzgen import rand_fasta, rand_fasta_grid, rand_fastq
 
 pytestmark = pytest.mark.gpu
@@ -109,7 +110,7 @@ def test_edge_inputs(eng):
 
 def test_synthetic_genomes_vs_c_oracle_and_properties(eng):
     """Config-2 style genomes at a size the oracle finishes in seconds, plus size-independent properties."""
-    gen = [eng.synth_fasta(20261018, i, 2_000_000) for i in range(6)]
+    gen = [kfsynth.synth_fasta(20261018, i, 2_000_000) for i in range(6)]
     counts, freq, totals, status = eng.count_buffers(gen, k=7)
     assert (status == 0).all()
     ref, _, st = c_oracle.count_buffers_mt(gen, 7, threads=4, want_freq=False)
@@ -200,7 +201,7 @@ def test_fuzz_fastq(eng, seed0):
 def test_synthetic_fastq_reads_vs_c_oracle(eng):
     """Config-4 style reads: 150 bp, random strand, 0.2 % N per base, 1 % reads with an N run, qualities that may
     start with '@' or '+'; sized so the C oracle finishes in seconds."""
-    samples = [eng.synth_fastq(20261018, i, 1_000_000, 60_000, 150) for i in range(3)]
+    samples = [kfsynth.synth_fastq(20261018, i, 1_000_000, 60_000, 150) for i in range(3)]
     assert any(b"\n@" in bytes(s[:200000]).replace(b"\n@g", b"") for s in samples)   # a quality line starts with '@'
     for k in (7, 9):
         counts, freq, totals, status = eng.count_buffers(samples, k=k)
@@ -291,7 +292,7 @@ def test_full_size_config_every_row_vs_c_oracle(eng):
     G, NB = 1000, 5_000_000
     threads = len(os.sched_getaffinity(0))
     with ThreadPoolExecutor(threads) as ex:
-        gen = list(ex.map(lambda i: eng.synth_fasta(20261018, i, NB), range(G)))
+        gen = list(ex.map(lambda i: kfsynth.synth_fasta(20261018, i, NB), range(G)))
     arena = eng.DeviceArena(gen)
     V = eng.vocab_size(7)
     counts = torch.empty((G, V), dtype=torch.int64, device="cuda")
@@ -321,11 +322,11 @@ def test_big_single_files_and_mixed_batch(eng):
     """One 150 Mbp single-contig genome (every line-kernel CTA holds a piece of the same file: 148 rows summed by the
     fold), one 60-column and one 70-column genome, an unwrapped one, FASTQ reads, an empty and an unsupported file in
     the same batch -- each row against the C oracle."""
-    big = eng.synth_fasta(7, 1, 150_000_000, max_contigs=1, n_runs=25)
-    g60 = eng.synth_fasta(7, 2, 20_000_000, line_width=60)
-    g70 = eng.synth_fasta(7, 3, 20_000_000, line_width=70)
-    flat = eng.synth_fasta(7, 4, 3_000_000, line_width=10 ** 8, max_contigs=5)
-    fq = eng.synth_fastq(7, 5, 1_000_000, 100_000, 150)
+    big = kfsynth.synth_fasta(7, 1, 150_000_000, max_contigs=1, n_runs=25)
+    g60 = kfsynth.synth_fasta(7, 2, 20_000_000, line_width=60)
+    g70 = kfsynth.synth_fasta(7, 3, 20_000_000, line_width=70)
+    flat = kfsynth.synth_fasta(7, 4, 3_000_000, line_width=10 ** 8, max_contigs=5)
+    fq = kfsynth.synth_fastq(7, 5, 1_000_000, 100_000, 150)
     bufs = [big, b"", g60, b"ACGT\n", g70, flat, fq]
     counts, freq, totals, status = eng.count_buffers(bufs, k=7)
     assert list(status) == [0, -9, 0, -5, 0, 0, 0]
@@ -345,8 +346,8 @@ def test_partitioned_kernel_large_k(eng, k):
     import random
     from fuzzgen import rand_fasta, rand_fasta_grid, rand_fastq
     rng = random.Random(1234 + k)
-    bufs = [rand_fasta(rng), eng.synth_fasta(7, 0, 700_000).tobytes(), rand_fasta_grid(rng), rand_fastq(rng),
-            eng.synth_fasta(7, 1, 3_000_000).tobytes(), b">only a header\n"]
+    bufs = [rand_fasta(rng), kfsynth.synth_fasta(7, 0, 700_000).tobytes(), rand_fasta_grid(rng), rand_fastq(rng),
+            kfsynth.synth_fasta(7, 1, 3_000_000).tobytes(), b">only a header\n"]
     ref = [o.canonical_counts_bytes(bytes(b), k) for b in bufs]
     for kw in ({}, {"part_all": True}, {"no_linegrid": True}):
         counts, freq, totals, status = eng.count_buffers(bufs, k=k, **kw)
@@ -367,7 +368,7 @@ def test_files_to_kf_pipeline_matches_buffer_path(eng, toy_inputs, tmp_path):
     reported per file and skipped; -raw_cnt rows switch to integers only when no k-mer is missing."""
     rng = random.Random(77)
     data = {"a": toy_inputs["G000830275sub"], "b": rand_fastq(rng), "c": toy_inputs["G000402355sub"], "d": rand_fasta_grid(rng),
-            "e": b"", "f": b"not a sequence file\n", "g": eng.synth_fasta(3, 0, 400_000).tobytes()}
+            "e": b"", "f": b"not a sequence file\n", "g": kfsynth.synth_fasta(3, 0, 400_000).tobytes()}
     ind, outd = tmp_path / "in", tmp_path / "out"
     ind.mkdir(); outd.mkdir()
     names = sorted(data)
@@ -405,7 +406,7 @@ def test_large_k_full_size_genomes_every_row_vs_c_oracle(eng, k, G):
     NB = 5_000_000
     threads = len(os.sched_getaffinity(0))
     with ThreadPoolExecutor(threads) as ex:
-        gen = list(ex.map(lambda i: eng.synth_fasta(777, i, NB), range(G)))
+        gen = list(ex.map(lambda i: kfsynth.synth_fasta(777, i, NB), range(G)))
     arena = eng.DeviceArena(gen)
     V = eng.vocab_size(k)
     counts = torch.empty((G, V), dtype=torch.int64, device="cuda")
@@ -434,8 +435,8 @@ def test_large_k_file_batching_over_a_small_workspace(eng, k, monkeypatch):
     squeezed to a few rows (KF_WS_LIMIT_BYTES) the groups hold 1-3 files: batch-global file ids in tiles and work
     items, rows relative to the group's first file, the decoded stream indexed by arena chunk."""
     rng = random.Random(99 + k)
-    bufs = [eng.synth_fasta(11, i, 400_000).tobytes() for i in range(4)] + [rand_fasta(rng), rand_fastq(rng), rand_fasta_grid(rng)] + \
-           [eng.synth_fasta(11, 9, 700_000).tobytes()]
+    bufs = [kfsynth.synth_fasta(11, i, 400_000).tobytes() for i in range(4)] + [rand_fasta(rng), rand_fastq(rng), rand_fasta_grid(rng)] + \
+           [kfsynth.synth_fasta(11, 9, 700_000).tobytes()]
     ref = [o.canonical_counts_bytes(bytes(b), k) for b in bufs]
     row_bytes = 4 << (2 * k)
     for nrows in (1, 3):
@@ -454,8 +455,8 @@ def test_frequency_matrix_fast_path_equals_the_kf_round_trip(eng, toy_inputs, tm
     from kf2vecfsw_b200 import frequency_matrix, frequencies
     ind = tmp_path / "in"
     ind.mkdir()
-    data = {"a": toy_inputs["G000830275sub"], "b": toy_inputs["G000402355sub"], "c": eng.synth_fasta(5, 0, 500_000).tobytes(),
-            "d": eng.synth_fastq(5, 0, 100_000, 3_000, 150).tobytes()}
+    data = {"a": toy_inputs["G000830275sub"], "b": toy_inputs["G000402355sub"], "c": kfsynth.synth_fasta(5, 0, 500_000).tobytes(),
+            "d": kfsynth.synth_fastq(5, 0, 100_000, 3_000, 150).tobytes()}
     for s, b in data.items():
         (ind / (s + (".fastq" if s == "d" else ".fna"))).write_bytes(b)
     old = frequencies.BATCH_BYTES

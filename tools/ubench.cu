@@ -164,7 +164,7 @@ void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
     const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
-    auto kern = count_fasta_lines_kernel<80, THREADS>;
+    auto kern = count_fasta_lines_kernel<80, THREADS, 0x400u>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t n_chunks = (uint32_t)(bytes / CHUNK);
     std::vector<Tile> tiles; std::vector<int> cta_begin(sms + 1, 0);
@@ -235,7 +235,7 @@ void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms, int m
     using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
     const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
-    auto kern = count_fasta_lines_kernel<80, THREADS>;
+    auto kern = count_fasta_lines_kernel<80, THREADS, 0x400u>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t slot = (arena_bytes / nfiles) / CHUNK * CHUNK;
     size_t file_bytes = slot - 100;
