@@ -27,7 +27,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + SOURCES + ["-o", OUT]
+    extra = os.environ.get("KF_NVCC_EXTRA", "").split()   # developer experiments (-DKF_... switches)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + SOURCES + ["-o", OUT]
     subprocess.check_call(cmd)
     return OUT
 

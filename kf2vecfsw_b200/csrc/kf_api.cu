@@ -312,12 +312,11 @@ int launch_fastq_k(int k, const uint8_t *d_arena, int grid, uint32_t file_base, 
 
 constexpr uint32_t LG_SMEM_BASE = 0x400;   // where dynamic shared memory begins on sm_100 (checked once: kf_init)
 
-template <int LW, uint32_t BASE>
+template <int LW, uint32_t BASE, bool VIRT = false>
 int launch_linegrid_b(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
-    using G = LineGeom<LW>;
     constexpr int NW = THREADS_LG / 32;
-    const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
-    auto kern = count_fasta_lines_kernel<LW, THREADS_LG, BASE>;
+    const size_t smem = lines_kernel_smem<LW>(NW);
+    auto kern = count_fasta_lines_kernel<LW, THREADS_LG, BASE, VIRT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
                                                              (unsigned long long *)g.d_fwd, g.d_file_row, g.d_cta_first_rank, CTAS_PER_SM,
@@ -327,10 +326,10 @@ int launch_linegrid_b(const uint8_t *d_arena, int grid_generic, cudaStream_t s) 
 }
 // The pair histogram's REDs carry its shared-window address as an immediate when it is where sm_100 puts it (kf_init
 // asked the device); otherwise the variant that adds the base per RED runs.
-template <int LW>
+template <int LW, bool VIRT = false>
 int launch_linegrid(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
-    return g.smem_base == LG_SMEM_BASE ? launch_linegrid_b<LW, LG_SMEM_BASE>(d_arena, grid_generic, s)
-                                       : launch_linegrid_b<LW, 0u>(d_arena, grid_generic, s);
+    return g.smem_base == LG_SMEM_BASE ? launch_linegrid_b<LW, LG_SMEM_BASE, VIRT>(d_arena, grid_generic, s)
+                                       : launch_linegrid_b<LW, 0u, VIRT>(d_arena, grid_generic, s);
 }
 
 template <int K>
@@ -538,7 +537,7 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     if (smem_path) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         // line width per file (0 = generic kernel) + zeroing of the rows the line kernel will not write
-        CK(cudaMemsetAsync(g.d_width_counts, 0, 4 * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(g.d_width_counts, 0, 8 * sizeof(uint32_t), s));
         probe_line_width_kernel<<<(f1 + 3) / 4, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, (int)f1,
                                                                 use_lg ? 0u : 1u, g.d_file_P, g.d_width_counts,
                                                                 (unsigned long long *)g.d_fwd, g.d_file_row, (uint32_t)NB);
@@ -553,8 +552,9 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             rc = launch_linegrid<80>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<70>(d_arena, grid, s);
+            if (rc == KF_OK) rc = launch_linegrid<80, true>(d_arena, grid, s);   // long-line files: virtual lines
             if (rc != KF_OK) return rc;
-            g.last_launches += 3;
+            g.last_launches += 4;
         }
         // file indices inside tiles are batch-global; k >= 8 rows are relative to f0, k <= 7 rows come from d_file_row
         rc = launch_count(k, d_arena, grid, force_walker, f0, s);
@@ -685,7 +685,7 @@ int kf_init(int device) {
     for (int i = 0; i < Ctx::EV_RING; i++) { CK(cudaEventCreate(&g.ring0[i])); CK(cudaEventCreate(&g.ring1[i])); }
     g.ev_k0 = g.ring0[0];
     g.ev_k1 = g.ring1[0];
-    CK(cudaMalloc((void **)&g.d_width_counts, 4 * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&g.d_width_counts, 8 * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&g.d_item_counter, 2 * sizeof(unsigned int)));
     g.sm_count = g.sm_all = prop.multiProcessorCount;
     {

@@ -896,9 +896,12 @@ __device__ __forceinline__ uint32_t digit_rev7(uint32_t x) {   // reverse the se
 
 // Decode the NWA aligned words of one line (+ look-ahead): returns non-zero iff a sequence byte is not A/C/G/T;
 // PK receives the 2-bit codes LSB-first (base j of the line at bits 2(j%16) of PK[j/16]; the '\n' is skipped).
-template <int LW>
+// GAP = bytes between the line's last base and the look-ahead bases: 1 (the '\n' of wrapped FASTA) or 0 (virtual lines cut
+// out of one long line, see vl_process_piece).
+template <int LW, int GAP = 1>
 __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::NWA + 1], uint32_t (&PK)[LineGeom<LW>::NPK + 1]) {
     using G = LineGeom<LW>;
+    static_assert(GAP == 0 || GAP == 1, "gap");
     constexpr uint32_t MPACK = (1u << 23) + (1u << 17) + (1u << 11) + (1u << 5);   // byte3 = c0 | c1<<2 | c2<<4 | c3<<6
     uint32_t acc4 = 0, accC = 0;
     uint32_t pk[G::NWA];
@@ -915,7 +918,7 @@ __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::
 #pragma unroll
         for (int bb = 0; bb < 4; bb++) {
             const int byte = 4 * i + bb;
-            if (byte < LW || (byte > LW && byte <= LW + G::LA)) m |= 0xFFu << (8 * bb);
+            if (byte < LW || (byte >= LW + GAP && byte < LW + GAP + G::LA)) m |= 0xFFu << (8 * bb);
         }
         if (m == 0xFFFFFFFFu) { acc4 |= Y; accC |= Z; }
         else if (m != 0) { acc4 |= Y & m; accC |= Z & m; }
@@ -934,14 +937,14 @@ __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::
         const uint32_t g8 = pk[i] >> 24;   // 4 codes, byte 0's in bits 1:0
 #pragma unroll
         for (int seg = 0; seg < 2; seg++) {
-            int b0 = (seg == 0) ? 0 : LW + 1 - 4 * i;                  // line bases | look-ahead bases
-            int b1 = (seg == 0) ? LW - 4 * i : LW + 1 + G::LA - 4 * i;
+            int b0 = (seg == 0) ? 0 : LW + GAP - 4 * i;                // line bases | look-ahead bases
+            int b1 = (seg == 0) ? LW - 4 * i : LW + GAP + G::LA - 4 * i;
             b0 = b0 < 0 ? 0 : b0;
             b1 = b1 > 4 ? 4 : b1;
             if (b1 > b0) {
                 const int n = b1 - b0;
                 const int byte = 4 * i + b0;
-                const int pos = byte < LW ? byte : byte - 1;          // sequence bytes before this one
+                const int pos = byte < LW ? byte : byte - GAP;        // sequence bytes before this one
                 const uint32_t val = (g8 >> (2 * b0)) & ((1u << (2 * n)) - 1u);
                 const int sh = 2 * (pos & 15);
                 PK[pos >> 4] |= val << sh;
@@ -1290,9 +1293,340 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
 }
 
 
+// byte-mask helpers (also used by the FASTQ kernels below)
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every byte of v that is non-zero
+    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t movemask4(uint32_t f) {       // f has 0x80 flags; -> 4-bit mask, byte 0 in bit 0
+    return ((f >> 7) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t newline_mask16(const uint4 w) {
+    const uint32_t n0 = ~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n1 = ~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n2 = ~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u;
+    const uint32_t n3 = ~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u;
+    return movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12);
+}
+
+// ================================================================================================
+// Virtual lines: long-line ("unwrapped") FASTA through the same pair histogram
+// ================================================================================================
+// Assemblers write one line per contig (kilobases to megabases).  There is no grid of '\n' to hang a lane on -- but
+// inside such a line any 80 bytes are 80 bases, so a warp cuts VIRTUAL lines of VL = 80 bytes wherever it likes: lane l
+// takes the bytes [B + 80 l, B + 80 l + 86) of a window that starts at a multiple of 16.  Compared with the wrapped
+// kernel: five aligned LDS.128 + one LDS.64 instead of 23 LDS.32 and 22 funnel shifts, no bank conflicts (lane pitch =
+// 5 x 16 bytes), nothing to delete.  What has to be known instead is whether a byte range lies in a sequence line or in
+// a header line -- and the line's start may be megabytes back:
+//   piece  : the state at the piece's first byte comes from an exact backward scan by the whole CTA (only the pieces
+//            that begin inside a file need one).
+//   unit   : a unit (byte range [Us, Ue), Us = A + n * 2560, claimed from the shared cursor) owns the k-mers whose first
+//            base lies in it.  Its state at Us: the last '\n' of the 256 bytes before Us decides; if there is none the
+//            unit ASSUMES "sequence line" and notes Us in a shared list.
+//   breaks : a lane whose 86 bytes hold a '\n' (or reach the file's end) stops the grid; the warp walks the line
+//            structure from there (tail of the line, header lines -- each one noted with its first and last byte --,
+//            blank lines) until a sequence line is long enough to carry the grid again, which restarts on the next slot
+//            boundary of the unit; the part slots on both sides are counted by all lanes together.
+//   verify : when the piece is done, an assumed unit start that lies inside a noted header line means text was counted
+//            that is no sequence (a header longer than 256 bytes across a unit boundary): the flush then discards the
+//            histograms and recounts the piece exactly, like after a wrapped 16-bit half.
+#ifdef KF_VL_TIMING
+__device__ unsigned long long g_vl_timing[16];   // developer instrumentation: warp cycles [0] walk_structure [1] unit start [2] stage waits [3] windows [4] #walks [5] #units [6] #windows [7] total
+__device__ unsigned long long g_vl_cta[4 * 160];   // per CTA: total cycles, pieces, max piece cycles, cycles in the piece-start backward scan
+#define VLT(var) const long long var = clock64()
+#define VLADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_vl_timing[i], (unsigned long long)(v)); } while (0)
+#else
+#define VLT(var)
+#define VLADD(i, v)
+#endif
+constexpr int VL = 80;                       // bytes (= bases) per virtual line
+constexpr int VL_WIN = 32 * VL;              // 2,560 bytes per window
+constexpr int VL_STAGE = VL_WIN + 16;        // + the last lane's look-ahead
+constexpr int VL_LOOKBACK = 256;
+constexpr int VL_LOG_SPEC = 1024;            // assumed unit starts per piece (u32 file offsets)
+constexpr int VL_LOG_HDR = 512;              // header lines per piece (first byte, terminating '\n': u32 file offsets)
+
+struct VlLog {            // shared memory, per CTA
+    uint32_t n_spec, n_hdr, overflow, pad;
+    uint32_t spec[VL_LOG_SPEC];
+    uint32_t hdr[2 * VL_LOG_HDR];
+};
+
+// All 32 lanes: count the K-mers whose first base lies in [lo, hi) of a stretch without '\n' in [lo, hi + K - 1) (the
+// caller knows): a K-mer counts iff its K bytes are bases.  Bytes are read where they lie (L1/L2).
+template <int K, class Sink>
+__device__ __forceinline__ void vl_count_stretch(const uint8_t *__restrict__ arena, uint64_t lo, uint64_t hi, uint64_t limit, Sink sink) {
+    if (hi <= lo) return;
+    const uint64_t avail = limit - lo;                    // bytes that may be looked at from lo on
+    const int nstream = avail > (uint64_t)(1 << 20) ? (1 << 20) : (int)avail;
+    ln_coop_line<K>(arena + lo, (int)(hi - lo), nstream, 1 << 30, sink);
+}
+
+// One warp, virtual lines: units of the piece [A, Xe) of the file [F0, F1); state_at_A: 0 = A lies inside a sequence line,
+// 1 = inside a header line that began before A, 2 = A is a line start.
+template <uint32_t BASE>
+__device__ __forceinline__ void vl_process_piece(const uint8_t *__restrict__ arena, const uint64_t A, const uint64_t Xe, const uint32_t state_at_A,
+                                                 const uint64_t F0, const uint64_t F1, uint8_t *buf, uint32_t *wscr, uint64_t *bar,
+                                                 uint32_t &par, uint32_t *s_cursor, const uint32_t nwarps, uint32_t *hist16, SingleSink gs,
+                                                 uint32_t &npairs, VlLog *log) {
+    constexpr int K = 7;
+    constexpr int LW = VL;
+    using G = LineGeom<LW>;
+    static_assert(G::NWA == 22 && (VL % 16) == 0, "five 16-byte pieces and one 8-byte look-ahead per lane");
+    const int lane = threadIdx.x & 31;
+    const uint32_t hbase = smem_addr(hist16);
+    const uint32_t one = opaque_one();
+    const GlobalSrc gsrc{arena};
+    auto emit = [&](uint32_t xk) { gs(xk << 2); };
+    if (A >= Xe) return;
+    const uint64_t plen = Xe - A;
+    struct Unit { uint64_t Us, Ue; };
+    auto claim = [&](Unit &U) -> bool {
+        uint32_t old = 0, sz = 0;
+        if (lane == 0) {
+            const uint64_t seen = *reinterpret_cast<volatile uint32_t *>(s_cursor);
+            const uint64_t left = seen < plen ? plen - seen : 0;
+            uint64_t nwin = left / ((uint64_t)VL_WIN * 2u * nwarps);
+            nwin = nwin < 2 ? 2 : (nwin > 64 ? 64 : nwin);
+#ifdef KF_EMU_RANDOM_UNITS
+            { extern unsigned g_emu_seed; uint64_t z = (seen + g_emu_seed) * 0x9E3779B97F4A7C15ull; z ^= z >> 29; nwin = 1 + (z % 5); }
+#endif
+            sz = (uint32_t)(nwin * VL_WIN);
+            old = atomicAdd(s_cursor, sz);
+        }
+        old = __shfl_sync(FULL, old, 0);
+        sz = __shfl_sync(FULL, sz, 0);
+        if ((uint64_t)old >= plen) return false;
+        U.Us = A + old;
+        U.Ue = U.Us + sz < Xe ? U.Us + sz : Xe;
+        return true;
+    };
+    auto log_spec = [&](uint64_t us) {
+        if (lane == 0) {
+            const uint32_t i = atomicAdd(&log->n_spec, 1u);
+            if (i < (uint32_t)VL_LOG_SPEC) log->spec[i] = (uint32_t)(us - F0); else log->overflow = 1u;
+        }
+    };
+    auto log_hdr = [&](uint64_t hs, uint64_t he) {
+        if (lane == 0) {
+            const uint32_t i = atomicAdd(&log->n_hdr, 1u);
+            if (i < (uint32_t)VL_LOG_HDR) { log->hdr[2 * i] = (uint32_t)(hs - F0); log->hdr[2 * i + 1] = (uint32_t)(he - F0); } else log->overflow = 1u;
+        }
+    };
+    // position of the first '\n' at or after q, F1 if there is none (all lanes)
+    auto next_nl = [&](uint64_t q) -> uint64_t {
+        if (q >= F1) return F1;
+        const uint64_t ls = fasta_line_start_at_or_after(gsrc, q + 1, F0, F1, lane);   // byte after the first '\n' >= q
+        return (ls == F1 && arena[F1 - 1] != 0x0Au) ? F1 : ls - 1;
+    };
+    // From the line start `pos`: blank lines and header lines are skipped (headers noted); returns the first byte of the
+    // next sequence line, or U.Ue when the unit (or the file) ends first.
+    auto skip_headers = [&](const Unit &U, uint64_t pos) -> uint64_t {
+        for (;;) {
+            if (pos >= F1 || pos >= U.Ue) return U.Ue;
+            const uint32_t c = arena[pos];
+            if (c == 0x0Au) { pos++; continue; }                 // blank line
+            if (c != (uint32_t)'>') return pos;
+            const uint64_t he = next_nl(pos);
+            log_hdr(pos, he);
+            if (he >= F1) return U.Ue;
+            pos = he + 1;
+        }
+    };
+    // From `pos` inside a sequence line (the bytes before it are done): count what lies between pos and the place where
+    // full virtual lines can go on, walking the line structure; returns that place -- a slot boundary of the unit's
+    // grid (U.Us + 80 n) -- or U.Ue.  after_pos: the boundary must lie beyond pos (the unit's last, partial slot).
+    auto walk_structure = [&](const Unit &U, uint64_t pos, const bool after_pos) -> uint64_t {
+        for (;;) {
+#ifdef KF_EMU_TRACE
+            if (lane == 0) fprintf(stderr, "  walk pos=%llu Us=%llu Ue=%llu after=%d\n", (unsigned long long)(pos - F0), (unsigned long long)(U.Us - F0), (unsigned long long)(U.Ue - F0), (int)after_pos);
+#endif
+            if (pos >= U.Ue || pos >= F1) return U.Ue;
+            const uint64_t nslot = (pos - U.Us + VL - 1) / VL + ((after_pos && (pos - U.Us) % VL == 0) ? 1 : 0);
+            const uint64_t slot = U.Us + nslot * VL;                              // next slot boundary
+            const uint64_t hi = slot < U.Ue ? slot : U.Ue;
+            // the line's '\n' if it lies before hi + K - 1 (a bounded look: the line may be megabytes long), F1 at the
+            // end of the file
+            const uint64_t lim = hi + (K - 1) < F1 ? hi + (K - 1) : F1;
+            uint64_t p = lim;
+            for (uint64_t q0 = pos; q0 < lim && p == lim; q0 += 96) {
+                int first = 3;
+#pragma unroll
+                for (int j = 2; j >= 0; j--) {
+                    const uint64_t a = q0 + 3ull * lane + j;
+                    if (a < lim && arena[a] == 0x0Au) first = j;
+                }
+                const unsigned Bm = __ballot_sync(FULL, first < 3);
+                if (Bm) {
+                    const int jl = __ffs((int)Bm) - 1;
+                    p = q0 + 3ull * jl + (uint64_t)__shfl_sync(FULL, first, jl);
+                }
+            }
+            if (p == lim && lim < F1) {
+                // the line carries on beyond the boundary (look-ahead included): the grid goes on there
+                vl_count_stretch<K>(arena, pos, hi, lim, gs);
+                return hi;
+            }
+            // the line ends first.  What follows its '\n'?  A sequence line (the record goes on: k-mers span the '\n') is
+            // the byte walker's case; a header line, the end of the file (or blank lines and then one of them) close it.
+            uint64_t nx = p + 1;
+            while (nx < F1 && arena[nx] == 0x0Au) nx++;
+            const bool closes = nx >= F1 || arena[nx] == (uint8_t)'>';
+            if (closes) {
+                vl_count_stretch<K>(arena, pos, p < U.Ue ? p : U.Ue, p, gs);
+                if (p >= F1) return U.Ue;
+                pos = skip_headers(U, p + 1);
+            } else {
+                if (lane == 0) fasta_walk_lane<K>(gsrc, pos, nx < U.Ue ? nx : U.Ue, false, false, emit);
+                KF_SYNCWARP();
+                pos = nx;
+            }
+        }
+    };
+    Unit U;
+    VLT(t_all0);
+    bool have = claim(U);
+    while (have) {
+        VLT(t_u0);
+        // ---- where the unit's grid starts: the state at Us decides ----
+        uint64_t B;
+        uint32_t st;   // 0: inside a sequence line, 1: inside a header line that began before Us, 2: Us is a line start
+        if (U.Us == A) {
+            st = state_at_A;
+        } else {
+            const uint64_t lb0 = U.Us - F0 >= (uint64_t)VL_LOOKBACK ? U.Us - VL_LOOKBACK : F0;   // (multiple of 16)
+            const uint64_t q = lb0 + 8ull * lane;
+            uint2 w = make_uint2(0u, 0u);
+            if (q < U.Us) w = __ldg(reinterpret_cast<const uint2 *>(arena + q));
+            int last = -1;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t c = ((i < 4 ? w.x : w.y) >> (8 * (i & 3))) & 0xFFu;
+                if (q + i < U.Us && c == 0x0Au) last = i;
+            }
+            const unsigned Bm = __ballot_sync(FULL, last >= 0);
+            if (Bm) {
+                const int j = 31 - __clz((int)Bm);
+                const int lj = __shfl_sync(FULL, last, j);
+                const uint64_t ls = lb0 + 8ull * j + (uint64_t)lj + 1;   // start of the line that holds Us (<= Us)
+                st = ls == U.Us ? 2u : (arena[ls] == (uint8_t)'>' ? 1u : 0u);
+            } else if (lb0 == F0) {
+                st = 1u;                  // still on the file's first line: the header ('>' is the file's first byte)
+            } else {
+                st = 0u;                  // assumed: sequence line -- checked when the piece is done
+                log_spec(U.Us);
+            }
+        }
+        if (st == 1u) {
+            const uint64_t he = next_nl(U.Us);
+            if (U.Us == A) log_hdr(A, he);   // (it began before the piece: nobody else notes it)
+            B = (he >= F1 || he + 1 >= U.Ue) ? U.Ue : walk_structure(U, skip_headers(U, he + 1), false);
+        } else if (st == 2u) {
+            B = walk_structure(U, skip_headers(U, U.Us), false);
+        } else {
+            B = U.Us;
+        }
+#ifdef KF_EMU_TRACE
+        if (lane == 0) fprintf(stderr, "unit Us=%llu Ue=%llu st=%u B=%llu\n", (unsigned long long)(U.Us - F0), (unsigned long long)(U.Ue - F0), st, (unsigned long long)(B - F0));
+#endif
+        // ---- windows of full virtual lines from B on ----
+        VLT(t_u1);
+        VLADD(1, t_u1 - t_u0); VLADD(5, 1);
+        bool staged = false;
+        while (B < U.Ue) {
+            const uint32_t nslots = (uint32_t)((U.Ue - B) / VL);
+            if (nslots == 0) {   // the piece ends inside a slot
+                VLT(t_w0);
+                B = walk_structure(U, B, true);
+                VLT(t_w1);
+                VLADD(0, t_w1 - t_w0); VLADD(4, 1);
+                continue;
+            }
+            const uint32_t nact = nslots < 32u ? nslots : 32u;
+            if (!staged) {
+                KF_SYNCWARP();
+                if (lane == 0) stage_issue(buf, arena + B, VL_STAGE, bar);
+            }
+            stage_wait(bar, par);
+            par ^= 1u;
+            staged = false;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(buf + (uint32_t)lane * VL);
+            uint32_t x[G::NWA + 1];
+#pragma unroll
+            for (int i = 0; i < 5; i++) { const uint4 v = s4[i]; x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w; }
+            { const uint2 v = *reinterpret_cast<const uint2 *>(buf + (uint32_t)lane * VL + VL); x[20] = v.x; x[21] = v.y; }
+            x[22] = 0;
+            // the next window of this unit, assuming this one is clean: its copy overlaps the decode
+            const uint64_t Bn = B + (uint64_t)VL_WIN;
+            if (nact == 32u && Bn + VL <= U.Ue) {
+                KF_SYNCWARP();
+                if (lane == 0) stage_issue(buf, arena + Bn, VL_STAGE, bar);
+                staged = true;
+            }
+            uint32_t PK[G::NPK + 1];
+            const bool active = (uint32_t)lane < nact;
+            const uint32_t anyV = ln_decode<LW, 0>(x, PK);
+            const bool dirty = active && anyV != 0;
+            const unsigned D = __ballot_sync(FULL, dirty);
+            uint32_t f = nact;   // lanes [0, f) are virtual lines of one sequence line
+            if (D) {
+                // which dirty lanes hold a '\n' or reach beyond the file?  (the raw bytes are still in x)
+                bool brk = false;
+                if (dirty) {
+                    const uint64_t sl = B + (uint64_t)lane * VL;
+                    brk = sl + VL + (K - 1) > F1;
+#pragma unroll
+                    for (int i = 0; i < G::NWA; i++) {
+                        const uint32_t z = x[i] ^ 0x0A0A0A0Au;
+                        uint32_t m = (z - 0x01010101u) & ~z & 0x80808080u;
+                        if (i == G::NWA - 1) m &= 0x00008080u;   // (bytes 86, 87 are not mine)
+                        brk = brk || m != 0;
+                    }
+                }
+                const unsigned Bk = __ballot_sync(FULL, brk);
+                if (Bk) f = (uint32_t)(__ffs((int)Bk) - 1);
+            }
+            if ((uint32_t)lane < f && active && !dirty) {
+                ln_count_pairs<LW, BASE>(PK, hist16, hbase, one);
+                npairs += G::NPAIR;
+            }
+            // dirty lanes before the break: N runs, IUPAC codes ... -- all lanes count such a line together
+            unsigned Dn = D & (f >= 32u ? 0xFFFFFFFFu : ((1u << f) - 1u));
+            while (Dn) {
+                const int j = __ffs((int)Dn) - 1;
+                Dn &= Dn - 1;
+                const uint64_t sl = B + (uint64_t)j * VL;
+                vl_count_stretch<K>(arena, sl, sl + VL, sl + VL + (K - 1), gs);
+            }
+            if (f < nact) {
+                // the grid breaks in slot f: drop the copy that was started for the next window, walk the structure
+                VLT(t_w0);
+                if (staged) { stage_wait(bar, par); par ^= 1u; staged = false; }
+                B = walk_structure(U, B + (uint64_t)f * VL, true);   // (its '\n' lies within the slot's 86 bytes: go beyond it)
+                VLT(t_w1);
+                VLADD(0, t_w1 - t_w0); VLADD(4, 1);
+            } else {
+                B += (uint64_t)nact * VL;
+            }
+        }
+        have = claim(U);
+    }
+    VLT(t_all1);
+    VLADD(7, t_all1 - t_all0);
+    (void)wscr;
+}
+
 // BASE: shared-window address of the pair histogram (= start of the dynamic shared memory: the kernel has no static
 // shared memory) as a compile-time constant, or 0 when it is not known -- the host asks kf_smem_base_probe_kernel once.
-template <int LW, int THREADS, uint32_t BASE>
+// VIRT: the files of this launch are long-line FASTA (file_P == KF_P_VIRTUAL), counted through virtual lines of 80 bytes
+// (vl_process_piece); LW must be 80 then (same shared-memory layout).
+constexpr uint32_t KF_P_VIRTUAL = 0xFFFFu;
+// dynamic shared memory of count_fasta_lines_kernel: pair + singles histograms, one staging buffer and one barrier per
+// warp, per-warp scratch and partial sums, cursor words, the backward scan's result, the virtual-line log
+template <int LW> constexpr size_t lines_kernel_smem(int nwarps) {
+    return (32768 + 8192) * sizeof(uint32_t) + (size_t)nwarps * LineGeom<LW>::STAGE + (size_t)nwarps * sizeof(uint64_t) +
+           (27 * (size_t)nwarps + 4) * sizeof(uint32_t) + 16 + sizeof(VlLog);
+}
+template <int LW, int THREADS, uint32_t BASE, bool VIRT = false>
 __global__ void __launch_bounds__(THREADS, 1)
 count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin,
                          const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
@@ -1300,7 +1634,9 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
                          const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ cta_first_rank, int cta_stride,
                          const uint32_t *__restrict__ width_counts) {
     using G = LineGeom<LW>;
-    if (width_counts[(LW - 50) / 10] == 0) return;   // no file of this width in the batch (uniform exit)
+    static_assert(!VIRT || (LW == 80 && VL_STAGE <= G::STAGE), "virtual lines use the 80-column layout");
+    constexpr uint32_t MYP = VIRT ? KF_P_VIRTUAL : (uint32_t)G::P;
+    if (width_counts[VIRT ? 4 : (LW - 50) / 10] == 0) return;   // no file of this kind in the batch (uniform exit)
     constexpr int NWARPS = THREADS / 32;
     constexpr int NWORDS = 32768;
     constexpr int NB7 = 16384;
@@ -1317,9 +1653,12 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     uint32_t *s_part = s_wscr + 24 * NWARPS;                          // per warp: pairs issued | pair low-half sums | singles half sums
     uint32_t *s_nsingle = s_part + 3 * NWARPS;                        // singles issued
     uint32_t *s_cursor = s_nsingle + 1;
+    unsigned long long *s_found = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(s_cursor + 3) + 7) & ~(uintptr_t)7);
+    VlLog *vlog = reinterpret_cast<VlLog *>(s_found + 1);                                   // VIRT only
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NWORDS + NSWORDS; i += THREADS) smem[i] = 0;
-    if (threadIdx.x == 0) { *s_nsingle = 0; *s_cursor = 0; }
+    if (threadIdx.x == 0) { *s_nsingle = 0; *s_cursor = 0; s_cursor[1] = 0; }
+    if (VIRT && threadIdx.x == 0) { vlog->n_spec = 0; vlog->n_hdr = 0; vlog->overflow = 0; }
     uint8_t *buf = stage_base + (size_t)warp * G::STAGE;
     uint64_t *bar = bars + warp;
     uint32_t par = 0;
@@ -1341,6 +1680,17 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         if (lane == 0) s_part[warp] = np;
         KF_T(tw0);
         __syncthreads();
+        if (VIRT) {
+            // an assumed unit start inside a noted header line: text was counted that is no sequence
+            const uint32_t ns = vlog->n_spec < (uint32_t)VL_LOG_SPEC ? vlog->n_spec : (uint32_t)VL_LOG_SPEC;
+            const uint32_t nh = vlog->n_hdr < (uint32_t)VL_LOG_HDR ? vlog->n_hdr : (uint32_t)VL_LOG_HDR;
+            bool bad = threadIdx.x == 0 && vlog->overflow != 0;
+            for (uint32_t i = threadIdx.x; i < ns; i += THREADS) {
+                const uint32_t us = vlog->spec[i];
+                for (uint32_t h = 0; h < nh; h++) bad = bad || (vlog->hdr[2 * h] < us && us <= vlog->hdr[2 * h + 1]);
+            }
+            if (bad) s_cursor[1] = 1u;   // (read after the next barrier)
+        }
         uint32_t low = 0, sing = 0, big = 0;
         for (int i = threadIdx.x; i < NWORDS; i += THREADS) { const uint32_t v = hist16[i]; low += v & 0xFFFFu; big |= v; }
         for (int i = threadIdx.x; i < NSWORDS; i += THREADS) { const uint32_t v = single16[i]; sing += (v & 0xFFFFu) + (v >> 16); }
@@ -1354,7 +1704,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         bool half_ok = true;
 #pragma unroll
         for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; ts += s_part[2 * NWARPS + w]; half_ok = half_ok && s_part[NWARPS + w] != 0xFFFFFFFFu; }
-        const bool ok = half_ok && tp == tl && ts == (unsigned long long)*s_nsingle;
+        const bool ok = half_ok && tp == tl && ts == (unsigned long long)*s_nsingle && !(VIRT && s_cursor[1] != 0);
         // every CTA that holds a piece of the file owns one row of it (file_row[file] + its rank among those CTAs; the
         // fold kernel sums the rows), so the row is WRITTEN, every bin, with plain 16-byte stores: no global atomics.
         // Only the first file of a CTA's tile range can have begun in an earlier CTA: its rank comes from the host.
@@ -1393,10 +1743,14 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         __syncthreads();
         uint4 *h4 = reinterpret_cast<uint4 *>(smem);
         for (int i = threadIdx.x; i < (NWORDS + NSWORDS) / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) *s_nsingle = 0;
+        if (threadIdx.x == 0) { *s_nsingle = 0; s_cursor[1] = 0; }
+        if (VIRT && threadIdx.x == 0) { vlog->n_spec = 0; vlog->n_hdr = 0; vlog->overflow = 0; }
         __syncthreads();
 #ifdef KF_PIECE_TIMING
         { long long tw3 = clock64(); if (*s_nsingle == 12345u) tw3 = 0; KF_TADD(2, tw3 - tw2); if (threadIdx.x == 0) atomicAdd(&g_piece_timing[3], 1ull); }
+#endif
+#ifdef KF_DEBUG_TRAP_RECOUNT
+        if (!ok) __trap();
 #endif
         if (!ok) {
             // a 16-bit half wrapped: recount this CTA's part of the file exactly, straight into its (zeroed) row
@@ -1408,7 +1762,17 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
             const uint64_t lo_b = file_lo > F0 ? file_lo : F0, hi_b = file_hi < F1 ? file_hi : F1;
             const uint64_t span = (hi_b - lo_b + NWARPS - 1) / NWARPS;
             const uint64_t a0 = lo_b + (uint64_t)warp * span, a1 = (a0 + span < hi_b) ? a0 + span : hi_b;
-            if (a0 < hi_b) {
+            if (VIRT) {
+                // byte ownership (k-mers whose first base lies in the piece): whole chunks per warp, the state at a warp's
+                // first chunk from the exact backward scan of the range processor
+                const uint64_t c_lo = lo_b / CHUNK, c_hi = (hi_b + CHUNK - 1) / CHUNK;
+                const uint64_t per = (c_hi - c_lo + NWARPS - 1) / NWARPS;
+                const uint64_t wc0 = c_lo + (uint64_t)warp * per, wc1 = wc0 + per < c_hi ? wc0 + per : c_hi;
+                if (wc0 < wc1) {
+                    const uint64_t o1 = wc1 * CHUNK < hi_b ? wc1 * CHUNK : hi_b;
+                    fasta_process_range<7, false, 2>(src, (uint32_t)wc0, (uint32_t)wc1, (uint32_t)(F0 / CHUNK), gs, wc0 * CHUNK, o1, false);
+                }
+            } else if (a0 < hi_b) {
                 const uint64_t lo = fasta_line_start_at_or_after(src, a0, F0, F1, lane);
                 const uint64_t hi = (a1 >= hi_b && hi_b >= F1) ? F1 : fasta_line_start_at_or_after(src, a1, F0, F1, lane);
                 lg_generic_region<7>(src, lo, hi, (uint32_t)(F0 / CHUNK), gs);
@@ -1422,7 +1786,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     KF_T(tk0);
     for (int t = cta_begin[blockIdx.x * cta_stride]; t < t1;) {
         const Tile T = tiles[t];
-        if (file_P[T.file] != (uint32_t)G::P) { ++t; continue; }
+        if (file_P[T.file] != MYP) { ++t; continue; }
         uint32_t n_chunks = T.n_chunks;
         int te = t + 1;
         while (te < t1 && tiles[te].file == T.file && tiles[te].first_chunk == T.first_chunk + n_chunks) {
@@ -1441,16 +1805,93 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         const uint64_t F0 = file_off[T.file], F1 = F0 + file_len[T.file];
         const uint64_t Xe = X1 < F1 ? X1 : F1;
         KF_T(ta0);
-        if (threadIdx.x == 0) *s_cursor = 0;
-        // every warp finds the piece's anchor (its first line start) by itself: same loads, served by L1 after the first
-        const uint64_t A = fasta_line_start_at_or_after(GlobalSrc{arena}, X0, F0, F1, lane);
-        __syncthreads();
-        KF_T(ta1);
-        if (threadIdx.x == 0) KF_TADD(5, ta1 - ta0);
+        if (threadIdx.x == 0) { *s_cursor = 0; *s_found = 0ull; }
         SingleSink gs;
         gs.h = single16;
         gs.n = s_nsingle;
+        KF_T(ta1);
+#ifdef KF_VL_TIMING
+        const long long t_p0 = clock64();
+#endif
+        if (VIRT) {
+            // the state at the piece's first byte.  A piece that begins inside the file: the last '\n' before X0 decides --
+            // exact backward scan by the whole CTA, four chunks per warp and round (the line may be megabytes long)
+            uint32_t st = 2u;
+            if (X0 > F0) {
+                // Groups of BS chunks counted backwards from X0; warp w takes the groups w, w + NWARPS, ...  No barrier in the
+                // loop: a warp stops when it has found a '\n' (its later groups lie further back), when it has passed the
+                // file's start, or when another warp has found one nearer to X0 than its next group.  Two groups in flight.
+                const uint64_t c_first = F0 / CHUNK, c_top = X0 / CHUNK;   // chunks [c_first, c_top) lie before the piece
+                constexpr int BS = 8;
+                const uint64_t n_groups = (c_top - c_first + BS - 1) / BS;
+                auto load_group = [&](uint64_t gi, uint4 (&w)[BS]) {
+#pragma unroll
+                    for (int u = 0; u < BS; u++) {
+                        const uint64_t back = gi * BS + (uint64_t)u + 1;
+                        w[u] = (gi < n_groups && c_top - c_first >= back) ? __ldg(reinterpret_cast<const uint4 *>(arena) + (c_top - back) * 32 + lane)
+                                                                          : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                };
+                auto scan_group = [&](uint64_t gi, const uint4 (&w)[BS]) -> bool {   // true: found (and published)
+                    uint32_t best = 0;   // 1 + offset (from F0) of the last '\n' this lane has seen, 0: none
+#pragma unroll
+                    for (int u = BS - 1; u >= 0; u--) {   // (u = 0 is the chunk nearest to X0: looked at last, so it wins)
+                        const uint32_t m = newline_mask16(w[u]);
+                        if (m) best = (uint32_t)((c_top - (gi * BS + (uint64_t)u + 1)) * CHUNK + (uint64_t)lane * 16 + (uint64_t)(31 - __clz((int)m)) - F0) + 1u;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { const uint32_t t = __shfl_xor_sync(FULL, best, o); best = t > best ? t : best; }
+                    if (best && lane == 0) atomicMax(s_found, F0 + (uint64_t)best);   // = position of that '\n' + 1: a line start
+                    return best != 0;
+                };
+                auto worth = [&](uint64_t gi) -> bool {   // may group gi still hold the nearest '\n'?
+                    if (gi >= n_groups) return false;
+                    unsigned long long fnd = 0;
+                    if (lane == 0) fnd = *reinterpret_cast<volatile unsigned long long *>(s_found);
+                    fnd = __shfl_sync(FULL, fnd, 0);                    // (one answer per warp)
+                    return fnd < (c_top - gi * BS) * (uint64_t)CHUNK;   // (the group's bytes lie below that position)
+                };
+                __syncthreads();   // s_found = 0 is visible
+                {
+                    uint4 wa[BS], wb[BS];
+                    uint64_t gi = (uint64_t)warp;
+                    load_group(gi, wa);
+                    for (;;) {
+                        if (!worth(gi)) break;
+                        load_group(gi + NWARPS, wb);
+                        if (scan_group(gi, wa)) break;
+                        gi += NWARPS;
+                        if (!worth(gi)) break;
+                        load_group(gi + NWARPS, wa);
+                        if (scan_group(gi, wb)) break;
+                        gi += NWARPS;
+                    }
+                }
+                __syncthreads();
+                const uint64_t ls = *s_found;   // start of the line that holds X0 (0: the file's first line, a header)
+                st = ls == 0ull ? 1u : (ls == X0 ? 2u : (arena[ls] == (uint8_t)'>' ? 1u : 0u));
+            }
+            __syncthreads();
+#ifdef KF_VL_TIMING
+            const long long t_p1 = clock64();
+#endif
+            vl_process_piece<BASE>(arena, X0, Xe, st, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs, vlog);
+#ifdef KF_VL_TIMING
+            __syncthreads();
+            if (threadIdx.x == 0 && blockIdx.x < 160) {
+                const long long t_p2 = clock64();
+                g_vl_cta[4 * blockIdx.x + 0] += (unsigned long long)(t_p2 - t_p0);
+                g_vl_cta[4 * blockIdx.x + 1] += 1;
+                if ((unsigned long long)(t_p2 - t_p1) > g_vl_cta[4 * blockIdx.x + 2]) g_vl_cta[4 * blockIdx.x + 2] = (unsigned long long)(t_p2 - t_p1);
+                g_vl_cta[4 * blockIdx.x + 3] += (unsigned long long)(t_p1 - t_p0);
+            }
+#endif
+        } else {
+        // every warp finds the piece's anchor (its first line start) by itself: same loads, served by L1 after the first
+        const uint64_t A = fasta_line_start_at_or_after(GlobalSrc{arena}, X0, F0, F1, lane);
+        __syncthreads();
         ln_process_piece<LW, BASE>(arena, A, Xe, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
+        }
         KF_T(ta2);
         KF_TADD(0, ta2 - ta1);
         t = te;
@@ -1470,21 +1911,6 @@ __global__ void kf_smem_base_probe_kernel(uint32_t *out) {
 }
 #endif
 
-// byte-mask helpers (also used by the FASTQ kernels below)
-__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v) {   // 0x80 in every byte of v that is non-zero
-    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t movemask4(uint32_t f) {       // f has 0x80 flags; -> 4-bit mask, byte 0 in bit 0
-    return ((f >> 7) * 0x01020408u) >> 24;
-}
-__device__ __forceinline__ uint32_t newline_mask16(const uint4 w) {
-    const uint32_t n0 = ~nonzero_bytes(w.x ^ 0x0A0A0A0Au) & 0x80808080u;
-    const uint32_t n1 = ~nonzero_bytes(w.y ^ 0x0A0A0A0Au) & 0x80808080u;
-    const uint32_t n2 = ~nonzero_bytes(w.z ^ 0x0A0A0A0Au) & 0x80808080u;
-    const uint32_t n3 = ~nonzero_bytes(w.w ^ 0x0A0A0A0Au) & 0x80808080u;
-    return movemask4(n0) | (movemask4(n1) << 4) | (movemask4(n2) << 8) | (movemask4(n3) << 12);
-}
-
 // Line width of each FASTA file, judged from its first lines: P = LW + 1 if the three lines after the
 // header are LW bases wide (LW one of 60/70/80), else 0 (generic kernel).  One warp per file: 512-byte chunks,
 // newline masks per lane, the first four '\n' positions picked out of the ballots.
@@ -1492,7 +1918,7 @@ __global__ void __launch_bounds__(128)
 probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
                         const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
                         uint32_t force_generic, uint32_t *__restrict__ file_P,
-                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80 */,
+                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80, [4] long lines */,
                         unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row, uint32_t row_bins) {
     const int lane = threadIdx.x & 31;
     const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -1500,7 +1926,7 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
     uint32_t P = 0;
     if (!force_generic && formats[f] == (uint8_t)'>') {
         const uint64_t F0 = file_off[f], L = file_len[f];
-        const uint64_t nchunks = (L + CHUNK - 1) / CHUNK < 128 ? (L + CHUNK - 1) / CHUNK : 128;   // look at most 64 KiB in
+        const uint64_t nchunks = (L + CHUNK - 1) / CHUNK < 16 ? (L + CHUNK - 1) / CHUNK : 16;   // look at most 8 KiB in
         uint64_t nlpos[4];
         int found = 0;
         for (uint64_t c = 0; c < nchunks && found < 4; c++) {
@@ -1523,10 +1949,17 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
             const uint64_t w0 = nlpos[1] - nlpos[0] - 1, w1 = nlpos[2] - nlpos[1] - 1, w2 = nlpos[3] - nlpos[2] - 1;
             if (w0 == w1 && w1 == w2 && (w0 == 60 || w0 == 70 || w0 == 80)) P = (uint32_t)w0 + 1;
         }
+        // long lines (one line per contig, as assemblers write them): fewer than four '\n' in the first 8 KiB, or a line of
+        // 2 KiB and more among the first ones -> virtual lines (exact for any structure; fast when '\n' are rare)
+        if (P == 0 && L >= 32768) {
+            bool longl = found < 4;
+            for (int i = 1; i < found; i++) longl = longl || nlpos[i] - nlpos[i - 1] > 2048;
+            if (longl) P = KF_P_VIRTUAL;
+        }
     }
     if (lane == 0) {
         file_P[f] = P;
-        atomicAdd(width_counts + (P ? (P - 51) / 10 : 0), 1u);
+        atomicAdd(width_counts + (P == KF_P_VIRTUAL ? 4 : P ? (P - 51) / 10 : 0), 1u);
     }
     // Forward rows: the line kernel WRITES every bin of the rows of the files it takes; every other file's rows are
     // added to with atomics (generic / FASTQ kernels) or never touched (unsupported input), so they are zeroed here --

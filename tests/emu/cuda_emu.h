@@ -117,6 +117,11 @@ inline T __shfl_up_sync(unsigned, T v, int d) {
     T r = (T)emu::exchange((uint64_t)v, l - d < 0 ? l : l - d);
     return r;
 }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

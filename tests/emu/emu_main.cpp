@@ -33,6 +33,9 @@ void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::functio
 }  // namespace emu
 
 namespace kf { void canonical_codes(int k, std::vector<uint32_t> &out); }
+#ifdef KF_EMU_RANDOM_UNITS
+namespace kf { unsigned g_emu_seed = 1; }   // unit sizes of the line kernels are drawn from it (env KF_EMU_SEED)
+#endif
 
 using namespace kf;
 
@@ -44,20 +47,22 @@ static void run(const uint8_t *arena, const std::vector<Tile> &tiles, const std:
     else    emu::launch(grid, THREADS, smem, [&]() { count_fasta_smem_kernel<K, THREADS, 1, false>(arena, tiles.data(), cta_begin.data(), fwd, file_row, file_P, wc); });
 }
 
-template <int LW, int THREADS>
+template <int LW, int THREADS, bool VIRT = false>
 static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
                    const uint32_t *file_P, const uint64_t *off, const uint64_t *len, unsigned long long *fwd,
                    const uint32_t *file_row, const uint32_t *file_first_cta, const uint32_t *wc) {
-    using G = LineGeom<LW>;
     constexpr int NW = THREADS / 32;
-    size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
+    size_t smem = lines_kernel_smem<LW>(NW);
     emu::launch(grid, THREADS, smem, [&]() {
-        count_fasta_lines_kernel<LW, THREADS, 0u>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
+        count_fasta_lines_kernel<LW, THREADS, 0u, VIRT>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
     });
 }
 
 int main(int argc, char **argv) {
     if (argc < 8) { fprintf(stderr, "usage\n"); return 2; }
+#ifdef KF_EMU_RANDOM_UNITS
+    if (const char *e = getenv("KF_EMU_SEED")) kf::g_emu_seed = (unsigned)atoi(e);
+#endif
     int k = atoi(argv[1]), threads = atoi(argv[2]), grid = atoi(argv[3]);
     bool fw = atoi(argv[4]) != 0;
     uint32_t tile_chunks = (uint32_t)atoi(argv[5]);
@@ -196,23 +201,26 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> formats(n);
     for (int i = 0; i < n; i++) formats[i] = len[i] ? arena[off[i]] : 0;
     std::vector<uint32_t> file_P(n, 0);
-    std::vector<uint32_t> wc(4, 0);
+    std::vector<uint32_t> wc(8, 0);
     const bool lg = use_lg && k == 7 && !fw;
     emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data(), fwd.data(), file_row.data(), (uint32_t)NB); });
     if (lg) {
         if (threads == 512) {
             run_lg<80, 512>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<80, 512, true>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         } else if (threads == 64) {
             run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
             run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
             run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<80, 64, true>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         } else {
             run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
             run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
             run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+            run_lg<80, 32, true>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         }
-        int nlg = 0; for (auto P : file_P) nlg += P != 0;
-        fprintf(stderr, "linegrid files: %d of %d\n", nlg, n);
+        int nlg = 0, nvl = 0; for (auto P : file_P) { nlg += P != 0; nvl += P == KF_P_VIRTUAL; }
+        fprintf(stderr, "linegrid files: %d of %d (virtual lines: %d)\n", nlg, n, nvl);
     }
 #define RUN(KK) case KK: if (threads == 512) run<KK, 512>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else if (threads == 64) run<KK, 64>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); else run<KK, 32>(arena.data(), tiles, cta_begin, grid, fw, fwd.data(), file_row.data(), file_P.data(), wc.data()); break;
     switch (k) { RUN(3) RUN(4) RUN(5) RUN(7) default: fprintf(stderr, "k not built in emu\n"); return 2; }

@@ -89,3 +89,46 @@ def rand_fasta_grid(rng: random.Random) -> bytes:
     if rng.random() < 0.3 and out.endswith(b'\n'):
         out = out[:-1]
     return bytes(out)
+
+
+def rand_fasta_long(rng: random.Random) -> bytes:
+    """Long-line ("unwrapped") FASTA as assemblers write it -- one line per contig, kilobases long -- with everything
+    that can go wrong around it: contigs shorter than k, N runs, lower case, IUPAC codes, records split over a few long
+    lines (k-mers span the '\\n'), blank lines, CRLF, headers of up to 3,000 bytes made of A/C/G/T text (longer than the
+    kernel's look-back: a unit boundary inside one must be found out), '>' inside sequence lines, missing final newline.
+    At least 32 KiB, so that the width probe takes it for a long-line file."""
+    out = bytearray()
+    big = rng.random() < 0.5
+    while len(out) < (rng.choice([33000, 60000, 150000]) if big else 33000):
+        kind = rng.random()
+        if kind < 0.15:
+            hl = rng.choice([300, 800, 3000])
+            hdr = ''.join(rng.choice('ACGT') for _ in range(hl))          # looks like sequence
+        elif kind < 0.3:
+            hl = rng.choice([79, 80, 81, 255, 256, 257])
+            hdr = ''.join(rng.choice('ACGTacgtN >|_.0123456789xyz') for _ in range(hl))
+        else:
+            hdr = 'contig_%d length=%d' % (len(out), rng.randint(1, 10 ** 6))
+        out += b'>' + hdr.encode() + b'\n'
+        L = rng.choice([0, 1, 6, 7, 8, 79, 80, 81, 86, 87, 160, 2559, 2560, 2561, 2566, 2640, 5120, 12000, 40000]) if rng.random() < 0.6 \
+            else rng.randint(0, 30000)
+        alphabet = 'ACGT' * 40 + 'acgt' * 3 + ('N' if rng.random() < 0.4 else '') + ('RY>-' if rng.random() < 0.1 else '')
+        seq = ''.join(rng.choice(alphabet) for _ in range(L))
+        for _ in range(rng.choice([0, 0, 1, 3])):
+            if L > 200:
+                p = rng.randint(0, L - 100)
+                n = rng.choice([1, 5, 79, 80, 81, 200])
+                seq = seq[:p] + 'N' * n + seq[p + n:]
+        seq = seq[:L]
+        eol = b'\r\n' if rng.random() < 0.04 else b'\n'
+        nlines = 1 if rng.random() < 0.8 else rng.randint(2, 4)
+        cuts = sorted(rng.randint(0, len(seq)) for _ in range(nlines - 1)) + [len(seq)]
+        a = 0
+        for c in cuts:
+            out += seq[a:c].encode() + eol
+            a = c
+            if rng.random() < 0.05:
+                out += b'\n' * rng.randint(1, 2)
+    if rng.random() < 0.3 and out.endswith(b'\n'):
+        out = out[:-1]
+    return bytes(out)

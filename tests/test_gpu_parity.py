@@ -575,3 +575,31 @@ def test_get_kmers_end_to_end(eng, toy_inputs, tmp_path, capsys):
         assert not (outd / ("noseq_k%d.npy" % k)).exists() and not (outd / ("ignored_k%d.npy" % k)).exists()
     out = capsys.readouterr().out
     assert "--- Processing G000830275sub ---" in out and "Warning: No valid ATCG k-mers found in noseq" in out and "Saved: " in out
+
+
+# ---- round 2: long-line ("unwrapped") FASTA through virtual lines ----
+@pytest.mark.parametrize("seed0", [0, 100])
+def test_fuzz_long_line_fasta(eng, seed0):
+    """One line per contig (what assemblers write) and everything around it -- the virtual-line path of the line kernel
+    against the oracle: 60 files per call, mixed with wrapped and generic files in one batch."""
+    from fuzzgen import rand_fasta_long
+    rng = random.Random(4000 + seed0)
+    bufs = [rand_fasta_long(rng) for _ in range(60)] + [rand_fasta_grid(rng) for _ in range(4)] + [rand_fasta(rng) for _ in range(4)]
+    rng.shuffle(bufs)
+    check_against_oracle(eng, bufs, 7)
+
+
+def test_unwrapped_genomes_vs_c_oracle(eng):
+    """Unwrapped synthetic genomes: 1 contig (one 5 Mbp line: pieces that begin megabytes into a line) and up to 50 contigs,
+    every row against the C oracle; and the same bases wrapped at 80 columns give the same counts."""
+    flat1 = [kfsynth.synth_fasta(31, i, 5_000_000, line_width=10 ** 9, max_contigs=1) for i in range(12)]
+    flat50 = [kfsynth.synth_fasta(32, i, 5_000_000, line_width=10 ** 9, max_contigs=50, n_runs=40) for i in range(12)]
+    small = [kfsynth.synth_fasta(33, i, 60_000, line_width=10 ** 9, max_contigs=200) for i in range(8)]
+    bufs = flat1 + flat50 + small
+    counts, freq, totals, status = eng.count_buffers(bufs, k=7)
+    assert (status == 0).all()
+    ref, _, _ = c_oracle.count_buffers_mt(bufs, 7, threads=8, want_freq=False)
+    assert np.array_equal(counts, ref)
+    wrapped = [kfsynth.synth_fasta(31, i, 5_000_000, line_width=80, max_contigs=1) for i in range(3)]
+    cw = eng.count_buffers(wrapped, k=7)[0]
+    assert np.array_equal(cw, counts[:3])

@@ -246,3 +246,47 @@ def test_emulated_sparse_sort_rle_fuzz(tmp_path):
             rc, rn, rt = o.sparse_counts_bytes(open(f, "rb").read(), k)
             assert tot == rt, (s, k, f)
             assert np.array_equal(codes, rc) and np.array_equal(counts, rn), (s, k, grid, thr, tile, f)
+
+
+BIN_RU = os.path.join(EMU, "emu_main_ru")
+
+
+@pytest.fixture(scope="module")
+def emu_binary_random_units(emu_binary):
+    srcs = [os.path.join(EMU, "emu_main.cpp"), os.path.join(ROOT, "kf2vecfsw_b200", "csrc", "kf_host.cpp")]
+    deps = srcs + [os.path.join(EMU, "cuda_emu.h"), os.path.join(ROOT, "kf2vecfsw_b200", "csrc", "kf_kernels.cuh")]
+    if not os.path.exists(BIN_RU) or any(os.path.getmtime(d) > os.path.getmtime(BIN_RU) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DKF_EMU", "-DKF_EMU_RANDOM_UNITS", "-I", EMU, "-I", os.path.join(ROOT, "include"),
+                               "-pthread"] + srcs + ["-o", BIN_RU])
+
+
+def run_emu_bin(binary, k, threads, grid, tile_chunks, files, seed=1):
+    env = dict(os.environ, KF_EMU_SEED=str(seed))
+    p = subprocess.run([binary, str(k), str(threads), str(grid), "0", str(tile_chunks), "1"] + files, capture_output=True, text=True, check=True, env=env,
+                       timeout=120)
+    out = p.stdout.strip().split("\n")
+    return [(int(out[2 * i].split()[0]), np.array(out[2 * i].split()[1:], dtype=np.uint64)) for i in range(len(files))], p.stderr
+
+
+def test_emulated_virtual_lines_fuzz(tmp_path, emu_binary_random_units):
+    """Long-line FASTA through the virtual-line path of the line kernel: grid anywhere inside a line, unit states from
+    the 256-byte look-back or assumed and verified at the end of the piece (headers longer than the look-back force the
+    exact recount), breaks walked by the warp, pieces cut anywhere (tiles of 3 .. 64 chunks, 1 .. 4 CTAs).  Both the
+    production unit sizes and random ones (1 .. 5 windows: many unit boundaries)."""
+    from fuzzgen import rand_fasta_long
+    n_virtual = n_files = 0
+    for s in range(1200, 1236):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 2)):
+            p = str(tmp_path / ("v%d_%d.fa" % (s, i)))
+            open(p, "wb").write(rand_fasta_long(rng))
+            files.append(p)
+        grid, thr, tile = rng.randint(1, 4), rng.choice([32, 64]), rng.choice([3, 8, 17, 64])
+        res, err = run_emu_bin(BIN_RU if s % 2 else BIN, 7, thr, grid, tile, files, seed=s)
+        n_virtual += int(err.split("virtual lines: ")[1].split(")")[0])      # files the probe took for long-line files
+        n_files += len(files)
+        for f, (tot, counts) in zip(files, res):
+            ref = o.canonical_counts_bytes(open(f, "rb").read(), 7)
+            assert np.array_equal(counts, ref), (s, grid, thr, tile, f, int(ref.sum()), int(counts.sum()))
+    assert n_virtual >= 0.6 * n_files, (n_virtual, n_files)   # (a file whose first lines are all short goes to the generic kernel)
