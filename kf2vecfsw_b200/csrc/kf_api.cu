@@ -315,7 +315,8 @@ constexpr uint32_t LG_SMEM_BASE = 0x400;   // where dynamic shared memory begins
 template <int LW, uint32_t BASE, bool VIRT = false>
 int launch_linegrid_b(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
     constexpr int NW = THREADS_LG / 32;
-    const size_t smem = lines_kernel_smem<LW>(NW);
+    const size_t smem = lines_kernel_smem<LW, VIRT>(NW);
+    static_assert(lines_kernel_smem<LW, VIRT>(NW) <= 227 * 1024, "shared memory of the line kernel");
     auto kern = count_fasta_lines_kernel<LW, THREADS_LG, BASE, VIRT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
@@ -553,8 +554,11 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<70>(d_arena, grid, s);
             if (rc == KF_OK) rc = launch_linegrid<80, true>(d_arena, grid, s);   // long-line files: virtual lines
+            if (rc == KF_OK) rc = launch_linegrid<100>(d_arena, grid, s);
+            if (rc == KF_OK) rc = launch_linegrid<120>(d_arena, grid, s);
+            if (rc == KF_OK) rc = launch_linegrid<50>(d_arena, grid, s);
             if (rc != KF_OK) return rc;
-            g.last_launches += 4;
+            g.last_launches += 7;
         }
         // file indices inside tiles are batch-global; k >= 8 rows are relative to f0, k <= 7 rows come from d_file_row
         rc = launch_count(k, d_arena, grid, force_walker, f0, s);

@@ -875,6 +875,7 @@ __device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64
 //   rare paths : a line holding a non-ACGT byte (or whose 6 look-ahead bytes do) goes to the exact byte walker on
 //                global memory; a line that breaks the grid (short last line, header, other width) goes to the
 //                exact generic range processor up to the next sequence line, where the grid restarts.
+constexpr int LN_SCR_WORDS = 36;   // per-warp scratch: one line + look-ahead re-fetched from global memory (P + LA + 3 bytes at LW = 120: 130)
 template <int LW>
 struct LineGeom {
     static_assert(LW % 2 == 0 && LW >= 32 && LW <= 120, "line width");
@@ -1258,7 +1259,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             const uint64_t sl = curB + (uint64_t)j * G::P;
             const uint64_t wb = sl & ~3ull;
             KF_SYNCWARP();
-            if (lane < 24) wscr[lane] = __ldg(reinterpret_cast<const uint32_t *>(arena + wb) + lane);
+            for (int i = lane; i < LN_SCR_WORDS; i += 32) wscr[i] = __ldg(reinterpret_cast<const uint32_t *>(arena + wb) + i);
             KF_SYNCWARP();
             const uint8_t *lb = reinterpret_cast<const uint8_t *>(wscr) + (uint32_t)(sl & 3u);
             bool has_nl = false;
@@ -1620,11 +1621,15 @@ __device__ __forceinline__ void vl_process_piece(const uint8_t *__restrict__ are
 // VIRT: the files of this launch are long-line FASTA (file_P == KF_P_VIRTUAL), counted through virtual lines of 80 bytes
 // (vl_process_piece); LW must be 80 then (same shared-memory layout).
 constexpr uint32_t KF_P_VIRTUAL = 0xFFFFu;
+// the wrapped widths that have a line-kernel instantiation, and where the batch's count of such files is kept
+__host__ __device__ constexpr int line_width_slot(int lw) {   // index into width_counts (0 = generic kernel, 4 = long lines)
+    return lw == 60 ? 1 : lw == 70 ? 2 : lw == 80 ? 3 : lw == 100 ? 5 : lw == 120 ? 6 : lw == 50 ? 7 : 0;
+}
 // dynamic shared memory of count_fasta_lines_kernel: pair + singles histograms, one staging buffer and one barrier per
 // warp, per-warp scratch and partial sums, cursor words, the backward scan's result, the virtual-line log
-template <int LW> constexpr size_t lines_kernel_smem(int nwarps) {
+template <int LW, bool VIRT = false> constexpr size_t lines_kernel_smem(int nwarps) {
     return (32768 + 8192) * sizeof(uint32_t) + (size_t)nwarps * LineGeom<LW>::STAGE + (size_t)nwarps * sizeof(uint64_t) +
-           (27 * (size_t)nwarps + 4) * sizeof(uint32_t) + 16 + sizeof(VlLog);
+           ((LN_SCR_WORDS + 3) * (size_t)nwarps + 4) * sizeof(uint32_t) + 16 + (VIRT ? sizeof(VlLog) : 0);
 }
 template <int LW, int THREADS, uint32_t BASE, bool VIRT = false>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -1636,7 +1641,8 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     using G = LineGeom<LW>;
     static_assert(!VIRT || (LW == 80 && VL_STAGE <= G::STAGE), "virtual lines use the 80-column layout");
     constexpr uint32_t MYP = VIRT ? KF_P_VIRTUAL : (uint32_t)G::P;
-    if (width_counts[VIRT ? 4 : (LW - 50) / 10] == 0) return;   // no file of this kind in the batch (uniform exit)
+    static_assert(VIRT || line_width_slot(LW) != 0, "no slot for this width");
+    if (width_counts[VIRT ? 4 : line_width_slot(LW)] == 0) return;   // no file of this kind in the batch (uniform exit)
     constexpr int NWARPS = THREADS / 32;
     constexpr int NWORDS = 32768;
     constexpr int NB7 = 16384;
@@ -1649,8 +1655,8 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     uint32_t *single16 = smem + NWORDS;    // rare paths: 16,384 7-mer bins, two u16 halves per word
     uint8_t *stage_base = reinterpret_cast<uint8_t *>(single16 + NSWORDS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(stage_base + (size_t)NWARPS * G::STAGE);
-    uint32_t *s_wscr = reinterpret_cast<uint32_t *>(bars + NWARPS);   // per warp: 24 words, one dirty line re-fetched from global
-    uint32_t *s_part = s_wscr + 24 * NWARPS;                          // per warp: pairs issued | pair low-half sums | singles half sums
+    uint32_t *s_wscr = reinterpret_cast<uint32_t *>(bars + NWARPS);   // per warp: LN_SCR_WORDS words, one dirty line re-fetched from global
+    uint32_t *s_part = s_wscr + LN_SCR_WORDS * NWARPS;                          // per warp: pairs issued | pair low-half sums | singles half sums
     uint32_t *s_nsingle = s_part + 3 * NWARPS;                        // singles issued
     uint32_t *s_cursor = s_nsingle + 1;
     unsigned long long *s_found = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(s_cursor + 3) + 7) & ~(uintptr_t)7);
@@ -1875,7 +1881,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
 #ifdef KF_VL_TIMING
             const long long t_p1 = clock64();
 #endif
-            vl_process_piece<BASE>(arena, X0, Xe, st, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs, vlog);
+            vl_process_piece<BASE>(arena, X0, Xe, st, F0, F1, buf, s_wscr + LN_SCR_WORDS * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs, vlog);
 #ifdef KF_VL_TIMING
             __syncthreads();
             if (threadIdx.x == 0 && blockIdx.x < 160) {
@@ -1890,7 +1896,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         // every warp finds the piece's anchor (its first line start) by itself: same loads, served by L1 after the first
         const uint64_t A = fasta_line_start_at_or_after(GlobalSrc{arena}, X0, F0, F1, lane);
         __syncthreads();
-        ln_process_piece<LW, BASE>(arena, A, Xe, F0, F1, buf, s_wscr + 24 * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
+        ln_process_piece<LW, BASE>(arena, A, Xe, F0, F1, buf, s_wscr + LN_SCR_WORDS * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
         }
         KF_T(ta2);
         KF_TADD(0, ta2 - ta1);
@@ -1918,7 +1924,7 @@ __global__ void __launch_bounds__(128)
 probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
                         const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
                         uint32_t force_generic, uint32_t *__restrict__ file_P,
-                        uint32_t *__restrict__ width_counts /* [0] generic, [1] 60, [2] 70, [3] 80, [4] long lines */,
+                        uint32_t *__restrict__ width_counts /* [line_width_slot()]: 0 generic, 1..3 60/70/80, 4 long lines, 5..7 100/120/50 */,
                         unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row, uint32_t row_bins) {
     const int lane = threadIdx.x & 31;
     const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -1947,7 +1953,7 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
         }
         if (found == 4) {
             const uint64_t w0 = nlpos[1] - nlpos[0] - 1, w1 = nlpos[2] - nlpos[1] - 1, w2 = nlpos[3] - nlpos[2] - 1;
-            if (w0 == w1 && w1 == w2 && (w0 == 60 || w0 == 70 || w0 == 80)) P = (uint32_t)w0 + 1;
+            if (w0 == w1 && w1 == w2 && line_width_slot((int)w0) != 0) P = (uint32_t)w0 + 1;
         }
         // long lines (one line per contig, as assemblers write them): fewer than four '\n' in the first 8 KiB, or a line of
         // 2 KiB and more among the first ones -> virtual lines (exact for any structure; fast when '\n' are rare)
@@ -1959,7 +1965,7 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
     }
     if (lane == 0) {
         file_P[f] = P;
-        atomicAdd(width_counts + (P == KF_P_VIRTUAL ? 4 : P ? (P - 51) / 10 : 0), 1u);
+        atomicAdd(width_counts + (P == KF_P_VIRTUAL ? 4 : P ? line_width_slot((int)P - 1) : 0), 1u);
     }
     // Forward rows: the line kernel WRITES every bin of the rows of the files it takes; every other file's rows are
     // added to with atomics (generic / FASTQ kernels) or never touched (unsupported input), so they are zeroed here --

@@ -163,7 +163,7 @@ template <int THREADS>
 void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
-    const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
+    const size_t smem = lines_kernel_smem<80>(NW);
     auto kern = count_fasta_lines_kernel<80, THREADS, 0x400u>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t n_chunks = (uint32_t)(bytes / CHUNK);
@@ -234,7 +234,7 @@ template <int THREADS>
 void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms, int max_contigs = 0, int n_runs = 0, long long bases = 0) {
     using G = LineGeom<80>;
     constexpr int NW = THREADS / 32;
-    const size_t smem = (32768 + 8192) * sizeof(uint32_t) + (size_t)NW * G::STAGE + NW * sizeof(uint64_t) + (27 * NW + 4) * sizeof(uint32_t);
+    const size_t smem = lines_kernel_smem<80>(NW);
     auto kern = count_fasta_lines_kernel<80, THREADS, 0x400u>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     size_t slot = (arena_bytes / nfiles) / CHUNK * CHUNK;
