@@ -42,6 +42,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-files", action="store_true", help="skip the files-on-disk -> .kf end-to-end measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configs (line widths, FASTQ, large k)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --genomes per GPU; strong: --genomes-total sharded over the GPUs (BASELINE.json configs[2])")
+    ap.add_argument("--genomes-total", type=int, default=10000, help="strong scaling: genomes of the whole job")
     return ap.parse_args()
 
 
@@ -157,6 +161,127 @@ def workload_name(genomes, bases, k, world):
             "BASELINE.json configs[%d]" % (genomes, bases, k, 1 if world == 1 else 2))
 
 
+def common_config(genomes, bases, k, world, scaling="weak", total=None):
+    """The `config` object: identical for both arms (`--impl ours` and `--impl reference`) of one launch."""
+    c = {"workload": workload_name(genomes, bases, k, world), "genomes_per_gpu": genomes, "bases_per_genome": bases, "k": k,
+         "l2_policy": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed" % (genomes * bases * 1.0126 / 1e9),
+         "parallelism": "genome-sharded, one process per GPU, no collective on the counting path"
+                        + ("; all-gather of the [N,8192] fp32 matrix of every step inside the timed region" if world > 1 else "")}
+    if scaling == "strong":
+        c["workload"] = ("%d synthetic bacterial-size genomes x %d bases (80-col FASTA), k=%d, sharded over %d GPU(s), [%d, 8192] fp32 matrix "
+                         "gathered in file order; BASELINE.json configs[2]" % (total, bases, k, world, total))
+        c["genomes_total"] = total
+    return c
+
+
+def peak_hbm():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def other_configs(engine, dev, threads, steps=5):
+    """BASELINE.json configs[3] (FASTQ), configs[4] (large k) and the k = 7 line-width variants, each with its own roofline
+    (algorithmic bytes / CUDA-event time of the counting kernels) and CPU baseline (C oracle, all host threads, bounded
+    sample).  Inputs resident in HBM; rank 0 of a 1-GPU run only."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle
+    peak, _ = peak_hbm()
+    out = {}
+
+    def timed_dense(arena, k, n, want_freq=True):
+        V = engine.vocab_size(k)
+        counts = torch.empty((n, V), dtype=torch.int64, device=dev)
+        freq = torch.empty((n, V), dtype=torch.float64, device=dev) if want_freq else None
+        ms, km = [], []
+        for _ in range(steps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); engine.count_device(arena, k=k, counts=counts, freq=freq); e1.record(); torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1)); km.append(engine.last_count_kernel_ms())
+        return sum(ms[1:]) / steps, sum(km[1:]) / steps, counts, V
+
+    def cpu(bufs, k):
+        t0 = time.perf_counter()
+        ref, _, _ = c_oracle.count_buffers_mt(bufs, k, threads, want_freq=True)
+        return time.perf_counter() - t0, ref
+
+    def entry(name, workload, bases, step_ms, kern_ms, alg_bytes, kernel, cpu_bases, cpu_s, cpu_sample, ok, **kw):
+        out[name] = dict({"workload": workload, "value": bases / step_ms / 1e6, "unit": UNIT, "ms_per_step": step_ms,
+                          "roofline": {"bound": "hbm", "achieved": alg_bytes / kern_ms / 1e6, "peak": peak, "unit": "GB/s",
+                                       "frac": alg_bytes / kern_ms / 1e6 / peak, "kernel": kernel, "kernel_ms": kern_ms,
+                                       "algorithmic_bytes_per_launch": int(alg_bytes)},
+                          "roofline_step": {"frac": alg_bytes / step_ms / 1e6 / peak, "window": "memsets + probe + counting + fold/normalise"},
+                          "cpu_baseline": {"value": cpu_bases / cpu_s / 1e9, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample},
+                          "parity_ok": bool(ok)}, **kw)
+
+    # ---- k = 7, other line structures: unwrapped (one line per contig), 100 and 60 columns ----
+    for name, lw, G7, kern in (("k7_unwrapped", 10 ** 9, 1000, "count_fasta_lines_kernel, virtual lines of 80 bytes (vl_process_piece)"),
+                               ("k7_100col", 100, 500, "count_fasta_lines_kernel, ln_process_piece<100>"),
+                               ("k7_60col", 60, 500, "count_fasta_lines_kernel, ln_process_piece<60>")):
+        with ThreadPoolExecutor(threads) as ex:
+            fa = list(ex.map(lambda i: kfsynth.synth_fasta(SEED, i, 5_000_000, line_width=lw), range(G7)))
+        arena = engine.DeviceArena(fa, device=dev)
+        step_ms, kern_ms, counts, V = timed_dense(arena, 7, G7)
+        dt, ref = cpu(fa[:threads * 2], 7)
+        ok = np.array_equal(ref[:4], counts[:4].cpu().numpy().astype(np.uint64))
+        entry(name, "%d synthetic genomes x 5 Mbp, k=7, %s" % (G7, "unwrapped FASTA (one line per contig)" if lw > 1000 else "%d-column FASTA" % lw),
+              G7 * 5e6, step_ms, kern_ms, arena.file_bytes + G7 * V * 12, kern, threads * 2 * 5e6, dt, "%d of the genomes, oracle/kf_oracle.c" % (threads * 2), ok)
+        del arena, counts, fa
+    # ---- configs[3]: FASTQ query reads, 150 bp, 30x of 5 Mbp, N-containing ----
+    n_samples, n_reads = 8, 1_000_000
+    with ThreadPoolExecutor(threads) as ex:
+        fq = list(ex.map(lambda i: kfsynth.synth_fastq(SEED, i, 5_000_000, n_reads, 150), range(n_samples)))
+    arena = engine.DeviceArena(fq, device=dev)
+    step_ms, kern_ms, counts, V = timed_dense(arena, 7, n_samples)
+    dt, ref = cpu(fq[:2], 7)
+    ok = np.array_equal(ref, counts[:2].cpu().numpy().astype(np.uint64)) and bool((engine.last_file_status(arena) == 0).all())
+    entry("fastq_k7", "BASELINE.json configs[3]: %d FASTQ samples x %d reads x 150 bp (30x of 5 Mbp, N-containing), k=7" % (n_samples, n_reads),
+          n_samples * n_reads * 150, step_ms, kern_ms, arena.file_bytes + n_samples * V * 12, "count_fastq_smem_kernel<7>",
+          2 * n_reads * 150, dt, "2 of the samples, oracle/kf_oracle.c", ok, bytes_per_base=arena.file_bytes / (n_samples * n_reads * 150))
+    del arena, counts, fq
+    # ---- configs[4]: large-k sweep on 5 Mbp genomes ----
+    GL = 296
+    with ThreadPoolExecutor(threads) as ex:
+        fa = list(ex.map(lambda i: kfsynth.synth_fasta(SEED, i, 5_000_000), range(GL)))
+    arena = engine.DeviceArena(fa, device=dev)
+    for k in (8, 9, 10):
+        step_ms, kern_ms, counts, V = timed_dense(arena, k, GL, want_freq=False)
+        dt, ref = cpu(fa[:4], k)
+        ok = np.array_equal(ref, counts[:4].cpu().numpy().astype(np.uint64))
+        entry("large_k%d" % k, "BASELINE.json configs[4]: %d synthetic genomes x 5 Mbp, k=%d, dense canonical rows" % (GL, k), GL * 5e6, step_ms,
+              kern_ms, arena.file_bytes + GL * V * 12, "count_fasta_part_kernel<%d> (partitioned shared-memory histogram) + tiled fold" % k,
+              4 * 5e6, dt, "4 of the genomes, oracle/kf_oracle.c", ok)
+        del counts
+    # k = 12: sparse (observed canonical k-mers, sorted) -- the sort-and-run-length path
+    GS = 64
+    arena_s = engine.DeviceArena(fa[:GS], device=dev)
+    ms = []
+    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        _, _, row_off, _, _ = engine.sparse_count_device(arena_s, 12, fetch=False)
+        torch.cuda.synchronize(dev)
+        ms.append((time.perf_counter() - t0) * 1e3)
+    codes, cnts, row_off, totals, _ = engine.sparse_count_device(arena_s, 12)
+    t0 = time.perf_counter()
+    rc, rn, rt = c_oracle.count_sparse(fa[0].tobytes(), 12)
+    dt = time.perf_counter() - t0
+    a, e = int(row_off[0]), int(row_off[1])
+    ok = rt == int(totals[0]) and np.array_equal(codes[a:e], rc) and np.array_equal(cnts[a:e].astype(np.uint64), rn)
+    entries = int(row_off[-1])
+    engine.sparse_release()
+    step_ms = min(ms[1:])
+    entry("large_k12_sparse", "BASELINE.json configs[4]: %d synthetic genomes x 5 Mbp, k=12, sparse (code, count) output sorted by code" % GS,
+          GS * 5e6, step_ms, step_ms, arena_s.file_bytes + entries * 12, "sparse_extract / sparse_sort / sparse_emit (whole call, host-timed: it "
+          "synchronises to size the output)", 5e6, dt, "1 genome, 1 thread (sort + run lengths), oracle/kf_oracle.c", ok, entries=entries)
+    out["large_k12_sparse"]["cpu_baseline"]["cores"] = 1
+    del arena, arena_s, fa
+    return out
+
+
 # SMs left to the overlapped all-gather when N > 1 (measured on 8 B200: 8 CTAs move the 262 MB gather in about the time
 # of one counting step, 4 are too few; 2 GPUs exchange a quarter of that)
 NCCL_CTAS = int(os.environ.get("KF_BENCH_NCCL_CTAS", "0"))
@@ -178,11 +303,9 @@ def main():
             "impl": "reference", "metric": METRIC, "value": gb, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 counts / f64 frequencies", "data": "synthetic",
-            "config": {"workload": workload_name(args.genomes, args.bases, args.k, args.gpus),
-                       "genomes_per_gpu": args.genomes, "bases_per_genome": args.bases, "k": args.k,
-                       "reference_arm": "CPU restatement of jellyfish count -C + dump -c + vocabulary merge + normalise "
-                                        "(oracle/kf_oracle.c; the Jellyfish binary is not in the image), all host threads, "
-                                        "each step a bounded sample of the workload: " + sample},
+            "config": common_config(args.genomes, args.bases, args.k, args.gpus),
+            "reference_arm": "CPU restatement of jellyfish count -C + dump -c + vocabulary merge + normalise (oracle/kf_oracle.c; the "
+                             "Jellyfish binary is not in the image), all host threads, each step a bounded sample of the workload: " + sample,
             "cpu_baseline": {"value": gb, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": gb, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -350,12 +473,15 @@ def main():
         finally:
             shutil.rmtree(root, ignore_errors=True)
 
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        del arena, counts, freq, feat, host
+        views = None
+        torch.cuda.empty_cache()
+        configs = other_configs(engine, dev, threads)
+
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src = peak_hbm()
         alg_bytes = file_bytes + G * V * 4 + G * V * 8          # BASELINE.md section 3, per rank
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from one `ncu --set full` capture of this
         # command (tools/ncu_summary.py writes the file); only quoted when it was taken on the same workload
@@ -370,18 +496,22 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 shared-memory counts -> u64 counts, f64 frequencies", "data": "synthetic",
-            "config": {"workload": workload_name(G, NB, k, world),
-                       "genomes_per_gpu": G, "bases_per_genome": NB, "k": k, "file_bytes_per_gpu": int(file_bytes),
-                       "l2_policy": "inputs (%.2f GB per GPU) are larger than the 126 MB L2; no flush needed" % (file_bytes / 1e9),
-                       "parallelism": "genome-sharded, one process per GPU, no collective on the counting path"
-                                      + ("; NCCL all-gather of the [N,8192] fp32 matrix of every step inside the timed region" if world > 1 else "")
-                                      + (", the gather of step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, "
-                                         "counting kernels sized for %d of the SMs)" % (NCCL_CTAS, sms_used) if overlap else "")},
+            "config": common_config(G, NB, k, world),
+            "file_bytes_per_gpu": int(file_bytes),
+            "gather": ("all-gather of step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, counting kernels sized "
+                       "for %d of the SMs)" % (NCCL_CTAS, sms_used)) if overlap else ("NCCL all-gather after the counting" if world > 1 else None),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "count_fasta_lines_kernel<80,512> (+ width probe; the 60/70-column and generic launches "
-                                   "exit at once on this input)", "kernel_ms": float(kms.item()),
-                         "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
+                         "kernel": "count_fasta_lines_kernel (one launch for all line widths; ln_process_piece<80> on this input)",
+                         "window": "width probe + counting kernels (CUDA events on the launching stream inside the library; the launches for "
+                                   "other widths and the generic kernel exit at once on this input); the fold/normalise kernel is NOT in this "
+                                   "window -- see roofline_step",
+                         "kernel_ms": float(kms.item()), "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
+            "roofline_step": {"bound": "hbm", "achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak, "ms": ms_step,
+                              "window": "the whole step as timed for `value`: probe + counting + fold/normalise (BASELINE.md section 3)"
+                                        + (" + all-gather" if world > 1 else "")},
+            "configs": configs,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "e2e_files": e2e_files,

@@ -315,8 +315,9 @@ constexpr uint32_t LG_SMEM_BASE = 0x400;   // where dynamic shared memory begins
 template <int LW, uint32_t BASE, bool VIRT = false>
 int launch_linegrid_b(const uint8_t *d_arena, int grid_generic, cudaStream_t s) {
     constexpr int NW = THREADS_LG / 32;
-    const size_t smem = lines_kernel_smem<LW, VIRT>(NW);
-    static_assert(lines_kernel_smem<LW, VIRT>(NW) <= 227 * 1024, "shared memory of the line kernel");
+    constexpr int SW = LW == 0 ? LN_MAX_LW : LW;   // LW == 0: all widths and the long-line files in one launch
+    const size_t smem = lines_kernel_smem<SW, VIRT || LW == 0>(NW);
+    static_assert(lines_kernel_smem<SW, VIRT || LW == 0>(NW) <= 227 * 1024, "shared memory of the line kernel");
     auto kern = count_fasta_lines_kernel<LW, THREADS_LG, BASE, VIRT>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
@@ -550,15 +551,10 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     if (g.pc_ntiles > 0) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         if (use_lg) {
-            rc = launch_linegrid<80>(d_arena, grid, s);
-            if (rc == KF_OK) rc = launch_linegrid<60>(d_arena, grid, s);
-            if (rc == KF_OK) rc = launch_linegrid<70>(d_arena, grid, s);
-            if (rc == KF_OK) rc = launch_linegrid<80, true>(d_arena, grid, s);   // long-line files: virtual lines
-            if (rc == KF_OK) rc = launch_linegrid<100>(d_arena, grid, s);
-            if (rc == KF_OK) rc = launch_linegrid<120>(d_arena, grid, s);
-            if (rc == KF_OK) rc = launch_linegrid<50>(d_arena, grid, s);
+            // one launch for every kind of file the line kernel takes: 50 / 60 / 70 / 80 / 100 columns and long lines
+            rc = launch_linegrid<0>(d_arena, grid, s);
             if (rc != KF_OK) return rc;
-            g.last_launches += 7;
+            g.last_launches += 1;
         }
         // file indices inside tiles are batch-global; k >= 8 rows are relative to f0, k <= 7 rows come from d_file_row
         rc = launch_count(k, d_arena, grid, force_walker, f0, s);

@@ -875,6 +875,7 @@ __device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64
 //   rare paths : a line holding a non-ACGT byte (or whose 6 look-ahead bytes do) goes to the exact byte walker on
 //                global memory; a line that breaks the grid (short last line, header, other width) goes to the
 //                exact generic range processor up to the next sequence line, where the grid restarts.
+constexpr int LN_MAX_LW = 100;     // widest wrapped FASTA with a line-kernel instantiation (shared memory: 120 columns would not leave room)
 constexpr int LN_SCR_WORDS = 36;   // per-warp scratch: one line + look-ahead re-fetched from global memory (P + LA + 3 bytes at LW = 120: 130)
 template <int LW>
 struct LineGeom {
@@ -1623,7 +1624,7 @@ __device__ __forceinline__ void vl_process_piece(const uint8_t *__restrict__ are
 constexpr uint32_t KF_P_VIRTUAL = 0xFFFFu;
 // the wrapped widths that have a line-kernel instantiation, and where the batch's count of such files is kept
 __host__ __device__ constexpr int line_width_slot(int lw) {   // index into width_counts (0 = generic kernel, 4 = long lines)
-    return lw == 60 ? 1 : lw == 70 ? 2 : lw == 80 ? 3 : lw == 100 ? 5 : lw == 120 ? 6 : lw == 50 ? 7 : 0;
+    return lw == 60 ? 1 : lw == 70 ? 2 : lw == 80 ? 3 : lw == 100 ? 5 : lw == 50 ? 7 : 0;
 }
 // dynamic shared memory of count_fasta_lines_kernel: pair + singles histograms, one staging buffer and one barrier per
 // warp, per-warp scratch and partial sums, cursor words, the backward scan's result, the virtual-line log
@@ -1638,11 +1639,20 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
                          const uint64_t *__restrict__ file_len, unsigned long long *__restrict__ g_fwd,
                          const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ cta_first_rank, int cta_stride,
                          const uint32_t *__restrict__ width_counts) {
-    using G = LineGeom<LW>;
-    static_assert(!VIRT || (LW == 80 && VL_STAGE <= G::STAGE), "virtual lines use the 80-column layout");
+    // LW == 0: every supported kind of file in ONE launch (the piece's width picks the code): no empty launches, and a
+    // batch of mixed widths keeps all CTAs busy.  Staging is sized for the widest line then.
+    constexpr bool ALL = LW == 0;
+    using G = LineGeom<ALL ? LN_MAX_LW : LW>;
+    static_assert(!(VIRT || ALL) || VL_STAGE <= G::STAGE, "virtual lines fit the staging buffers");
+    static_assert(!VIRT || LW == 80, "virtual lines use the 80-column layout");
     constexpr uint32_t MYP = VIRT ? KF_P_VIRTUAL : (uint32_t)G::P;
-    static_assert(VIRT || line_width_slot(LW) != 0, "no slot for this width");
-    if (width_counts[VIRT ? 4 : line_width_slot(LW)] == 0) return;   // no file of this kind in the batch (uniform exit)
+    static_assert(ALL || VIRT || line_width_slot(LW) != 0, "no slot for this width");
+    if (ALL) {
+        uint32_t any = 0;
+#pragma unroll
+        for (int i = 1; i < 8; i++) any |= width_counts[i];
+        if (any == 0) return;   // every file goes to the generic kernel (uniform exit)
+    } else if (width_counts[VIRT ? 4 : line_width_slot(LW)] == 0) return;   // no file of this kind in the batch (uniform exit)
     constexpr int NWARPS = THREADS / 32;
     constexpr int NWORDS = 32768;
     constexpr int NB7 = 16384;
@@ -1664,7 +1674,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < NWORDS + NSWORDS; i += THREADS) smem[i] = 0;
     if (threadIdx.x == 0) { *s_nsingle = 0; *s_cursor = 0; s_cursor[1] = 0; }
-    if (VIRT && threadIdx.x == 0) { vlog->n_spec = 0; vlog->n_hdr = 0; vlog->overflow = 0; }
+    if ((VIRT || ALL) && threadIdx.x == 0) { vlog->n_spec = 0; vlog->n_hdr = 0; vlog->overflow = 0; }
     uint8_t *buf = stage_base + (size_t)warp * G::STAGE;
     uint64_t *bar = bars + warp;
     uint32_t par = 0;
@@ -1686,7 +1696,8 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         if (lane == 0) s_part[warp] = np;
         KF_T(tw0);
         __syncthreads();
-        if (VIRT) {
+        const bool virt = VIRT || (ALL && file_P[file] == KF_P_VIRTUAL);
+        if (virt) {
             // an assumed unit start inside a noted header line: text was counted that is no sequence
             const uint32_t ns = vlog->n_spec < (uint32_t)VL_LOG_SPEC ? vlog->n_spec : (uint32_t)VL_LOG_SPEC;
             const uint32_t nh = vlog->n_hdr < (uint32_t)VL_LOG_HDR ? vlog->n_hdr : (uint32_t)VL_LOG_HDR;
@@ -1710,7 +1721,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         bool half_ok = true;
 #pragma unroll
         for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; ts += s_part[2 * NWARPS + w]; half_ok = half_ok && s_part[NWARPS + w] != 0xFFFFFFFFu; }
-        const bool ok = half_ok && tp == tl && ts == (unsigned long long)*s_nsingle && !(VIRT && s_cursor[1] != 0);
+        const bool ok = half_ok && tp == tl && ts == (unsigned long long)*s_nsingle && !(virt && s_cursor[1] != 0);
         // every CTA that holds a piece of the file owns one row of it (file_row[file] + its rank among those CTAs; the
         // fold kernel sums the rows), so the row is WRITTEN, every bin, with plain 16-byte stores: no global atomics.
         // Only the first file of a CTA's tile range can have begun in an earlier CTA: its rank comes from the host.
@@ -1750,7 +1761,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         uint4 *h4 = reinterpret_cast<uint4 *>(smem);
         for (int i = threadIdx.x; i < (NWORDS + NSWORDS) / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
         if (threadIdx.x == 0) { *s_nsingle = 0; s_cursor[1] = 0; }
-        if (VIRT && threadIdx.x == 0) { vlog->n_spec = 0; vlog->n_hdr = 0; vlog->overflow = 0; }
+        if ((VIRT || ALL) && threadIdx.x == 0) { vlog->n_spec = 0; vlog->n_hdr = 0; vlog->overflow = 0; }
         __syncthreads();
 #ifdef KF_PIECE_TIMING
         { long long tw3 = clock64(); if (*s_nsingle == 12345u) tw3 = 0; KF_TADD(2, tw3 - tw2); if (threadIdx.x == 0) atomicAdd(&g_piece_timing[3], 1ull); }
@@ -1768,7 +1779,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
             const uint64_t lo_b = file_lo > F0 ? file_lo : F0, hi_b = file_hi < F1 ? file_hi : F1;
             const uint64_t span = (hi_b - lo_b + NWARPS - 1) / NWARPS;
             const uint64_t a0 = lo_b + (uint64_t)warp * span, a1 = (a0 + span < hi_b) ? a0 + span : hi_b;
-            if (VIRT) {
+            if (virt) {
                 // byte ownership (k-mers whose first base lies in the piece): whole chunks per warp, the state at a warp's
                 // first chunk from the exact backward scan of the range processor
                 const uint64_t c_lo = lo_b / CHUNK, c_hi = (hi_b + CHUNK - 1) / CHUNK;
@@ -1792,7 +1803,8 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
     KF_T(tk0);
     for (int t = cta_begin[blockIdx.x * cta_stride]; t < t1;) {
         const Tile T = tiles[t];
-        if (file_P[T.file] != MYP) { ++t; continue; }
+        const uint32_t cur_P = file_P[T.file];
+        if (ALL ? cur_P == 0u : cur_P != MYP) { ++t; continue; }
         uint32_t n_chunks = T.n_chunks;
         int te = t + 1;
         while (te < t1 && tiles[te].file == T.file && tiles[te].first_chunk == T.first_chunk + n_chunks) {
@@ -1819,7 +1831,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
 #ifdef KF_VL_TIMING
         const long long t_p0 = clock64();
 #endif
-        if (VIRT) {
+        if (VIRT || (ALL && cur_P == KF_P_VIRTUAL)) {
             // the state at the piece's first byte.  A piece that begins inside the file: the last '\n' before X0 decides --
             // exact backward scan by the whole CTA, four chunks per warp and round (the line may be megabytes long)
             uint32_t st = 2u;
@@ -1896,7 +1908,20 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         // every warp finds the piece's anchor (its first line start) by itself: same loads, served by L1 after the first
         const uint64_t A = fasta_line_start_at_or_after(GlobalSrc{arena}, X0, F0, F1, lane);
         __syncthreads();
-        ln_process_piece<LW, BASE>(arena, A, Xe, F0, F1, buf, s_wscr + LN_SCR_WORDS * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs);
+#define KF_LN_PIECE(W) ln_process_piece<W, BASE>(arena, A, Xe, F0, F1, buf, s_wscr + LN_SCR_WORDS * warp, bar, par, s_cursor, (uint32_t)NWARPS, hist16, gs, npairs)
+        if constexpr (ALL) {
+            switch (cur_P) {   // (uniform over the CTA)
+                case 81: KF_LN_PIECE(80); break;
+                case 61: KF_LN_PIECE(60); break;
+                case 71: KF_LN_PIECE(70); break;
+                case 101: KF_LN_PIECE(100); break;
+                case 51: KF_LN_PIECE(50); break;
+                default: break;
+            }
+        } else {
+            KF_LN_PIECE(LW);
+        }
+#undef KF_LN_PIECE
         }
         KF_T(ta2);
         KF_TADD(0, ta2 - ta1);
@@ -1924,7 +1949,7 @@ __global__ void __launch_bounds__(128)
 probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off,
                         const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
                         uint32_t force_generic, uint32_t *__restrict__ file_P,
-                        uint32_t *__restrict__ width_counts /* [line_width_slot()]: 0 generic, 1..3 60/70/80, 4 long lines, 5..7 100/120/50 */,
+                        uint32_t *__restrict__ width_counts /* [line_width_slot()]: 0 generic, 1..3 60/70/80, 4 long lines, 5 100, 7 50 */,
                         unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row, uint32_t row_bins) {
     const int lane = threadIdx.x & 31;
     const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);

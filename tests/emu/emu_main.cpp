@@ -52,7 +52,7 @@ static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const s
                    const uint32_t *file_P, const uint64_t *off, const uint64_t *len, unsigned long long *fwd,
                    const uint32_t *file_row, const uint32_t *file_first_cta, const uint32_t *wc) {
     constexpr int NW = THREADS / 32;
-    size_t smem = lines_kernel_smem<LW, VIRT>(NW);
+    size_t smem = lines_kernel_smem<(LW == 0 ? LN_MAX_LW : LW), (VIRT || LW == 0)>(NW);
     emu::launch(grid, THREADS, smem, [&]() {
         count_fasta_lines_kernel<LW, THREADS, 0u, VIRT>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
     });
@@ -205,26 +205,10 @@ int main(int argc, char **argv) {
     const bool lg = use_lg && k == 7 && !fw;
     emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data(), fwd.data(), file_row.data(), (uint32_t)NB); });
     if (lg) {
-        if (threads == 512) {
-            run_lg<80, 512>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<80, 512, true>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-        } else if (threads == 64) {
-            run_lg<80, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<60, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<70, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<80, 64, true>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<100, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<120, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<50, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-        } else {
-            run_lg<80, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<60, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<70, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<80, 32, true>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<100, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<120, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-            run_lg<50, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
-        }
+        // one launch for all widths and the long-line files, as kf_api.cu does
+        if (threads == 512) run_lg<0, 512>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+        else if (threads == 64) run_lg<0, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+        else run_lg<0, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         int nlg = 0, nvl = 0; for (auto P : file_P) { nlg += P != 0; nvl += P == KF_P_VIRTUAL; }
         fprintf(stderr, "linegrid files: %d of %d (virtual lines: %d)\n", nlg, n, nvl);
     }

@@ -66,7 +66,7 @@ def rand_fasta_grid(rng: random.Random) -> bytes:
     lines, several records, N runs, lower case, IUPAC, an occasional record in another width, blank lines,
     CRLF records, long headers, missing final newline."""
     out = bytearray()
-    lw = rng.choice([60, 70, 80, 60, 70, 80, 50, 100, 120])
+    lw = rng.choice([60, 70, 80, 60, 70, 80, 50, 100, 120])   # (120: no line-kernel instantiation -> generic kernel)
     nrec = rng.randint(1, 5)
     for r in range(nrec):
         hl = rng.choice([5, 20, 79, 80, 81, 100, 600]) if rng.random() < 0.4 else rng.randint(1, 60)
