@@ -566,6 +566,15 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     if (g.pc_fq_ntiles > 0) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         if ((rc = launch_fastq_k(k, d_arena, grid, f0, s)) != KF_OK) return rc;
+        // files the record-chasing kernel found out of 4-line layout: read front to back, one warp each (exact, slow)
+        if (smem_path)
+            fastq_multiline_kernel<unsigned long long><<<(nf * 32 + 127) / 128, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, f0, f1, k,
+                                                                                             (unsigned long long *)g.d_fwd, g.d_file_row, g.d_fq_err);
+        else
+            fastq_multiline_kernel<uint32_t><<<(nf * 32 + 127) / 128, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, f0, f1, k,
+                                                                                   (uint32_t *)g.d_fwd, nullptr, g.d_fq_err);
+        CK(cudaGetLastError());
+        g.last_launches++;
         CK(cudaEventRecord(g.ev_k1, s));
         g.ev_valid = true;
         g.last_launches += 1;

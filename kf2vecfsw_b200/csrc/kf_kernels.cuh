@@ -2254,6 +2254,99 @@ count_fastq_gmem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// FASTQ that is not in 4-line layout (sequences and qualities wrapped over several lines)
+// ------------------------------------------------------------------------------------------------
+// Record boundaries of multi-line FASTQ cannot be found locally ('@' and '+' are legal first quality characters), so such
+// a file is read the way Jellyfish reads it -- front to back: header line, sequence lines up to the line that starts
+// with '+', then quality lines until as many quality characters as bases have gone by (oracle/kf_oracle.c walk_fastq).
+// One warp per file, exact and slow (a file the record-chasing kernel above reported in fq_err, and only that, comes
+// here): the warp finds each line's end together, and counts the k-mers that END in a sequence line from the stream
+// "last k-1 bytes of the record so far" + line, so k-mers run on over the line ends of a record.  Row: the file's forward
+// counts (u64 for k <= 7, u32 above), zeroed first -- the fast kernel has left partial counts in it.
+template <typename RowT>
+__global__ void __launch_bounds__(128)
+fastq_multiline_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ file_off, const uint64_t *__restrict__ file_len,
+                       const uint8_t *__restrict__ formats, uint32_t f0, uint32_t f1, int k, RowT *__restrict__ g_fwd,
+                       const uint32_t *__restrict__ file_row, unsigned long long *__restrict__ fq_err) {
+    __shared__ uint8_t s_tail[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t f = f0 + (uint32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (f >= f1 || formats[f] != (uint8_t)'@') return;
+    const uint64_t F0 = file_off[f], F1 = F0 + file_len[f];
+    const unsigned long long e = fq_err[f];
+    if (e == ~0ull || e < F0 || e >= F1) return;                       // 4-line layout held
+    {
+        // a violation followed by line ends only (trailing blank lines ...) is none
+        bool other = false;
+        for (uint64_t p = e + lane; p < F1 && p < e + 4096; p += 32) other = other || (arena[p] != 0x0Au && arena[p] != 0x0Du);
+        if (F1 - e > 4096) other = true;
+        if (__ballot_sync(FULL, other) == 0u) { if (lane == 0) fq_err[f] = ~0ull; return; }
+    }
+    const size_t NB = (size_t)1 << (2 * k);
+    RowT *row = g_fwd + (file_row ? (size_t)file_row[f] : (size_t)(f - f0)) * NB;
+    for (size_t i = lane; i < NB; i += 32) row[i] = (RowT)0;
+    __threadfence();
+    KF_SYNCWARP();
+    const GlobalSrc gsrc{arena};
+    uint8_t *tail = s_tail[warp];
+    const int T = k - 1;                                               // bytes of the record's stream kept between lines
+    auto line_end = [&](uint64_t q) -> uint64_t {                      // position of the first '\n' at or after q, F1 if none
+        if (q >= F1) return F1;
+        const uint64_t ls = fasta_line_start_at_or_after(gsrc, q + 1, F0, F1, lane);
+        return (ls == F1 && arena[F1 - 1] != 0x0Au) ? F1 : ls - 1;
+    };
+    auto skip_nl = [&](uint64_t p) -> uint64_t { while (p < F1 && arena[p] == 0x0Au) p++; return p; };
+    auto ignore_line = [&](uint64_t p) -> uint64_t { const uint64_t q = line_end(p); return q < F1 ? q + 1 : F1; };
+    auto reset_tail = [&]() { KF_SYNCWARP(); if (lane < 32) tail[lane] = 0; KF_SYNCWARP(); };
+    uint64_t p = ignore_line(F0);                                      // the first '@' header
+    while (p < F1) {
+        uint64_t nseq = 0, nq = 0;
+        p = skip_nl(p);
+        reset_tail();
+        while (p < F1 && arena[p] != (uint8_t)'+') {
+            const uint64_t q = line_end(p);
+            const uint64_t len = q - p;
+            // stream = tail[0 .. T) + line[0 .. len): the k-mers that start at stream positions [0, len) end in this line
+            for (uint64_t s0 = lane; s0 < len; s0 += 32) {
+                bool valid = true;
+                uint32_t kmer = 0;
+                for (int t = 0; t < k; t++) {
+                    const uint64_t i = s0 + (uint64_t)t;
+                    const uint32_t c = i < (uint64_t)T ? tail[i] : arena[p + (i - (uint64_t)T)];
+                    valid = valid && is_base(c);
+                    kmer = (kmer << 2) | ((c >> 1) & 3u);
+                }
+                if (valid) atomicAdd(row + kmer, (RowT)1);
+            }
+            KF_SYNCWARP();
+            // the new tail: the last T bytes of the stream
+            uint8_t nt = 0;
+            if (lane < T) {
+                const uint64_t i = len + (uint64_t)lane;               // stream position of the new tail's byte `lane`
+                nt = i < (uint64_t)T ? tail[i] : arena[p + (i - (uint64_t)T)];
+            }
+            KF_SYNCWARP();
+            if (lane < T) tail[lane] = nt;
+            KF_SYNCWARP();
+            nseq += len;
+            p = skip_nl(q);
+        }
+        if (p >= F1) break;
+        p = ignore_line(p);                                            // the '+' line
+        p = skip_nl(p);
+        while (p < F1 && nq < nseq) {
+            const uint64_t q = line_end(p);
+            nq += q - p;
+            p = skip_nl(q);
+        }
+        p = skip_nl(p);
+        p = ignore_line(p);                                            // the next '@' header
+    }
+    __threadfence();
+    if (lane == 0) fq_err[f] = ~0ull;                                  // counted: no error to report
+}
+
+// ------------------------------------------------------------------------------------------------
 // Chunked-genome mode (kf2vec/main.py:813-881): every sliding window of a linearised contig becomes a one-record
 // pseudo-file ">\n<window bytes>" in a scratch arena, so the counting kernels above see it as an ordinary input
 // and each window yields one row.  One CTA per window; src windows may overlap and need no alignment.

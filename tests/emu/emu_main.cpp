@@ -233,6 +233,8 @@ int main(int argc, char **argv) {
 #define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), off.data(), len.data(), fwd.data(), file_row.data(), err.data()); }); \
                           else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), off.data(), len.data(), fwd.data(), file_row.data(), err.data()); }); break;
             switch (k) { RUNQ(3) RUNQ(4) RUNQ(5) RUNQ(7) default: return 2; }
+            // files out of 4-line layout: the exact front-to-back walk, one warp per file (as kf_api.cu launches it)
+            emu::launch((unsigned)((n * 32 + 127) / 128), 128, 0, [&]() { fastq_multiline_kernel<unsigned long long>(arena.data(), off.data(), len.data(), formats.data(), 0u, (uint32_t)n, k, fwd.data(), file_row.data(), err.data()); });
             for (int f = 0; f < n; f++)
                 if (err[f] != ~0ull && err[f] - off[f] < len[f]) fprintf(stderr, "fastq layout violation file %d at %llu\n", f, err[f] - off[f]);
         }

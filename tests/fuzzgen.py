@@ -132,3 +132,30 @@ def rand_fasta_long(rng: random.Random) -> bytes:
     if rng.random() < 0.3 and out.endswith(b'\n'):
         out = out[:-1]
     return bytes(out)
+
+
+def rand_fastq_multiline(rng: random.Random) -> bytes:
+    """FASTQ as old tools wrote it: sequence and quality wrapped over several lines (widths of their own), qualities that
+    begin a line with '@' or '+', reads shorter than k, N runs, lower case, blank lines between records, missing final
+    newline -- what Jellyfish reads front to back (oracle: walk_fastq)."""
+    out = bytearray()
+    for r in range(rng.randint(1, 25)):
+        L = rng.choice([0, 1, 6, 7, 8, 13, 60, 61, 150, 500]) if rng.random() < 0.5 else rng.randint(0, 400)
+        alphabet = 'ACGT' * 20 + 'acgt' * 3 + 'N' * (2 if rng.random() < 0.5 else 0)
+        seq = ''.join(rng.choice(alphabet) for _ in range(L))
+        qual = ''.join(chr(rng.randint(33, 74)) for _ in range(L))
+        ws, wq = rng.choice([1, 3, 5, 7, 60, 70, 80, 1000]), rng.choice([1, 4, 60, 61, 80, 1000])
+        out += ('@r%d %s\n' % (r, ''.join(rng.choice('ACGT@+>: /') for _ in range(rng.randint(0, 30))))).encode()
+        for i in range(0, max(L, 1), ws):
+            out += seq[i:i + ws].encode() + b'\n'
+        out += b'+' + (b'r%d' % r if rng.random() < 0.2 else b'') + b'\n'
+        for i in range(0, max(L, 1), wq):
+            line = qual[i:i + wq]
+            if line and rng.random() < 0.2:
+                line = rng.choice('@+') + line[1:]
+            out += line.encode() + b'\n'
+        if rng.random() < 0.1:
+            out += b'\n'
+    if rng.random() < 0.3 and out.endswith(b'\n'):
+        out = out[:-1]
+    return bytes(out)

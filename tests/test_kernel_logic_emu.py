@@ -290,3 +290,20 @@ def test_emulated_virtual_lines_fuzz(tmp_path, emu_binary_random_units):
             ref = o.canonical_counts_bytes(open(f, "rb").read(), 7)
             assert np.array_equal(counts, ref), (s, grid, thr, tile, f, int(ref.sum()), int(counts.sum()))
     assert n_virtual >= 0.6 * n_files, (n_virtual, n_files)   # (a file whose first lines are all short goes to the generic kernel)
+
+
+def test_emulated_multiline_fastq(tmp_path):
+    """FASTQ out of 4-line layout: the record-chasing kernel reports it, the one-warp-per-file walk recounts it exactly."""
+    from fuzzgen import rand_fastq, rand_fastq_multiline
+    for s in range(1400, 1420):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 3)):
+            p = str(tmp_path / ("m%d_%d.fq" % (s, i)))
+            open(p, "wb").write(rand_fastq_multiline(rng) if rng.random() < 0.8 else rand_fastq(rng))
+            files.append(p)
+        k = rng.choice([3, 4, 5, 7])
+        res = run_emu(k, rng.choice([32, 64]), rng.randint(1, 3), False, rng.choice([1, 3, 64]), files)
+        for f, (tot, counts, _) in zip(files, res):
+            ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
+            assert np.array_equal(counts, ref), (s, k, f)
