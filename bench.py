@@ -75,6 +75,31 @@ def generate_genomes(engine, ids, n_bases, threads, pinned=True):
     return host, views
 
 
+def build_arena_chunked(engine, ids, n_bases, threads, dev, chunk=500):
+    """Device arena of the synthetic genomes `ids`, generated chunk by chunk through one reused pinned buffer (10,000 genomes
+    are 50 GB: they need not exist in host memory at once)."""
+    import numpy as np
+    import torch
+    sizes = [kfsynth.synth_fasta_size(SEED, g, n_bases) for g in ids]
+    arena = engine.DeviceArena.empty(sizes, [0x3E] * len(ids), device=dev)
+    cap = max(sum(sizes[i:i + chunk]) for i in range(0, len(ids), chunk))
+    stage = [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    for ci, c0 in enumerate(range(0, len(ids), chunk)):
+        idx = list(range(c0, min(len(ids), c0 + chunk)))
+        buf = stage[ci & 1].numpy()
+        offs = np.zeros(len(idx) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([sizes[i] for i in idx])
+        views = [buf[offs[j]:offs[j + 1]] for j in range(len(idx))]
+        with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+            list(ex.map(lambda j: kfsynth.synth_fasta(SEED, ids[idx[j]], n_bases, out=views[j]), range(len(idx))))
+        if ci >= 2:
+            torch.cuda.synchronize(dev)          # (the copies out of this staging buffer two chunks ago are done)
+        for j, i in enumerate(idx):
+            arena.load(i, views[j])
+    torch.cuda.synchronize(dev)
+    return arena
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled every 2 ms over the timed region through NVML (the same
     counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; B200_PROFILING.md recipe)."""
@@ -321,11 +346,13 @@ def main():
     global NCCL_CTAS
     if NCCL_CTAS <= 0:
         NCCL_CTAS = 8
-    # measured: at 2 GPUs the 65 MB gather costs less (0.07 ms) than the SMs the overlap needs; from 4 GPUs on it pays
-    overlap = world >= 4 or (world > 1 and "KF_BENCH_NCCL_CTAS" in os.environ)
+    # How the [N, V] matrix is assembled when N > 1.  "peer" (default): every rank pushes its block into every peer's matrix
+    # with device-to-device copies over NVLink (copy engines, no SM: kf2vecfsw_b200.dist.PeerGather), the gather of step i
+    # beside the counting of step i + 1, which keeps all SMs.  "nccl": NCCL's all-gather (round 1), overlapped from 4 GPUs
+    # on with NCCL_MAX_CTAS CTAs and the counting kernels sized for the remaining SMs.
+    gather_impl = os.environ.get("KF_BENCH_GATHER", "peer") if world > 1 else None
+    overlap = gather_impl == "nccl" and (world >= 4 or "KF_BENCH_NCCL_CTAS" in os.environ)
     if overlap:
-        # the all-gather of batch i runs beside the counting of batch i+1: NCCL gets at most NCCL_CTAS CTAs, and the
-        # counting kernels (one persistent CTA per SM, ~205 KB of shared memory each) are sized for the other SMs
         os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -334,34 +361,67 @@ def main():
     sms_used = engine.set_sm_limit(0)
     if overlap:
         sms_used = engine.set_sm_limit(sms_used - NCCL_CTAS)
-    k, G, NB = args.k, args.genomes, args.bases
+    k, NB = args.k, args.bases
+    strong = args.scaling == "strong"
+    if strong:
+        # BASELINE.json configs[2]: --genomes-total genomes sharded over the GPUs in contiguous blocks (rank order = file
+        # order, so the gathered matrix is in the original row order)
+        tot = args.genomes_total
+        rows = [tot // world + (1 if r < tot % world else 0) for r in range(world)]
+    else:
+        rows = [args.genomes] * world
+    G = rows[rank]
+    first = sum(rows[:rank])
     V = engine.vocab_size(k)
     threads = max(1, host_threads() // max(1, world))
 
-    ids = list(range(rank * G, (rank + 1) * G))
-    host, views = generate_genomes(engine, ids, NB, threads)
-    arena = engine.DeviceArena(views, device=dev)
+    ids = list(range(first, first + G))
+    host = views = None
+    if strong:
+        arena = build_arena_chunked(engine, ids, NB, threads, dev)
+        args.no_e2e = True            # (the end-to-end arm is measured on the weak-scaling configuration)
+    else:
+        host, views = generate_genomes(engine, ids, NB, threads)
+        arena = engine.DeviceArena(views, device=dev)
     file_bytes = arena.file_bytes
     counts = torch.empty((G, V), dtype=torch.int64, device=dev)
     freq = torch.empty((G, V), dtype=torch.float64, device=dev)
     feat = torch.empty((G, V), dtype=torch.float32, device=dev)
     totals = torch.empty(G, dtype=torch.int64, device=dev)
-    # N > 1: the [N, V] backbone matrix is assembled on every GPU by an all-gather that runs while the next batch is
-    # being counted (two buffer pairs); every gather completes inside the timed region (drain before the end event)
+    pg = kfdist.PeerGather(rows, V, torch.float32, dev) if gather_impl == "peer" else None
     og = kfdist.OverlappedGather(G, V, torch.float32, dev) if overlap else None
-    gathered = torch.empty((world * G, V), dtype=torch.float32, device=dev) if (world > 1 and not overlap) else None
+    gathered = torch.empty((world * max(rows), V), dtype=torch.float32, device=dev) if (gather_impl == "nccl" and not overlap) else None
+    gpad = torch.zeros((max(rows), V), dtype=torch.float32, device=dev) if gathered is not None and G < max(rows) else None
     kernel_ms = []
+    nsub = [0]
 
     def step(record=False):
         # everything is enqueued on torch's current stream: no host synchronisation inside a step
-        f = og.slot() if og else feat
+        f = pg.slot() if pg else (og.slot() if og else feat)
         engine.count_device(arena, k=k, counts=counts, freq=freq, feat=f, totals=totals)
-        if og:
+        if pg:
+            pg.submit()
+            if nsub[0] > 0:            # the previous step's matrix: complete by now (its pushes ran beside this counting)
+                pg.wait(step=nsub[0] - 1)
+                pg.release(step=nsub[0] - 1)
+            nsub[0] += 1
+        elif og:
             og.submit()
         elif gathered is not None:
-            dist.all_gather_into_tensor(gathered, f)
+            if gpad is not None:
+                gpad[:G].copy_(f)
+                dist.all_gather_into_tensor(gathered, gpad)
+            else:
+                dist.all_gather_into_tensor(gathered, f)
         if record:
             kernel_ms.append(engine.last_count_kernel_ms())   # (waits for the library's events: only outside the timed region)
+
+    def drain():
+        if pg and nsub[0] > 0:
+            pg.wait(step=nsub[0] - 1)
+            pg.release(step=nsub[0] - 1)
+        if og:
+            og.drain()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -371,6 +431,7 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -380,8 +441,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
-    if og:
-        og.drain()
+    drain()
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -400,13 +460,24 @@ def main():
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
     ms_step = float(ms_total.item()) / args.steps
-    value = world * G * NB / (ms_step * 1e-3) / 1e9
+    value = sum(rows) * NB / (ms_step * 1e-3) / 1e9
+    gather_ok = None
+    if pg:
+        # the gathered matrix of the last step against this rank's own rows and a checksum of every rank's block
+        full = pg.full[(nsub[0] - 1) % pg.NBUF]
+        mine = bool(torch.equal(full[first:first + G], (freq * 1e4).to(torch.float32)))
+        sums = torch.zeros(world, dtype=torch.float64, device=dev)
+        sums[rank] = full[first:first + G].double().sum()
+        dist.all_reduce(sums)
+        got = torch.stack([full[sum(rows[:r]):sum(rows[:r + 1])].double().sum() for r in range(world)])
+        gather_ok = mine and bool(torch.equal(got, sums))
 
     # parity spot check against the oracle (not timed): first and last genome of this rank
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     pick = [0, G - 1] if G > 1 else [0]
-    ref, _, _ = c_oracle.count_buffers_mt([views[i] for i in pick], k, 2, want_freq=False)
+    pick_bufs = [views[i] for i in pick] if views is not None else [kfsynth.synth_fasta(SEED, ids[i], NB) for i in pick]
+    ref, _, _ = c_oracle.count_buffers_mt(pick_bufs, k, 2, want_freq=False)
     got = counts[pick].cpu().numpy().astype(np.uint64)
     parity_ok = bool(np.array_equal(ref, got))
 
@@ -426,7 +497,7 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e_ok = bool(np.array_equal(out_counts[pick], ref))
-        e2e = {"value": world * G * NB * args.steps / float(dt.item()) / 1e9, "unit": UNIT,
+        e2e = {"value": sum(rows) * NB * args.steps / float(dt.item()) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(file_bytes), "d2h_bytes_per_step": int(G * V * 16 + G * 8),
                "ms_per_step": float(dt.item()) / args.steps * 1e3, "parity_ok": e2e_ok,
                "api": "kf_count_buffers (C ABI, pinned host buffers in, counts+frequencies out)",
@@ -442,7 +513,7 @@ def main():
     # files on disk -> .kf files written, through the call get_frequencies makes (kf_files_to_kf: reads,
     # GPU stage and writes pipelined), on a bounded number of the same genomes written to a scratch directory first
     e2e_files = None
-    if rank == 0 and world == 1 and not args.no_e2e and not args.no_files:
+    if rank == 0 and world == 1 and not args.no_e2e and not args.no_files and views is not None:
         import shutil
         import tempfile
         NF = min(G, 400)
@@ -474,7 +545,7 @@ def main():
             shutil.rmtree(root, ignore_errors=True)
 
     configs = None
-    if rank == 0 and world == 1 and not args.no_configs:
+    if rank == 0 and world == 1 and not args.no_configs and not strong:
         del arena, counts, freq, feat, host
         views = None
         torch.cuda.empty_cache()
@@ -494,12 +565,16 @@ def main():
         achieved = alg_bytes / (float(kms.item()) * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32 shared-memory counts -> u64 counts, f64 frequencies", "data": "synthetic",
-            "config": common_config(G, NB, k, world),
+            "config": common_config(G if not strong else rows[0], NB, k, world, args.scaling, sum(rows)),
             "file_bytes_per_gpu": int(file_bytes),
-            "gather": ("all-gather of step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, counting kernels sized "
-                       "for %d of the SMs)" % (NCCL_CTAS, sms_used)) if overlap else ("NCCL all-gather after the counting" if world > 1 else None),
+            "gather": None if world == 1 else (
+                "peer pushes over NVLink copy engines (cuMemcpyDtoDAsync into every peer's [N,V] matrix + flag words waited on with "
+                "cuStreamWaitValue32: no SM, no NCCL kernel), the gather of step i beside the counting of step i+1 on all %d SMs" % sms_used
+                if pg else ("NCCL all-gather of step i overlapping the counting of step i+1 (two buffer pairs; NCCL_MAX_CTAS=%d, counting "
+                            "kernels sized for %d of the SMs)" % (NCCL_CTAS, sms_used) if overlap else "NCCL all-gather after the counting")),
+            "gather_ok": gather_ok,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "count_fasta_lines_kernel (one launch for all line widths; ln_process_piece<80> on this input)",

@@ -84,3 +84,139 @@ class OverlappedGather:
             if self.pending[b] is not None:
                 self.pending[b].wait()
                 self.pending[b] = None
+
+
+class PeerGather:
+    """All-gather of the per-rank [rows_r, cols] blocks into the [N, cols] matrix on every GPU of one node WITHOUT using an
+    SM.  The counting kernels are persistent CTAs that fill every SM (one CTA of ~210 KB of shared memory each), so a
+    collective that runs as a kernel -- NCCL's ring -- either waits for them or needs SMs set aside for it.  Here every
+    rank pushes its block straight into its slot of every peer's matrix with device-to-device copies over NVLink
+    (``cuMemcpyDtoDAsync`` on a side stream: copy engines), followed by a 4-byte copy of the step number into the peer's
+    flag word; a consumer orders its stream behind the arrival of all blocks with ``cuStreamWaitValue32`` on its OWN flag
+    words.  No kernel, no host synchronisation in a step.  The matrices live in torch symmetric memory (set up once).
+
+    ``slot()`` returns the view of this rank's rows inside its own matrix (the producer writes there: no local copy);
+    ``submit(producer_stream)`` pushes it to the peers; ``wait(stream)`` makes ``stream`` wait for every rank's block of
+    that step and returns the matrix; ``release(stream)`` tells the peers, in stream order, that the matrix may be
+    overwritten (two matrices are used in turn: a push for step t+2 waits for every peer's release of step t)."""
+
+    NBUF = 2
+
+    def __init__(self, rows, cols: int, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from cuda.bindings import driver
+        self.drv = driver
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows = [int(r) for r in rows]
+        assert len(self.rows) == self.world
+        self.row0 = [sum(self.rows[:r]) for r in range(self.world)]
+        self.N = sum(self.rows)
+        self.cols = cols
+        self.device = device
+        # Symmetric memory (cuMem allocations exchanged as fabric / fd handles, what NCCL itself uses): peer copies into it run
+        # over NVLink at ~550 GB/s on B200; memory shared through classic CUDA IPC handles was measured at 24 GB/s here.
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.full, self.flags, self.peer_full, self.peer_flags = [], [], [[] for _ in range(self.world)], [[] for _ in range(self.world)]
+        for _ in range(self.NBUF):
+            t = symm_mem.empty((self.N, cols), dtype=dtype, device=device)
+            h = symm_mem.rendezvous(t, group=grp)
+            # flag words: [0 : world) arrival of rank q's block, [world : 2 world) rank q's release of this matrix
+            f = symm_mem.empty((2 * self.world,), dtype=torch.int32, device=device)
+            hf = symm_mem.rendezvous(f, group=grp)
+            t.zero_()
+            f.zero_()
+            self.full.append(t)
+            self.flags.append(f)
+            for q in range(self.world):
+                self.peer_full[q].append(t if q == self.rank else h.get_buffer(q, (self.N, cols), dtype))
+                self.peer_flags[q].append(f if q == self.rank else hf.get_buffer(q, (2 * self.world,), torch.int32))
+        self.steps = torch.arange(0, 1 << 20, dtype=torch.int32, device=device)   # source of the 4-byte flag copies (step tags)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.ready = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.t = 0            # steps submitted
+        self.esize = self.full[0].element_size()
+
+    def _check(self, res):
+        err = res[0] if isinstance(res, tuple) else res
+        if int(err) != 0:
+            raise RuntimeError("CUDA driver call failed: %s" % err)
+
+    def _wait_geq(self, stream_handle: int, ptr: int, value: int):
+        drv = self.drv
+        self._check(drv.cuStreamWaitValue32(drv.CUstream(stream_handle), drv.CUdeviceptr(ptr), value,
+                                            int(drv.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ.value)))
+
+    def _copy(self, dst: int, src: int, nbytes: int, stream_handle: int):
+        drv = self.drv
+        self._check(drv.cuMemcpyDtoDAsync(drv.CUdeviceptr(dst), drv.CUdeviceptr(src), nbytes, drv.CUstream(stream_handle)))
+
+    def _tag_ptr(self, tag: int) -> int:
+        assert 0 < tag < (1 << 20), "PeerGather: more than 2^20 steps"
+        return self.steps.data_ptr() + 4 * tag
+
+    def slot(self):
+        b = self.t % self.NBUF
+        r0 = self.row0[self.rank]
+        return self.full[b][r0:r0 + self.rows[self.rank]]
+
+    def submit(self, producer_stream=None):
+        """Pushes the block last handed out by slot() (written on ``producer_stream``, default: the current stream)."""
+        import torch
+        if producer_stream is None:
+            producer_stream = torch.cuda.current_stream(self.device)
+        b = self.t % self.NBUF
+        tag = self.t + 1
+        cs = self.copy_stream.cuda_stream
+        drv = self.drv  # noqa: F841
+        self.ready.record(producer_stream)
+        self.copy_stream.wait_event(self.ready)
+        r0, n = self.row0[self.rank], self.rows[self.rank]
+        nbytes = n * self.cols * self.esize
+        src = self.full[b][r0:r0 + n].data_ptr()
+        if self.t >= self.NBUF:
+            # every peer has released this matrix (step t - NBUF): its flag word for me holds at least that step's tag
+            for q in range(self.world):
+                if q != self.rank:
+                    self._wait_geq(cs, self.flags[b].data_ptr() + 4 * (self.world + q), tag - self.NBUF)
+        for d in range(1, self.world):
+            q = (self.rank + d) % self.world     # (every rank starts with another peer: the links are used evenly)
+            if nbytes:
+                self._copy(self.peer_full[q][b].data_ptr() + r0 * self.cols * self.esize, src, nbytes, cs)
+            self._copy(self.peer_flags[q][b].data_ptr() + 4 * self.rank, self._tag_ptr(tag), 4, cs)
+        self.t += 1
+        return self.full[b]
+
+    def wait(self, stream=None, step=None):
+        """Orders ``stream`` behind the arrival of every rank's block of step ``step`` (default: the last one submitted);
+        returns the [N, cols] matrix."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        t = self.t - 1 if step is None else step
+        b = t % self.NBUF
+        for q in range(self.world):
+            if q != self.rank:
+                self._wait_geq(stream.cuda_stream, self.flags[b].data_ptr() + 4 * q, t + 1)
+        return self.full[b]
+
+    def release(self, stream=None, step=None):
+        """This rank is done with the matrix of step ``step`` (default: the last one submitted) once ``stream`` has got to
+        this point.  The flag copies go through the side stream (a copy-engine operation in the middle of a compute
+        stream costs a bubble between its kernels)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        t = self.t - 1 if step is None else step
+        b = t % self.NBUF
+        self.done.record(stream)
+        self.copy_stream.wait_event(self.done)
+        for q in range(self.world):
+            if q != self.rank:
+                self._copy(self.peer_flags[q][b].data_ptr() + 4 * (self.world + self.rank), self._tag_ptr(t + 1), 4, self.copy_stream.cuda_stream)

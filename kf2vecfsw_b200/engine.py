@@ -343,6 +343,32 @@ class DeviceArena:
                 self.tensor[int(off): int(off) + a.size].copy_(src, non_blocking=True)
         torch.cuda.synchronize(self.device)
 
+    @classmethod
+    def empty(cls, lens, first_bytes, device=None):
+        """An arena laid out for files of the given lengths (first_bytes: '>' / '@' per file), all NUL; fill with load()."""
+        import torch
+        _require_init()
+        self = cls.__new__(cls)
+        self.device = torch.device("cuda", _INIT_DEVICE) if device is None else device
+        self.n = len(lens)
+        self.lens = np.asarray(lens, dtype=np.uint64).copy()
+        padded = (self.lens + np.uint64(KF_CHUNK - 1)) // np.uint64(KF_CHUNK) * np.uint64(KF_CHUNK)
+        self.offsets = np.zeros(self.n, dtype=np.uint64)
+        if self.n > 1:
+            self.offsets[1:] = np.cumsum(padded)[:-1]
+        self.nbytes = int(padded.sum()) + KF_TAIL_PAD
+        self.formats = np.asarray(first_bytes, dtype=np.uint8).copy()
+        self.tensor = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
+        return self
+
+    def load(self, i: int, host_array, non_blocking: bool = True) -> None:
+        """Copies file i's bytes (uint8 array, pinned for an asynchronous copy) to its place in the arena."""
+        import torch
+        a = _as_u8(host_array)
+        assert a.size == int(self.lens[i])
+        off = int(self.offsets[i])
+        self.tensor[off: off + a.size].copy_(torch.from_numpy(a), non_blocking=non_blocking)
+
     @property
     def file_bytes(self) -> int:
         return int(self.lens.sum())

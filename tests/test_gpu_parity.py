@@ -617,3 +617,47 @@ def test_unwrapped_genomes_vs_c_oracle(eng):
     wrapped = [kfsynth.synth_fasta(31, i, 5_000_000, line_width=80, max_contigs=1) for i in range(3)]
     cw = eng.count_buffers(wrapped, k=7)[0]
     assert np.array_equal(cw, counts[:3])
+
+
+def _peer_gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from kf2vecfsw_b200.dist import PeerGather
+    rows = [5, 3][:world] if world == 2 else [4] * world
+    pg = PeerGather(rows, 64, torch.float32, dev)
+    ok = True
+    for step in range(5):                      # more steps than matrices: the release / reuse handshake is exercised
+        pg.slot().fill_(float(100 * step + rank))
+        pg.submit()
+        full = pg.wait()
+        torch.cuda.synchronize(dev)
+        for r in range(world):
+            ok = ok and bool((full[sum(rows[:r]):sum(rows[:r + 1])] == float(100 * step + r)).all())
+        pg.release()
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_gather_two_gpus():
+    """dist.PeerGather (copy-engine all-gather through symmetric memory, flag words + cuStreamWaitValue32) on two GPUs of one
+    node; skipped on a single-GPU box (bench.py --gpus N uses it for every N > 1 and checks the gathered matrix there)."""
+    import torch
+    import torch.multiprocessing as mp
+    import socket
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
