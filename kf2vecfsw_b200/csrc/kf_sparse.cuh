@@ -6,14 +6,20 @@
 // (A0 C1 G2 T3, first base most significant -- the vocabulary order of the dense path), which is what Jellyfish dumps
 // (in hash order).
 //
-// Pipeline over one batch of files (MSD radix partition by the code's leading bits, then per-bucket sort + run lengths):
-//   1. sparse_extract_kernel<0>  text -> canonical codes -> per-(file, bucket) histogram (shared memory, flushed per file)
-//   2. sparse_scan_buckets_kernel exclusive scan per file: where every bucket's keys go inside the file's key region
-//   3. sparse_extract_kernel<1>  the same parse again; every code is stored in its bucket (global cursor per bucket)
-//   4. sparse_sort_kernel        item = (file, run of buckets): each bucket sorted in shared memory (bitonic; in global
-//                                memory in place when it does not fit), distinct codes counted
-//   5. sparse_scan_items_kernel  exclusive scan of the distinct counts: where every item's output goes
-//   6. sparse_emit_kernel        run-length encode the item's (now globally sorted) key range into (code, count)
+// Pipeline over one batch of files (MSD radix partition by the code's leading 12 bits, then per bucket):
+//   1. sparse_tile_kernel<0>      text -> canonical codes -> per-(tile, bucket) counts (shared-memory histogram per tile)
+//   2. sparse_tile_scan_kernel    per file: where every (tile, bucket) run goes inside the file's key region
+//   3. sparse_tile_kernel<1>      the same parse again (the tile comes from L2); every code is stored at its place
+//                                 (cursors in shared memory: no global atomics)
+//   k <= 12 (a bucket's codes differ in <= 12 bits): histogram instead of sort
+//   4. sparse_bucket_distinct_kernel   one warp per bucket: bit map -> number of distinct codes
+//   5. sparse_scan_distinct_kernel     per file: where every bucket's entries go
+//   6. sparse_bucket_emit_kernel       one warp per bucket: 2^R bins in shared memory -> (code, count) ascending
+//   k >= 13: sort
+//   4. sparse_sort_kernel         item = (file, run of buckets): each bucket sorted in shared memory (bitonic; in global
+//                                 memory in place when it does not fit), distinct codes counted
+//   5. sparse_scan_items_kernel   exclusive scan of the distinct counts: where every item's output goes
+//   6. sparse_emit_kernel         run-length encode the item's (now globally sorted) key range into (code, count)
 // The parser is the dense path's (fasta_process_range): a k-mer is owned by the 16-byte lane that holds its first base,
 // so both passes enumerate exactly the same k-mers.  k <= 16: the lane's 32-base window yields forward and
 // reverse-complement codes with two shifts each; k >= 17: every lane runs the canonical byte walker.
@@ -110,70 +116,65 @@ struct SparseSink {
 template <int MODE, typename KT> struct sink_takes_window<SparseSink<MODE, KT>> { static constexpr bool value = true; };
 template <int MODE, typename KT> struct sink_walks_itself<SparseSink<MODE, KT>> { static constexpr bool value = true; };
 
-// Passes 1 and 3.  Persistent: CTA b owns tiles [cta_begin[b], cta_begin[b+1]) of the FASTA plan (dense path's tiles).
-// file ids in the tiles are batch-global; file_base = first file of this sub-batch; tables below are relative to it.
-//   MODE 0: g_hist [nf][SP_BUCKETS] += the CTA's shared-memory histogram, at every file change
-//   MODE 1: keys + kbase[f] = file f's key region, g_cursor [nf][SP_BUCKETS] = next free slot of every bucket
+// ------------------------------------------------------------------------------------------------
+// Partition without global atomics (passes 1-3 of the pipeline in kf_sparse_host.inc)
+// ------------------------------------------------------------------------------------------------
+// A tile (<= 512 KiB of one file, the dense path's plan) is one CTA's unit: MODE 0 counts the tile's canonical codes per
+// bucket in shared memory and writes the 4,096 counts to tile_hist[tile]; the scan below turns them into the place of
+// every (tile, bucket) run inside the file's key region; MODE 1 loads those places as shared-memory cursors, parses the
+// tile again (it comes from L2) and stores every code at atomicAdd(cursor[bucket], 1) -- a shared-memory atomic.  The first
+// version took the cursor from global memory: one returning global atomic per k-mer, 7 Gbases/s.
 template <int MODE, typename KT, bool WALK_ALL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
-sparse_extract_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin, int k,
-                      uint32_t file_base, uint32_t *__restrict__ g_hist, uint32_t *__restrict__ g_cursor, KT *__restrict__ keys,
-                      const uint64_t *__restrict__ kbase) {
-    __shared__ uint32_t hist[MODE == 0 ? SP_BUCKETS : 1];
+sparse_tile_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin, int k,
+                   uint32_t file_base, uint32_t *__restrict__ tile_hist, KT *__restrict__ keys, const uint64_t *__restrict__ kbase) {
+    __shared__ uint32_t hist[SP_BUCKETS];
     constexpr int NWARPS = THREADS / 32;
     const int warp = threadIdx.x >> 5;
-    if (MODE == 0) {
-        for (uint32_t i = threadIdx.x; i < SP_BUCKETS; i += THREADS) hist[i] = 0;
-        __syncthreads();
-    }
-    int cur_file = -1;
-    auto flush = [&](int file) {
-        if (MODE != 0) return;
-        __syncthreads();
-        uint32_t *gh = g_hist + (size_t)(file - (int)file_base) * SP_BUCKETS;
-        for (uint32_t i = threadIdx.x; i < SP_BUCKETS; i += THREADS) {
-            const uint32_t v = hist[i];
-            if (v) { atomicAdd(gh + i, v); hist[i] = 0; }
-        }
-        __syncthreads();
-    };
     SparseSink<MODE, KT> sink;
     sink.k = k;
     sink.e.hist = hist;
+    sink.e.cursor = hist;
     sink.e.shift = (uint32_t)(2 * k - SP_BUCKET_BITS);
-    sink.e.cursor = nullptr;
     sink.e.keys = nullptr;
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
         const Tile T = tiles[t];
-        if ((int)T.file != cur_file) {
-            if (cur_file >= 0) flush(cur_file);
-            cur_file = (int)T.file;
-            if (MODE == 1) {
-                sink.e.cursor = g_cursor + (size_t)(T.file - file_base) * SP_BUCKETS;
-                sink.e.keys = keys + kbase[T.file - file_base];
-            }
-        }
+        uint4 *th4 = reinterpret_cast<uint4 *>(tile_hist + (size_t)t * SP_BUCKETS);
+        uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+        for (uint32_t i = threadIdx.x; i < SP_BUCKETS / 4; i += THREADS) h4[i] = MODE == 0 ? make_uint4(0u, 0u, 0u, 0u) : th4[i];
+        __syncthreads();
+        if (MODE == 1) sink.e.keys = keys + kbase[T.file - file_base];
         const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
         const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
         const uint32_t cend = T.first_chunk + T.n_chunks;
         const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
         if (c0 < c1) fasta_process_range<12, WALK_ALL, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, sink);
+        __syncthreads();
+        if (MODE == 0)
+            for (uint32_t i = threadIdx.x; i < SP_BUCKETS / 4; i += THREADS) th4[i] = h4[i];
+        __syncthreads();
     }
-    if (cur_file >= 0) flush(cur_file);
 }
 
-// Pass 2: one CTA per file.  boff [nf][SP_BUCKETS + 1] = exclusive scan of the file's bucket counts (last = total),
-// cursor [nf][SP_BUCKETS] = the same (pass 3 advances it), totals [file_base + f] = the file's valid k-mers.
+// Pass 2: one CTA per file.  tile_hist [tiles][SP_BUCKETS]: counts in, places out (offset of the (tile, bucket) run inside
+// the file's key region); boff [nf][SP_BUCKETS + 1] = exclusive scan of the file's bucket totals (last = all keys).
 __global__ void __launch_bounds__(1024)
-sparse_scan_buckets_kernel(const uint32_t *__restrict__ g_hist, uint32_t *__restrict__ boff, uint32_t *__restrict__ cursor,
-                           unsigned long long *__restrict__ totals, uint32_t file_base) {
+sparse_tile_scan_kernel(uint32_t *__restrict__ tile_hist, const int *__restrict__ file_t0, uint32_t *__restrict__ boff,
+                        unsigned long long *__restrict__ totals, uint32_t file_base) {
     static_assert(SP_BUCKETS == 4096, "four buckets per thread");
     __shared__ uint32_t wsum[32];
     const uint32_t f = blockIdx.x;
-    const uint32_t *h = g_hist + (size_t)f * SP_BUCKETS;
+    const int ta = file_t0[f], tb = file_t0[f + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint4 v = reinterpret_cast<const uint4 *>(h)[threadIdx.x];
+    uint4 run = make_uint4(0u, 0u, 0u, 0u);
+    for (int t = ta; t < tb; t++) {   // per bucket: counts -> running offsets over the file's tiles
+        uint4 *p = reinterpret_cast<uint4 *>(tile_hist + (size_t)t * SP_BUCKETS) + threadIdx.x;
+        const uint4 c = *p;
+        *p = run;
+        run.x += c.x; run.y += c.y; run.z += c.z; run.w += c.w;
+    }
+    const uint4 v = run;   // the file's bucket totals
     const uint32_t mine = v.x + v.y + v.z + v.w;
     uint32_t inc = mine;
 #pragma unroll
@@ -191,10 +192,112 @@ sparse_scan_buckets_kernel(const uint32_t *__restrict__ g_hist, uint32_t *__rest
     const uint4 o4 = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
     uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
     bo[4 * threadIdx.x] = o4.x; bo[4 * threadIdx.x + 1] = o4.y; bo[4 * threadIdx.x + 2] = o4.z; bo[4 * threadIdx.x + 3] = o4.w;
-    reinterpret_cast<uint4 *>(cursor + (size_t)f * SP_BUCKETS)[threadIdx.x] = o4;
     if (threadIdx.x == 1023) {
         bo[SP_BUCKETS] = ex + mine;
         if (totals) totals[file_base + f] = (unsigned long long)(ex + mine);
+    }
+    for (int t = ta; t < tb; t++) {   // + the bucket's start
+        uint4 *p = reinterpret_cast<uint4 *>(tile_hist + (size_t)t * SP_BUCKETS) + threadIdx.x;
+        uint4 c = *p;
+        c.x += o4.x; c.y += o4.y; c.z += o4.z; c.w += o4.w;
+        *p = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Buckets of few remaining bits (2k - 12 <= 12, i.e. k <= 12): histogram instead of sort
+// ------------------------------------------------------------------------------------------------
+// The codes of one bucket differ in their low R = 2k - 12 bits only: at most 4,096 values.  One warp per bucket:
+//   sparse_bucket_distinct_kernel  a 2^R-bit map in shared memory (atomicOr) -> number of distinct codes of the bucket
+//   sparse_scan_distinct_kernel    per file: exclusive scan of the 4,096 numbers -> where the bucket's entries go
+//   sparse_bucket_emit_kernel      2^R u32 bins in shared memory per warp (atomicAdd), then the bins are walked 32 at a time
+//                                  (ballot + popc give the place of every non-zero bin: ascending codes, coalesced stores)
+constexpr int SP_HIST_MAX_R = 12;
+constexpr int SP_HIST_WARPS = 8;      // warps (= buckets in flight) per CTA: 8 x 16 KB of bins
+
+__global__ void __launch_bounds__(32 * SP_HIST_WARPS)
+sparse_bucket_distinct_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ kbase, const uint32_t *__restrict__ boff, int R,
+                              uint32_t *__restrict__ nd /* [nf][SP_BUCKETS] */) {
+    __shared__ uint32_t bitmap[SP_HIST_WARPS][(1 << SP_HIST_MAX_R) / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x * SP_HIST_WARPS + warp;      // (file, bucket)
+    const uint32_t f = item >> SP_BUCKET_BITS, b = item & (SP_BUCKETS - 1);
+    const uint32_t nwords = (1u << R) / 32u ? (1u << R) / 32u : 1u;
+    uint32_t *bm = bitmap[warp];
+    for (uint32_t i = lane; i < nwords; i += 32) bm[i] = 0;
+    KF_SYNCWARP();
+    const uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
+    const uint32_t s = bo[b], n = bo[b + 1] - s;
+    const uint32_t *gk = keys + kbase[f] + s;
+    const uint32_t lowmask = (1u << R) - 1u;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t low = gk[i] & lowmask;
+        atomicOr(bm + (low >> 5), 1u << (low & 31u));
+    }
+    KF_SYNCWARP();
+    uint32_t c = 0;
+    for (uint32_t i = lane; i < nwords; i += 32) c += (uint32_t)__popc(bm[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane == 0) nd[item] = c;
+}
+
+// per file: ooff [nf][SP_BUCKETS] = exclusive scan of nd over the file's buckets, nd_file [nf] = the file's distinct codes
+__global__ void __launch_bounds__(1024)
+sparse_scan_distinct_kernel(const uint32_t *__restrict__ nd, uint32_t *__restrict__ ooff, unsigned long long *__restrict__ nd_file) {
+    __shared__ uint32_t wsum[32];
+    const uint32_t f = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4 v = reinterpret_cast<const uint4 *>(nd + (size_t)f * SP_BUCKETS)[threadIdx.x];
+    const uint32_t mine = v.x + v.y + v.z + v.w;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t ex = wsum[warp] + inc - mine;
+    reinterpret_cast<uint4 *>(ooff + (size_t)f * SP_BUCKETS)[threadIdx.x] = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+    if (threadIdx.x == 1023) nd_file[f] = (unsigned long long)(ex + mine);
+}
+
+__global__ void __launch_bounds__(32 * SP_HIST_WARPS)
+sparse_bucket_emit_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ kbase, const uint32_t *__restrict__ boff, int R,
+                          const uint32_t *__restrict__ ooff, const unsigned long long *__restrict__ out_base /* [nf]: first entry of the file */,
+                          unsigned long long *__restrict__ codes_out, uint32_t *__restrict__ counts_out) {
+    KF_DYN_SMEM(uint32_t, sp_bins);                               // SP_HIST_WARPS x 2^R u32
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x * SP_HIST_WARPS + warp;      // (file, bucket)
+    const uint32_t f = item >> SP_BUCKET_BITS, b = item & (SP_BUCKETS - 1);
+    const uint32_t nbins = 1u << R;
+    uint32_t *bins = sp_bins + (size_t)warp * nbins;
+    const uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
+    const uint32_t s = bo[b], n = bo[b + 1] - s;
+    if (n == 0) return;                                           // (the whole warp)
+    for (uint32_t i = lane; i < nbins; i += 32) bins[i] = 0;
+    KF_SYNCWARP();
+    const uint32_t *gk = keys + kbase[f] + s;
+    const uint32_t lowmask = nbins - 1u;
+    for (uint32_t i = lane; i < n; i += 32) atomicAdd(bins + (gk[i] & lowmask), 1u);
+    KF_SYNCWARP();
+    unsigned long long pos = out_base[f] + (unsigned long long)ooff[item];
+    const unsigned long long hi = (unsigned long long)b << R;
+    for (uint32_t i0 = 0; i0 < nbins; i0 += 32) {
+        const uint32_t i = i0 + (uint32_t)lane;
+        const uint32_t c = i < nbins ? bins[i] : 0u;
+        const unsigned m = __ballot_sync(FULL, c != 0u);
+        if (c) {
+            const unsigned long long o = pos + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+            codes_out[o] = hi | (unsigned long long)i;
+            counts_out[o] = c;
+        }
+        pos += (unsigned long long)__popc(m);
     }
 }
 

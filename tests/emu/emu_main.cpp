@@ -107,34 +107,54 @@ int main(int argc, char **argv) {
         const int thr = threads == 512 ? 64 : threads;
         std::vector<uint64_t> kbase(n + 1, 0);
         for (int f = 0; f < n; f++) kbase[f + 1] = kbase[f] + ((len[f] && arena[off[f]] == '>') ? len[f] : 0);
+        std::vector<int> file_t0(n + 1, 0);
+        { size_t t = 0; for (int f = 0; f < n; f++) { file_t0[f] = (int)t; while (t < tiles.size() && tiles[t].file == (uint32_t)f) t++; } file_t0[n] = (int)t; }
+        const int R = 2 * k - SP_BUCKET_BITS;
+        const bool hist_path = R <= SP_HIST_MAX_R && k <= 16;
         uint32_t S = 1;
         while (S < SP_BUCKETS / 8 && (uint64_t)n * S < 16) S <<= 1;
-        const uint32_t n_items = (uint32_t)n * S;
-        std::vector<uint32_t> hist((size_t)n * SP_BUCKETS, 0u), boff((size_t)n * (SP_BUCKETS + 1), 0u), cursor((size_t)n * SP_BUCKETS, 0u), nd(n_items, 0u);
-        std::vector<unsigned long long> ooff(n_items + 1, 0ull), totals(n, 0ull);
+        const uint32_t n_items = hist_path ? (uint32_t)n * SP_BUCKETS : (uint32_t)n * S;
+        std::vector<uint32_t> tile_hist((tiles.size() + 1) * SP_BUCKETS, 0xDEADu), boff((size_t)n * (SP_BUCKETS + 1), 0u), nd(n_items, 0u), ooff32(n_items, 0u);
+        std::vector<unsigned long long> ooff(n_items + 1, 0ull), totals(n, 0ull), nd_file(n, 0ull), out_base(n, 0ull);
         auto body = [&](auto kt) {
             using KT = decltype(kt);
             std::vector<KT> keys(kbase[n] + 16, (KT)0x5A5A5A5A5A5A5A5Aull);
-            auto extract = [&](auto modec) {
+            auto tile_pass = [&](auto modec) {
                 constexpr int M = decltype(modec)::value;
                 emu::launch(grid, thr, 0, [&]() {
-                    if (k > 16) { if (thr == 32) sparse_extract_kernel<M, KT, true, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data());
-                                  else sparse_extract_kernel<M, KT, true, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data()); }
-                    else { if (thr == 32) sparse_extract_kernel<M, KT, false, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data());
-                           else sparse_extract_kernel<M, KT, false, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, hist.data(), cursor.data(), keys.data(), kbase.data()); }
+                    if (k > 16) { if (thr == 32) sparse_tile_kernel<M, KT, true, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data());
+                                  else sparse_tile_kernel<M, KT, true, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data()); }
+                    else { if (thr == 32) sparse_tile_kernel<M, KT, false, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data());
+                           else sparse_tile_kernel<M, KT, false, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data()); }
                 });
             };
-            extract(std::integral_constant<int, 0>());
-            emu::launch(n, 1024, 0, [&]() { sparse_scan_buckets_kernel(hist.data(), boff.data(), cursor.data(), totals.data(), 0u); });
-            extract(std::integral_constant<int, 1>());
-            emu::launch(n_items, 64, 65536, [&]() { sparse_sort_kernel<KT, 64>(keys.data(), kbase.data(), boff.data(), S, nd.data()); });
-            emu::launch(1, 1024, 0, [&]() { sparse_scan_items_kernel(nd.data(), ooff.data(), n_items); });
-            std::vector<unsigned long long> codes(ooff[n_items] + 1, 0ull);
-            std::vector<uint32_t> cnts(ooff[n_items] + 1, 0u);
-            emu::launch(n_items, 64, 0, [&]() { sparse_emit_kernel<KT, 64>(keys.data(), kbase.data(), boff.data(), S, ooff.data(), codes.data(), cnts.data()); });
+            tile_pass(std::integral_constant<int, 0>());
+            emu::launch(n, 1024, 0, [&]() { sparse_tile_scan_kernel(tile_hist.data(), file_t0.data(), boff.data(), totals.data(), 0u); });
+            tile_pass(std::integral_constant<int, 1>());
+            std::vector<unsigned long long> codes;
+            std::vector<uint32_t> cnts;
+            std::vector<unsigned long long> row_off(n + 1, 0ull);
+            if constexpr (sizeof(KT) == 4) {
+                if (hist_path) {
+                    emu::launch(n_items / SP_HIST_WARPS, 32 * SP_HIST_WARPS, 0, [&]() { sparse_bucket_distinct_kernel((const uint32_t *)keys.data(), kbase.data(), boff.data(), R, nd.data()); });
+                    emu::launch(n, 1024, 0, [&]() { sparse_scan_distinct_kernel(nd.data(), ooff32.data(), nd_file.data()); });
+                    unsigned long long run = 0;
+                    for (int f = 0; f < n; f++) { out_base[f] = run; run += nd_file[f]; row_off[f + 1] = run; }
+                    codes.assign(run + 1, 0ull); cnts.assign(run + 1, 0u);
+                    emu::launch(n_items / SP_HIST_WARPS, 32 * SP_HIST_WARPS, (size_t)SP_HIST_WARPS * ((size_t)1 << R) * 4, [&]() {
+                        sparse_bucket_emit_kernel((const uint32_t *)keys.data(), kbase.data(), boff.data(), R, ooff32.data(), out_base.data(), codes.data(), cnts.data()); });
+                }
+            }
+            if (!hist_path) {
+                emu::launch(n_items, 64, 65536, [&]() { sparse_sort_kernel<KT, 64>(keys.data(), kbase.data(), boff.data(), S, nd.data()); });
+                emu::launch(1, 1024, 0, [&]() { sparse_scan_items_kernel(nd.data(), ooff.data(), n_items); });
+                codes.assign(ooff[n_items] + 1, 0ull); cnts.assign(ooff[n_items] + 1, 0u);
+                emu::launch(n_items, 64, 0, [&]() { sparse_emit_kernel<KT, 64>(keys.data(), kbase.data(), boff.data(), S, ooff.data(), codes.data(), cnts.data()); });
+                for (int f = 0; f < n; f++) row_off[f + 1] = ooff[(size_t)(f + 1) * S];
+            }
             for (int f = 0; f < n; f++) {
                 printf("%llu", totals[f]);
-                for (unsigned long long e = ooff[(size_t)f * S]; e < ooff[(size_t)(f + 1) * S]; e++) printf(" %llu:%u", codes[e], cnts[e]);
+                for (unsigned long long e = row_off[f]; e < row_off[f + 1]; e++) printf(" %llu:%u", codes[e], cnts[e]);
                 printf("\nF\n");
             }
         };
