@@ -44,7 +44,6 @@ extern "C" {
 #define KF_FLAG_FORCE_WALKER 4u  /* debug: disable the vectorised fast path (byte walker only)   */
 #define KF_FLAG_NO_LINEGRID 8u   /* debug: generic kernels only (no fixed-line-width kernel at k = 7, no partitioned kernel at k = 8..10) */
 #define KF_FLAG_PART_ALL 16u     /* debug: k = 8..10 partitioned kernel for files of any size (default: >= 256 KiB) */
-#define KF_FLAG_FUSED_FOLD 32u   /* experiment: the k = 7 line kernel finishes files that lie wholly in one CTA by itself (fold + normalise in its flush); measured slower than the separate fold kernel, off by default */
 
 /* limits */
 #define KF_MIN_K 1

@@ -62,8 +62,6 @@ struct Ctx {
     uint32_t *d_file_P = nullptr; size_t fP_cap = 0;
     uint32_t *d_width_counts = nullptr;
     uint32_t *d_file_row = nullptr; size_t frow_cap = 0;          // first forward-count row of every file (+ total)
-    uint32_t *d_file_done = nullptr; size_t fdone_cap = 0;       // k = 7: files the line kernel has finished by itself (fold fused into its flush)
-    FoldOut cur_fo{};                                             // outputs of the current call, for the line kernel
     uint32_t *d_cta_first_rank = nullptr; size_t cfr_cap = 0;    // per line-kernel CTA: how many earlier CTAs hold a piece of its first file
     uint32_t pc_rows = 0;
     // k = 8..10: (file, partition) work items of the partitioned shared-memory kernel
@@ -324,7 +322,7 @@ int launch_linegrid_b(const uint8_t *d_arena, int grid_generic, cudaStream_t s) 
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid_generic / CTAS_PER_SM, THREADS_LG, smem, s>>>(d_arena, g.d_tiles, g.d_cta_begin, g.d_file_P, g.d_file_off, g.d_file_len,
                                                              (unsigned long long *)g.d_fwd, g.d_file_row, g.d_cta_first_rank, CTAS_PER_SM,
-                                                             g.d_width_counts, g.cur_fo);
+                                                             g.d_width_counts);
     CK(cudaGetLastError());
     return KF_OK;
 }
@@ -538,17 +536,13 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
     }
     const bool force_walker = (flags & KF_FLAG_FORCE_WALKER) != 0;
     const bool use_lg = smem_path && k == 7 && !force_walker && !(flags & KF_FLAG_NO_LINEGRID);
-    if (use_lg) {
-        if ((rc = ensure(g.d_file_done, g.fdone_cap, (size_t)f1 * sizeof(uint32_t))) != KF_OK) return rc;
-        g.cur_fo = FoldOut{g.d_canon[k], d_counts, d_freq, d_feat, d_totals, (flags & KF_FLAG_FUSED_FOLD) ? g.d_file_done : nullptr, flags, (uint32_t)V};
-    }
     if (smem_path) {
         if (!g.ev_valid) CK(cudaEventRecord(g.ev_k0, s));
         // line width per file (0 = generic kernel) + zeroing of the rows the line kernel will not write
         CK(cudaMemsetAsync(g.d_width_counts, 0, 8 * sizeof(uint32_t), s));
         probe_line_width_kernel<<<(f1 + 3) / 4, 128, 0, s>>>(d_arena, g.d_file_off, g.d_file_len, g.d_formats, (int)f1,
                                                                 use_lg ? 0u : 1u, g.d_file_P, g.d_width_counts,
-                                                                (unsigned long long *)g.d_fwd, g.d_file_row, (uint32_t)NB, use_lg ? g.d_file_done : nullptr);
+                                                                (unsigned long long *)g.d_fwd, g.d_file_row, (uint32_t)NB);
         CK(cudaGetLastError());
         CK(cudaEventRecord(g.ev_k1, s));
         g.ev_valid = true;
@@ -594,14 +588,12 @@ int run_files(const uint8_t *d_arena, const uint64_t *offsets, const uint64_t *l
             const size_t fsm = NB * sizeof(uint32_t);
             CK(cudaFuncSetAttribute(fold_normalize_smem_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             fold_normalize_smem_kernel<uint32_t><<<nf, FOLD_THREADS, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
-                                                                             use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals,
-                                                                             use_lg ? g.d_file_done : nullptr);
+                                                                             use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
         } else {
             const size_t fsm = NB * sizeof(unsigned long long);
             CK(cudaFuncSetAttribute(fold_normalize_smem_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
             fold_normalize_smem_kernel<unsigned long long><<<nf, FOLD_THREADS, fsm, s>>>((const unsigned long long *)g.d_fwd, g.d_canon[k], k, V, flags,
-                                                                                       use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals,
-                                                                             use_lg ? g.d_file_done : nullptr);
+                                                                                       use_lg ? g.d_file_P : nullptr, g.d_file_row, d_counts, d_freq, d_feat, d_totals);
         }
     } else if (V > (1 << 14)) {
         // large vocabulary: counts + per-file total first, then the normalisation from the counts just written (the
@@ -727,7 +719,7 @@ int kf_shutdown(void) {
     sparse_free_all();
     void *dev_ptrs[] = {g.d_fwd, g.d_tiles, g.d_cta_begin, g.d_arena, g.d_counts, g.d_freq, g.d_totals, g.d_seq, g.d_win_off, g.d_win_len,
                         g.d_fq_tiles, g.d_fq_cta_begin, g.d_fq_err, g.d_file_off, g.d_file_len, g.d_formats, g.d_file_P, g.d_file_row,
-                        g.d_cta_first_rank, g.d_width_counts, g.d_file_t0, g.d_items, g.d_item_counter, g.d_stream, g.d_fold_tot, g.d_file_done};
+                        g.d_cta_first_rank, g.d_width_counts, g.d_file_t0, g.d_items, g.d_item_counter, g.d_stream, g.d_fold_tot};
     for (void *p : dev_ptrs) if (p) cudaFree(p);
     for (auto &p : g.d_canon) { if (p) cudaFree(p); p = nullptr; }
     for (auto &p : g.d_rank) { if (p) cudaFree(p); p = nullptr; }

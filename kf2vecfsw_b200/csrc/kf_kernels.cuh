@@ -875,25 +875,6 @@ __device__ KF_NOINLINE void lg_generic_region(const Src src, uint64_t lo, uint64
 //   rare paths : a line holding a non-ACGT byte (or whose 6 look-ahead bytes do) goes to the exact byte walker on
 //                global memory; a line that breaks the grid (short last line, header, other width) goes to the
 //                exact generic range processor up to the next sequence line, where the grid restarts.
-__device__ __forceinline__ uint32_t revcomp_std(uint32_t x, int k) {
-    uint32_t y = __brev(~x);
-    y = ((y & 0xAAAAAAAAu) >> 1) | ((y & 0x55555555u) << 1);
-    return y >> (32 - 2 * k);
-}
-__device__ __forceinline__ uint32_t std_to_gray(uint32_t x) { return x ^ ((x >> 1) & 0x55555555u); }
-
-// What the line kernel needs to finish a file by itself (fold to canonical, total, +0.5, normalise: main.py:327-342) when
-// the whole file lies in one CTA: no forward row is written and read back, the fold kernel skips the file (file_done).
-struct FoldOut {
-    const uint32_t *canon;            // canonical 7-mers in vocabulary order (sorted alphabet codes), V entries
-    unsigned long long *counts;       // [n, V] or null
-    double *freq;                     // [n, V] or null
-    float *feat;                      // [n, V] or null
-    unsigned long long *totals;       // [n] or null
-    uint32_t *file_done;              // [n]: 1 = finished here (zeroed by the probe kernel); null: never finish here
-    uint32_t flags, V;
-};
-
 constexpr int LN_MAX_LW = 100;     // widest wrapped FASTA with a line-kernel instantiation (shared memory: 120 columns would not leave room)
 constexpr int LN_SCR_WORDS = 36;   // per-warp scratch: one line + look-ahead re-fetched from global memory (P + LA + 3 bytes at LW = 120: 130)
 template <int LW>
@@ -1657,7 +1638,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
                          const uint32_t *__restrict__ file_P, const uint64_t *__restrict__ file_off,
                          const uint64_t *__restrict__ file_len, unsigned long long *__restrict__ g_fwd,
                          const uint32_t *__restrict__ file_row, const uint32_t *__restrict__ cta_first_rank, int cta_stride,
-                         const uint32_t *__restrict__ width_counts, const FoldOut fo) {
+                         const uint32_t *__restrict__ width_counts) {
     // LW == 0: every supported kind of file in ONE launch (the piece's width picks the code): no empty launches, and a
     // batch of mixed widths keeps all CTAs busy.  Staging is sized for the widest line then.
     constexpr bool ALL = LW == 0;
@@ -1755,16 +1736,10 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
         // file's rows in g_fwd (the fold kernel undoes it).  xk is the first 7-mer of the 8-mers xk + a*16384 (word
         // a*8192 + (xk >> 1); odd xk: half of the high half, even xk: low - high / 2) and the second 7-mer of the 8-mers
         // 4xk .. 4xk+3 (words 2xk, 2xk+1: sum of the low halves).  One thread: xk = 2j and 2j+1.
-        // A file that lies wholly in this CTA (one row) is finished here: its forward counts go to shared memory instead of
-        // the row, the canonical fold gathers from there.
-        const bool whole = ok && fo.file_done != nullptr && file_row[file + 1] - file_row[file] == 1u && file_len[file] < (1ull << 32);
-        constexpr int NJ = (NB7 / 2 + THREADS - 1) / THREADS;
-        uint32_t c0r[NJ], c1r[NJ];
-#pragma unroll
-        for (int jj = 0; jj < NJ; jj++) {
-            const int j = threadIdx.x + jj * THREADS;
-            uint32_t c0 = 0, c1 = 0;
-            if (ok && j < NB7 / 2) {
+#pragma unroll 4
+        for (int j = threadIdx.x; j < NB7 / 2; j += THREADS) {
+            unsigned long long c0 = 0, c1 = 0;
+            if (ok) {
                 const uint4 pw = *reinterpret_cast<const uint4 *>(hist16 + 4 * j);
                 const uint32_t sw = single16[j];
                 c0 = (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu) + (sw & 0xFFFFu);
@@ -1776,59 +1751,7 @@ count_fasta_lines_kernel(const uint8_t *__restrict__ arena, const Tile *__restri
                     c1 += w >> 17;
                 }
             }
-            c0r[jj] = c0; c1r[jj] = c1;
-            if (!whole && j < NB7 / 2) reinterpret_cast<ulonglong2 *>(g)[j] = make_ulonglong2((unsigned long long)c0, (unsigned long long)c1);
-        }
-        if (whole) {
-            __syncthreads();                       // every thread has read the histograms
-            uint32_t *fwd = hist16;                // 16,384 u32 forward counts, index = 7-mer with its digits reversed
-#pragma unroll
-            for (int jj = 0; jj < NJ; jj++) {
-                const int j = threadIdx.x + jj * THREADS;
-                if (j < NB7 / 2) *reinterpret_cast<uint2 *>(fwd + 2 * j) = make_uint2(c0r[jj], c1r[jj]);
-            }
-            __syncthreads();
-            constexpr int NI = (NB7 / 2 + THREADS - 1) / THREADS;   // canonical 7-mers per thread (V = 8,192)
-            uint32_t cc[NI];
-            uint32_t local = 0;
-#pragma unroll
-            for (int it = 0; it < NI; it++) {
-                const uint32_t i = threadIdx.x + (uint32_t)it * THREADS;
-                uint32_t v = 0;
-                if (i < fo.V) {
-                    const uint32_t m = fo.canon[i];
-                    const uint32_t r = revcomp_std(m, 7);
-                    v = fwd[digit_rev7(std_to_gray(m))];
-                    if (r != m) v += fwd[digit_rev7(std_to_gray(r))];
-                }
-                cc[it] = v;
-                local += v;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
-            if (lane == 0) s_part[warp] = local;
-            __syncthreads();
-            unsigned long long total = 0;
-#pragma unroll
-            for (int w = 0; w < NWARPS; w++) total += s_part[w];
-            const bool pc = fo.flags & 1u, raw = fo.flags & 2u;
-            const double denom = (double)total + (pc ? 0.5 * (double)fo.V : 0.0);
-            const size_t orow = (size_t)file * (size_t)fo.V;
-#pragma unroll
-            for (int it = 0; it < NI; it++) {
-                const uint32_t i = threadIdx.x + (uint32_t)it * THREADS;
-                if (i < fo.V) {
-                    if (fo.counts) fo.counts[orow + i] = (unsigned long long)cc[it];
-                    double v = (double)cc[it] + (pc ? 0.5 : 0.0);
-                    if (!raw) v = v / denom;   // IEEE fp64 division: correctly rounded, bit-exact with numpy
-                    if (fo.freq) fo.freq[orow + i] = v;
-                    if (fo.feat) fo.feat[orow + i] = (float)(v * 1e4);   // train_classifier_model.py:149,323
-                }
-            }
-            if (threadIdx.x == 0) {
-                if (fo.totals) fo.totals[file] = total;
-                fo.file_done[file] = 1u;
-            }
+            reinterpret_cast<ulonglong2 *>(g)[j] = make_ulonglong2(c0, c1);
         }
 #ifdef KF_PIECE_TIMING
         const long long tw2 = clock64();
@@ -2027,12 +1950,10 @@ probe_line_width_kernel(const uint8_t *__restrict__ arena, const uint64_t *__res
                         const uint64_t *__restrict__ file_len, const uint8_t *__restrict__ formats, int n,
                         uint32_t force_generic, uint32_t *__restrict__ file_P,
                         uint32_t *__restrict__ width_counts /* [line_width_slot()]: 0 generic, 1..3 60/70/80, 4 long lines, 5 100, 7 50 */,
-                        unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row, uint32_t row_bins,
-                        uint32_t *__restrict__ file_done) {
+                        unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row, uint32_t row_bins) {
     const int lane = threadIdx.x & 31;
     const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (f >= n) return;
-    if (lane == 0 && file_done) file_done[f] = 0u;
     uint32_t P = 0;
     if (!force_generic && formats[f] == (uint8_t)'>') {
         const uint64_t F0 = file_off[f], L = file_len[f];
@@ -2446,6 +2367,12 @@ gather_windows_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restric
 // ------------------------------------------------------------------------------------------------
 // Fold to canonical + total + pseudocount + normalise (main.py:327-342), one CTA per file
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t revcomp_std(uint32_t x, int k) {
+    uint32_t y = __brev(~x);
+    y = ((y & 0xAAAAAAAAu) >> 1) | ((y & 0x55555555u) << 1);
+    return y >> (32 - 2 * k);
+}
+__device__ __forceinline__ uint32_t std_to_gray(uint32_t x) { return x ^ ((x >> 1) & 0x55555555u); }
 
 // k <= 7: the file's rows are summed with coalesced loads into shared memory (4^k entries: u32 when no bin of the
 // batch can reach 2^32, i.e. every file is shorter than 4 GiB -- 64 KB at k = 7, three CTAs per SM -- else u64), then
@@ -2463,12 +2390,11 @@ __global__ void __launch_bounds__(FOLD_THREADS)
 fold_normalize_smem_kernel(const unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ canon, int k, long long V,
                            uint32_t flags, const uint32_t *__restrict__ file_P, const uint32_t *__restrict__ file_row,
                            unsigned long long *__restrict__ counts, double *__restrict__ freq, float *__restrict__ feat,
-                           unsigned long long *__restrict__ totals, const uint32_t *__restrict__ file_done) {
+                           unsigned long long *__restrict__ totals) {
     KF_DYN_SMEM(unsigned long long, fold_smem);
     SmT *row = reinterpret_cast<SmT *>(fold_smem);
     const uint32_t NB = 1u << (2 * k);
     const uint32_t file = blockIdx.x;
-    if (file_done && file_done[file]) return;   // finished by the line kernel (a file that lay wholly in one CTA)
     const uint32_t row0 = file_row[file], nrows = file_row[file + 1] - row0;
     const unsigned long long *g = g_fwd + (size_t)row0 * NB;
     const size_t orow = (size_t)file * (size_t)V;

@@ -19,7 +19,6 @@ KF_CHUNK = 512
 KF_TAIL_PAD = 4096
 KF_FLAG_NO_LINEGRID = 8
 KF_FLAG_PART_ALL = 16
-KF_FLAG_FUSED_FOLD = 32
 KF_MAX_K = 12
 KF_SPARSE_MIN_K = 6
 KF_SPARSE_MAX_K = 31
@@ -121,7 +120,7 @@ def _check(rc: int, what: str = ""):
 def _flags(pseudocount: bool, raw_cnt: bool, force_walker: bool = False, no_linegrid: bool = False, part_all: bool = False) -> int:
     return (KF_FLAG_PSEUDOCOUNT if pseudocount else 0) | (KF_FLAG_RAW_CNT if raw_cnt else 0) | \
            (KF_FLAG_FORCE_WALKER if force_walker else 0) | (KF_FLAG_NO_LINEGRID if no_linegrid else 0) | \
-           (KF_FLAG_PART_ALL if part_all else 0) | (KF_FLAG_FUSED_FOLD if os.environ.get("KF_FUSED_FOLD") else 0)
+           (KF_FLAG_PART_ALL if part_all else 0)
 
 
 # ---- lifecycle -----------------------------------------------------------------------------------

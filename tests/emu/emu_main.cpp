@@ -50,11 +50,11 @@ static void run(const uint8_t *arena, const std::vector<Tile> &tiles, const std:
 template <int LW, int THREADS, bool VIRT = false>
 static void run_lg(const uint8_t *arena, const std::vector<Tile> &tiles, const std::vector<int> &cta_begin, int grid,
                    const uint32_t *file_P, const uint64_t *off, const uint64_t *len, unsigned long long *fwd,
-                   const uint32_t *file_row, const uint32_t *file_first_cta, const uint32_t *wc, const FoldOut fo = FoldOut{}) {
+                   const uint32_t *file_row, const uint32_t *file_first_cta, const uint32_t *wc) {
     constexpr int NW = THREADS / 32;
     size_t smem = lines_kernel_smem<(LW == 0 ? LN_MAX_LW : LW), (VIRT || LW == 0)>(NW);
     emu::launch(grid, THREADS, smem, [&]() {
-        count_fasta_lines_kernel<LW, THREADS, 0u, VIRT>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc, fo);
+        count_fasta_lines_kernel<LW, THREADS, 0u, VIRT>(arena, tiles.data(), cta_begin.data(), file_P, off, len, fwd, file_row, file_first_cta, 1, wc);
     });
 }
 
@@ -223,19 +223,12 @@ int main(int argc, char **argv) {
     std::vector<uint32_t> file_P(n, 0);
     std::vector<uint32_t> wc(8, 0);
     const bool lg = use_lg && k == 7 && !fw;
-    std::vector<uint32_t> canon; canonical_codes(k, canon);
-    long long V = (long long)canon.size();
-    std::vector<unsigned long long> counts((size_t)n * V, 0xBADBADull), totals(n, 0xBADull);
-    std::vector<double> freq((size_t)n * V, -1.0);
-    std::vector<uint32_t> file_done(n, 0xDEADu);   // (garbage: the probe kernel must zero it)
-    const bool fused = lg && getenv("KF_EMU_FUSED_FOLD") != nullptr;   // (the experiment of KF_FLAG_FUSED_FOLD)
-    const FoldOut fo{canon.data(), counts.data(), freq.data(), (float *)nullptr, totals.data(), fused ? file_done.data() : (uint32_t *)nullptr, 0u, (uint32_t)V};
-    emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data(), fwd.data(), file_row.data(), (uint32_t)NB, lg ? file_done.data() : (uint32_t *)nullptr); });
+    emu::launch(n, 32, 0, [&]() { probe_line_width_kernel(arena.data(), off.data(), len.data(), formats.data(), n, lg ? 0u : 1u, file_P.data(), wc.data(), fwd.data(), file_row.data(), (uint32_t)NB); });
     if (lg) {
         // one launch for all widths and the long-line files, as kf_api.cu does
-        if (threads == 512) run_lg<0, 512>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data(), fo);
-        else if (threads == 64) run_lg<0, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data(), fo);
-        else run_lg<0, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data(), fo);
+        if (threads == 512) run_lg<0, 512>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+        else if (threads == 64) run_lg<0, 64>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
+        else run_lg<0, 32>(arena.data(), tiles, cta_begin, grid, file_P.data(), off.data(), len.data(), fwd.data(), file_row.data(), file_first_cta.data(), wc.data());
         int nlg = 0, nvl = 0; for (auto P : file_P) { nlg += P != 0; nvl += P == KF_P_VIRTUAL; }
         fprintf(stderr, "linegrid files: %d of %d (virtual lines: %d)\n", nlg, n, nvl);
     }
@@ -266,8 +259,11 @@ int main(int argc, char **argv) {
                 if (err[f] != ~0ull && err[f] - off[f] < len[f]) fprintf(stderr, "fastq layout violation file %d at %llu\n", f, err[f] - off[f]);
         }
     }
-    if (lg) { int nd = 0; for (int f = 0; f < n; f++) nd += file_done[f] == 1u; fprintf(stderr, "files finished by the line kernel: %d of %d\n", nd, n); }
-    emu::launch(n, FOLD_THREADS, NB * sizeof(unsigned long long), [&]() { fold_normalize_smem_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data(), lg ? file_done.data() : (const uint32_t *)nullptr); });
+    std::vector<uint32_t> canon; canonical_codes(k, canon);
+    long long V = (long long)canon.size();
+    std::vector<unsigned long long> counts((size_t)n * V), totals(n);
+    std::vector<double> freq((size_t)n * V);
+    emu::launch(n, FOLD_THREADS, NB * sizeof(unsigned long long), [&]() { fold_normalize_smem_kernel<unsigned long long>(fwd.data(), canon.data(), k, V, 0u, lg ? file_P.data() : (const uint32_t *)nullptr, file_row.data(), counts.data(), freq.data(), (float *)nullptr, totals.data()); });
     for (int f = 0; f < n; f++) {
         printf("%llu", totals[f]);
         for (long long i = 0; i < V; i++) printf(" %llu", counts[(size_t)f * V + i]);

@@ -661,19 +661,3 @@ def test_peer_gather_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
-
-
-def test_fused_fold_experiment_is_exact(eng, toy_inputs, monkeypatch):
-    """KF_FLAG_FUSED_FOLD (off by default: measured slower than the separate fold kernel): files that lie wholly in one CTA
-    are folded and normalised inside the line kernel's flush -- same counts, totals and bit-identical frequencies."""
-    bufs = [toy_inputs["G000830275sub"], toy_inputs["G000402355sub"]] + [kfsynth.synth_fasta(9, i, 1_500_000) for i in range(20)] + \
-           [kfsynth.synth_fasta(9, 50, 3_000_000, line_width=10 ** 9)]
-    base = eng.count_buffers(bufs, k=7)
-    monkeypatch.setenv("KF_FUSED_FOLD", "1")
-    for kw in ({}, {"pseudocount": True}, {"raw_cnt": True}):
-        a = eng.count_buffers(bufs, k=7, **kw)
-        monkeypatch.delenv("KF_FUSED_FOLD")
-        b = eng.count_buffers(bufs, k=7, **kw)
-        monkeypatch.setenv("KF_FUSED_FOLD", "1")
-        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1], equal_nan=True) and np.array_equal(a[2], b[2])
-    assert np.array_equal(base[0], b[0]) or True

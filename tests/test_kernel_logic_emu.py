@@ -307,23 +307,3 @@ def test_emulated_multiline_fastq(tmp_path):
         for f, (tot, counts, _) in zip(files, res):
             ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
             assert np.array_equal(counts, ref), (s, k, f)
-
-
-def test_emulated_fused_fold_experiment(toy_inputs, tmp_path):
-    """KF_FLAG_FUSED_FOLD: the line kernel finishes the files that lie wholly in one CTA by itself -- counts and fp64
-    frequencies as the separate fold kernel gives them."""
-    files = []
-    for s in ("G000830275sub", "G000402355sub", "G000830295"):
-        p = str(tmp_path / (s + ".fna"))
-        open(p, "wb").write(toy_inputs[s])
-        files.append((s, p))
-    env = dict(os.environ, KF_EMU_FUSED_FOLD="1")
-    for grid in (1, 2):
-        p = subprocess.run([BIN, "7", "64", str(grid), "0", "64", "1"] + [f for _, f in files], capture_output=True, text=True, check=True, env=env)
-        assert "files finished by the line kernel: %d of 3" % (3 if grid == 1 else 1) in p.stderr or grid == 2, p.stderr
-        out = p.stdout.strip().split("\n")
-        for i, (s, _) in enumerate(files):
-            ref = o.canonical_counts_bytes(toy_inputs[s], 7)
-            vals, _ = o.row_values(ref, False, False)
-            assert np.array_equal(np.array(out[2 * i].split()[1:], dtype=np.uint64), ref), (grid, s)
-            assert np.array_equal(np.array(out[2 * i + 1].split()[1:], dtype=np.float64), vals), (grid, s)

@@ -181,7 +181,7 @@ void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     CK(cudaMalloc(&d_P, 4)); CK(cudaMemcpy(d_P, &P, 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_off, 8)); CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_len, 8)); CK(cudaMemcpy(d_len, &len, 8, cudaMemcpyHostToDevice));
-    uint32_t *d_wc; uint32_t wc[8] = {1, 1, 1, 1, 1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 32)); CK(cudaMemcpy(d_wc, wc, 32, cudaMemcpyHostToDevice));
+    uint32_t *d_wc; uint32_t wc[4] = {1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 16)); CK(cudaMemcpy(d_wc, wc, 16, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_fwd, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_fwd, 0, (size_t)sms * 16384 * 8));
     CK(cudaMalloc(&d_scr, (size_t)sms * 16384 * 8)); CK(cudaMemset(d_scr, 0, (size_t)sms * 16384 * 8));
     uint32_t *d_row, *d_fc; uint32_t rows[2] = {0u, (uint32_t)sms};
@@ -193,7 +193,7 @@ void run_lg(const uint8_t *arena, size_t bytes, int sms) {
     for (int it = 0; it < 5; it++) {
         CK(cudaMemset(d_fwd, 0, (size_t)sms * 16384 * 8));
         CK(cudaEventRecord(e0));
-        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, 1, d_wc, FoldOut{});
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, 1, d_wc);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (it >= 1 && ms < best) best = ms;
@@ -283,7 +283,7 @@ void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms, int m
     CK(cudaMalloc(&d_P, 4 * nfiles)); CK(cudaMemcpy(d_P, P.data(), 4 * nfiles, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_off, 8 * nfiles)); CK(cudaMemcpy(d_off, off.data(), 8 * nfiles, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_len, 8 * nfiles)); CK(cudaMemcpy(d_len, len.data(), 8 * nfiles, cudaMemcpyHostToDevice));
-    uint32_t *d_wc; uint32_t wc[8] = {1, 1, 1, 1, 1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 32)); CK(cudaMemcpy(d_wc, wc, 32, cudaMemcpyHostToDevice));
+    uint32_t *d_wc; uint32_t wc[4] = {1, 1, 1, 1}; CK(cudaMalloc(&d_wc, 16)); CK(cudaMemcpy(d_wc, wc, 16, cudaMemcpyHostToDevice));
     std::vector<uint32_t> frow(nfiles + 1, 0), ffc(sms, 0);
     {
         std::vector<uint32_t> cnt(nfiles, 0); std::vector<int> last(nfiles, -1);
@@ -309,7 +309,7 @@ void run_lg_files(uint8_t *arena, size_t arena_bytes, int nfiles, int sms, int m
         CK(cudaMemset(d_fwd, 0, nrows * 16384 * 8));
         CK(cudaMemcpyToSymbol(g_piece_timing, zero, sizeof zero));
         CK(cudaEventRecord(e0));
-        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, 1, d_wc, FoldOut{});
+        kern<<<sms, THREADS, smem>>>(arena, d_tiles, d_cb, d_P, d_off, d_len, d_fwd, d_row, d_fc, 1, d_wc);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (it >= 1 && ms < best) { best = ms; CK(cudaMemcpyFromSymbol(tm, g_piece_timing, sizeof tm)); }
