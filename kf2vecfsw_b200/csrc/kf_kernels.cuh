@@ -454,6 +454,7 @@ __device__ inline void __syncwarp_emu() { emu::exchange(0, 0); }
 #define KF_LDCG(p) (*(p))
 __device__ inline void stage_bar_init(uint64_t *) {}
 __device__ inline void stage_issue(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ inline void stage_issue2(void *d0, const void *s0, void *d1, const void *s1, uint32_t bytes, uint64_t *) { memcpy(d0, s0, bytes); memcpy(d1, s1, bytes); }
 __device__ inline void stage_wait(uint64_t *, uint32_t) { KF_SYNCWARP(); }
 __device__ inline uint32_t smem_addr(const void *) { return 0; }
 __device__ inline void red_shared_add(uint32_t *hist, uint32_t, uint32_t off, uint32_t v) { atomicAdd(hist + (off >> 2), v); }
@@ -475,6 +476,17 @@ __device__ __forceinline__ void stage_issue(void *dst, const void *src, uint32_t
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// one lane: two bulk copies of `bytes` each on one barrier phase
+__device__ __forceinline__ void stage_issue2(void *d0, const void *s0, void *d1, const void *s1, uint32_t bytes, uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(d0)),
+                 "l"(s0), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(d1)),
+                 "l"(s1), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void stage_wait(uint64_t *bar, uint32_t parity) {
@@ -888,7 +900,21 @@ struct LineGeom {
     static constexpr int NPAIR = LW / 2;
     static constexpr int WIN = 32 * P;               // bytes per full window
     static constexpr int NEED = 31 * P + 4 * NWA + 4;                 // bytes a window must hold from its first line start
-    static constexpr int STAGE = ((NEED + 16 + 112 + 15) / 16) * 16;  // + alignment + slack to find a unit's first line start
+    // DUAL: a window is staged as two halves of 16 lines (two bulk copies; 16 P is a multiple of 16), the second one HOFF
+    // bytes after the first with HOFF = 64 (mod 128), i.e. 16 banks out of phase.  At P = 71 the lanes' first words fall
+    // on 8 banks (17.75 words per line: four-way conflicts on every LDS); with the upper 16 lanes moved by 16 banks they
+    // are two-way: 0.39 -> 0.45 of the roofline on 70-column files.  At P = 81 (two-way to start with) the same layout plus
+    // windows that start at a multiple of 4 bytes is conflict-free, but measured SLOWER (round 1 and again in round 2:
+    // one-record file 11.8 -> 10.8 bases/clk/SM, headline kernel 1.76 -> 1.81 ms): two bulk copies per window cost more
+    // than the 29 wavefronts per window they save.
+    static constexpr bool DUAL = LW == 70;
+    static constexpr int HNEED = 15 * P + 4 * NWA + 4;                // bytes a half must hold from its first line start
+    static constexpr int HCOPY = ((HNEED + 15 + 112 + 15) / 16) * 16; // + alignment + slack to find a unit's first line start
+    static constexpr int HOFF = ((HCOPY + 63) / 128) * 128 + 64;      // >= HCOPY, = 64 (mod 128)
+    static constexpr int STAGE = DUAL ? HOFF + HCOPY : ((NEED + 16 + 112 + 15) / 16) * 16;  // + alignment + slack to find a unit's first line start
+    static_assert(!DUAL || (HOFF >= HCOPY && HOFF % 128 == 64 && (16 * P) % 16 == 0), "half layout");
+    // staged bytes from `base` that line l of the window may use (its slot and look-ahead must lie inside the copy)
+    static constexpr int WOFF_MAX = DUAL ? HCOPY - HNEED : STAGE - NEED;
 };
 
 __device__ __forceinline__ uint32_t digit_rev7(uint32_t x) {   // reverse the seven 2-bit digits of a 14-bit value
@@ -1083,6 +1109,14 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
     };
     LnUnit U;
     bool have = claim(U);
+    // staging of the window whose bytes start at `from` (a multiple of 16): one bulk copy, or two halves of 16 lines
+    auto issue = [&](uint64_t from) {
+        if constexpr (G::DUAL) stage_issue2(buf, arena + from, buf + G::HOFF, arena + from + 16 * G::P, G::HCOPY, bar);
+        else stage_issue(buf, arena + from, G::STAGE, bar);
+    };
+    // offset of line l of the window in the staging buffer, less woff
+    const uint32_t lane_off = G::DUAL ? (uint32_t)(lane & 15) * G::P + (uint32_t)(lane >> 4) * G::HOFF : (uint32_t)lane * G::P;
+    auto line_off = [&](uint32_t l) -> uint32_t { return G::DUAL ? (l & 15u) * G::P + (l >> 4) * G::HOFF : l * G::P; };
     // window state: B = first line start of the window (unknown while `search`), woff = B - staged base
     uint64_t B = 0, base = 0;
     uint32_t woff = 0;
@@ -1103,7 +1137,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         wleft = 0;
         if (!search) set_wleft(u);
         KF_SYNCWARP();
-        if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
+        if (lane == 0) issue(base);
     };
     auto refetch = [&](uint64_t at) {   // window whose first line starts at `at` (same unit)
         base = at & ~15ull;
@@ -1112,7 +1146,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         search = false;
         set_wleft(U);
         KF_SYNCWARP();
-        if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
+        if (lane == 0) issue(base);
     };
     if (have) start_unit(U);
     while (have) {
@@ -1141,11 +1175,11 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
                 continue;
             }
             woff = (uint32_t)(B - base);
-            if ((uint64_t)(B - base) + G::NEED > (uint64_t)G::STAGE) { refetch(B); continue; }
+            if ((uint64_t)(B - base) > (uint64_t)G::WOFF_MAX) { refetch(B); continue; }
             set_wleft(U);
         }
         // ---- pull my line (+ look-ahead) into registers, byte-aligned ----
-        const uint32_t o = woff + (uint32_t)lane * G::P;
+        const uint32_t o = woff + lane_off;
         const uint32_t *sw = reinterpret_cast<const uint32_t *>(buf) + (o >> 2);
         const uint32_t ash = (o & 3u) * 8u;
         uint32_t x[G::NWA + 1];
@@ -1166,7 +1200,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             base = B & ~15ull;
             woff = (uint32_t)B & 15u;
             KF_SYNCWARP();
-            if (lane == 0) stage_issue(buf, arena + base, G::STAGE, bar);
+            if (lane == 0) issue(base);
         } else {
         // on the grid: my slot ends with a '\n' AND lies inside the file (a short last line + arena padding + the next
         // file's header can add up to exactly one slot -- profiles/r01: one k-mer in 5e9 counted across two files)
@@ -1187,7 +1221,7 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
             // staged window.  Anything else ([sf, q) holds another kind of line) goes to the exact generic path below.
             // q = the next line start that is not a header: where the grid restarts.
             KF_T(tq0);
-            const uint8_t *lb = buf + woff + f * G::P;
+            const uint8_t *lb = buf + woff + line_off(f);
             const int lim = F1 - sf < (uint64_t)G::P ? (int)(F1 - sf) : G::P;   // bytes of the slot that belong to the file
             int nlp = G::P + 1;   // index of the line's '\n' (none within LW + 1 bytes: the line is longer than the grid's)
 #pragma unroll
@@ -1197,7 +1231,9 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
                 if (m && nlp > G::P) nlp = 32 * i + __ffs((int)m) - 1;
             }
             if (nlp > G::P && lim < G::P) nlp = lim;   // the file ends inside the slot without a final '\n'
-            const WindowSrc wsrc{arena, buf, base, (uint32_t)G::STAGE};
+            // (two halves: the one that holds line f)
+            const WindowSrc wsrc = G::DUAL ? WindowSrc{arena, buf + (f >> 4) * G::HOFF, base + (uint64_t)(f >> 4) * (16 * G::P), (uint32_t)G::HCOPY}
+                                           : WindowSrc{arena, buf, base, (uint32_t)G::STAGE};
             const bool is_hdr = lb[0] == (uint8_t)'>';   // sf is a line start: a '>' here opens a header line
             if (nlp <= G::P && is_hdr) {
                 fast_break = true;                        // a header line that ends inside the slot: nothing to count
