@@ -276,9 +276,18 @@ void build_fastq_plan(const uint64_t *offsets, const uint64_t *lens, const uint8
     for (int b = 0; b <= grid; b++) cta_begin[(size_t)b] = (int)((uint64_t)tiles.size() * (uint64_t)b / (uint64_t)grid);
 }
 
+constexpr int THREADS_FQ_PAIRS = 1024;   // k = 7 FASTQ: one CTA per SM (192 KB of histograms), 32 warps against the scattered loads
+
 template <int K>
 int launch_fastq(const uint8_t *d_arena, int grid, uint32_t file_base, cudaStream_t s) {
-    if constexpr (K <= KF_MAX_K_SMEM) {
+    if constexpr (K == 7) {
+        // 7-mers counted as 8-mer pairs (half the shared-memory atomics)
+        constexpr size_t smem = (32768 + 16384 + 2 * (THREADS_FQ_PAIRS / 32) + 4) * sizeof(uint32_t);
+        auto kern = count_fastq_pairs_kernel<THREADS_FQ_PAIRS>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid / CTAS_PER_SM, THREADS_FQ_PAIRS, smem, s>>>(d_arena, g.d_fq_tiles, g.d_fq_cta_begin, CTAS_PER_SM, g.d_file_off, g.d_file_len,
+                                                               (unsigned long long *)g.d_fwd, g.d_file_row, g.d_fq_err);
+    } else if constexpr (K <= KF_MAX_K_SMEM) {
         constexpr size_t smem = sizeof(uint32_t) << (2 * K);
         auto kern = count_fastq_smem_kernel<K, THREADS_SMEM, CTAS_PER_SM>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

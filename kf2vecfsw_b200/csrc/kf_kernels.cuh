@@ -2101,10 +2101,59 @@ __device__ __forceinline__ uint64_t fq_line_end_checked(const uint8_t *__restric
     }
 }
 
+// A sink may take a FASTQ piece's 16 positions at once (fq16(hi, lo, ok): bit j of ok = the k-mer at base j counts).
+template <class S> struct sink_takes_fq16 { static constexpr bool value = false; };
+
+// k = 7 FASTQ: 7-mers counted as 8-mers ("pairs", as the line kernel does): the 8-mer at an even base j of the piece is the
+// 7-mers j and j + 1 -- half the shared-memory atomics, which is what a FASTQ warp's time is made of.  Pair histogram:
+// 65,536 8-mer bins (first base MOST significant here) as 32,768 words of two u16 halves, word = v >> 1, low half = every
+// pair of the word, high half = the odd ones; a 7-mer whose partner is not valid (read ends, N) goes to a u32 singles
+// histogram in a rarely taken branch.  npairs / the low-half checksum catch a wrapped half (flush: exact recount).
+struct FqPairSink {
+    uint32_t *hist16, *single;
+    uint32_t hbase;          // shared-window address of hist16 (0 in the emulation)
+    uint32_t npairs;         // pairs issued by this thread since the last flush
+    __device__ __forceinline__ void fq16(uint32_t hi, uint32_t lo, uint32_t ok) {
+        const uint32_t pm = ok & (ok >> 1) & 0x5555u;          // even j: 7-mers j and j + 1 both count
+        npairs += (uint32_t)__popc(pm);
+        if (pm) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const uint32_t off8 = kmer_off_at<8>(hi, lo, j);   // 4 * v
+                red_shared_add_if(hist16, hbase, (off8 >> 1) & 0x1FFFCu, ((off8 & 4u) << 14) | 1u, pm, 1u << j);
+            }
+        }
+        uint32_t sm = ok & ~(pm | (pm << 1));                  // counted 7-mers outside a pair
+        while (sm) {
+            const int j = __ffs((int)sm) - 1;
+            sm &= sm - 1;
+            const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+            atomicAdd(single + ((uint32_t)(w >> (50 - 2 * j)) & 0x3FFFu), 1u);
+        }
+    }
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+template <> struct sink_takes_fq16<FqPairSink> { static constexpr bool value = true; };
+struct FqRecountSink {   // exact recount after a wrapped half: the two 7-mers of every pair, one global atomic each
+    unsigned long long *g;   // the file's u64 row
+    __device__ __forceinline__ void fq16(uint32_t hi, uint32_t lo, uint32_t ok) const {
+        uint32_t pm = ok & (ok >> 1) & 0x5555u;
+        pm |= pm << 1;
+        const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+        while (pm) {
+            const int j = __ffs((int)pm) - 1;
+            pm &= pm - 1;
+            atomicAdd(g + ((uint32_t)(w >> (50 - 2 * j)) & 0x3FFFu), 1ull);
+        }
+    }
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+template <> struct sink_takes_fq16<FqRecountSink> { static constexpr bool value = true; };
+
 // k-mers that start in one 16-byte piece: hi = its bases, lo = the next piece's, bad32 = bad bits of both (piece in the
 // low half); the k-mer at byte j counts iff bad[j .. j+K) is clear.
 template <int K, class Sink>
-__device__ __forceinline__ void fq_emit16(uint32_t hi, uint32_t lo, uint32_t bad32, Sink sink) {
+__device__ __forceinline__ void fq_emit16(uint32_t hi, uint32_t lo, uint32_t bad32, Sink &sink) {
     uint32_t o = bad32;
     int cover = 1;
 #pragma unroll
@@ -2116,7 +2165,9 @@ __device__ __forceinline__ void fq_emit16(uint32_t hi, uint32_t lo, uint32_t bad
         }
     }
     const uint32_t ok = ~o & 0xFFFFu;
-    if (ok) {
+    if constexpr (sink_takes_fq16<Sink>::value) {
+        sink.fq16(hi, lo, ok);
+    } else if (ok) {
 #pragma unroll
         for (int j = 0; j < 16; j++) {
             if constexpr (sink_has_add_if<Sink>::value) sink.add_if(kmer_off_at<K>(hi, lo, j), ok, 1u << j);
@@ -2130,7 +2181,7 @@ __device__ __forceinline__ void fq_emit16(uint32_t hi, uint32_t lo, uint32_t bad
 // previous piece is counted when the next one -- its look-ahead -- has been decoded), plus lines together, jump.
 template <int K, class Sink>
 __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ arena, uint64_t F0, uint64_t F1, uint64_t X0,
-                                                   uint64_t X1, Sink sink, unsigned long long *fq_err) {
+                                                   uint64_t X1, Sink &sink, unsigned long long *fq_err) {
     if (X0 >= F1) X0 = X1 = F1;
     if (X1 > F1) X1 = F1;
     // ---- put the range start on a record boundary ----
@@ -2263,6 +2314,104 @@ count_fastq_smem_kernel(const uint8_t *__restrict__ arena, const Tile *__restric
             if (v) { atomicAdd(g + i, (unsigned long long)v); hist[i] = 0; }
         }
         __syncthreads();
+        t = te;
+    }
+}
+
+// FASTQ counting, k = 7: the pair histogram (FqPairSink).  One CTA per SM (192 KB of histograms); CTA b owns the tile ranges
+// [cta_begin[b * stride], cta_begin[(b + 1) * stride]) of the plan, its warps take tiles from a shared counter; flush when
+// the CTA moves to another file: checksum, 7-mer counts out of the pair + singles histograms, u64 atomics into the file's
+// row (several CTAs may hold tiles of one file).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+count_fastq_pairs_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin, int stride,
+                         const uint64_t *__restrict__ file_off, const uint64_t *__restrict__ file_len,
+                         unsigned long long *__restrict__ g_fwd, const uint32_t *__restrict__ file_row,
+                         unsigned long long *__restrict__ fq_err) {
+    constexpr int K = 7, NB = 16384, NWORDS = 32768, NWARPS = THREADS / 32;
+    KF_DYN_SMEM(uint32_t, smem);
+    uint32_t *hist16 = smem, *single = smem + NWORDS;
+    uint32_t *s_part = single + NB;         // [2 * NWARPS] pairs issued | low-half sums
+    uint32_t *s_next = s_part + 2 * NWARPS;
+    for (int i = threadIdx.x; i < NWORDS + NB; i += THREADS) smem[i] = 0;
+    if (threadIdx.x == 0) *s_next = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FqPairSink sink;
+    sink.hist16 = hist16;
+    sink.single = single;
+    sink.hbase = smem_addr(hist16);
+    sink.npairs = 0;
+    const int t1 = cta_begin[(blockIdx.x + 1) * stride];
+    for (int t = cta_begin[blockIdx.x * stride]; t < t1;) {
+        const uint32_t file = tiles[t].file;
+        int te = t + 1;
+        while (te < t1 && tiles[te].file == file) ++te;
+        const uint64_t F0 = file_off[file], F1 = F0 + file_len[file];
+        for (;;) {
+            int tt = 0;
+            if (lane == 0) tt = t + (int)atomicAdd(s_next, 1u);
+            tt = __shfl_sync(FULL, tt, 0);
+            if (tt >= te) break;
+            const Tile T = tiles[tt];
+            const uint64_t tb = (uint64_t)T.first_chunk * CHUNK, tend = tb + (uint64_t)T.n_chunks * CHUNK;
+            const uint64_t x0 = tb + (uint64_t)lane * FQ_LANE_BYTES;
+            const uint64_t x1 = x0 + FQ_LANE_BYTES < tend ? x0 + FQ_LANE_BYTES : tend;
+            if (x0 < tend) fastq_lane_records<K>(arena, F0, F1, x0, x1, sink, fq_err + file);
+        }
+        // ---- flush ----
+        uint32_t np = sink.npairs;
+        sink.npairs = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync(FULL, np, o);
+        if (lane == 0) s_part[warp] = np;
+        __syncthreads();
+        if (threadIdx.x == 0) *s_next = 0;
+        uint32_t low = 0;
+        for (int i = threadIdx.x; i < NWORDS; i += THREADS) low += hist16[i] & 0xFFFFu;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) low += __shfl_xor_sync(FULL, low, o);
+        if (lane == 0) s_part[NWARPS + warp] = low;
+        __syncthreads();
+        unsigned long long tp = 0, tl = 0;
+        for (int w = 0; w < NWARPS; w++) { tp += s_part[w]; tl += s_part[NWARPS + w]; }
+        const bool ok = tp == tl;
+        unsigned long long *g = g_fwd + (size_t)file_row[file] * NB;
+        // 7-mer x (first base most significant): first of the 8-mers 4x + b (words 2x, 2x + 1: every pair of both), second
+        // of the 8-mers a * 16384 + x (word a * 8192 + (x >> 1): the odd half for odd x, low - high for even x)
+        for (int j = threadIdx.x; j < NB / 2; j += THREADS) {
+            uint32_t c0 = single[2 * j], c1 = single[2 * j + 1];
+            if (ok) {
+                const uint4 pw = *reinterpret_cast<const uint4 *>(hist16 + 4 * j);
+                c0 += (pw.x & 0xFFFFu) + (pw.y & 0xFFFFu);
+                c1 += (pw.z & 0xFFFFu) + (pw.w & 0xFFFFu);
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const uint32_t w = hist16[a * 8192 + j];
+                    c0 += (w & 0xFFFFu) - (w >> 16);
+                    c1 += w >> 16;
+                }
+            }
+            if (c0) atomicAdd(g + 2 * j, (unsigned long long)c0);
+            if (c1) atomicAdd(g + 2 * j + 1, (unsigned long long)c1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < NWORDS + NB; i += THREADS) smem[i] = 0;
+        __syncthreads();
+        if (!ok) {
+            // a 16-bit half wrapped: this CTA's tiles of the file again, the pairs' 7-mers straight into the row.  (The
+            // singles were added above; FqRecountSink counts only what the pair histogram held.)
+            FqRecountSink rs;
+            rs.g = g;
+            for (int tt = t + warp; tt < te; tt += NWARPS) {
+                const Tile T = tiles[tt];
+                const uint64_t tb = (uint64_t)T.first_chunk * CHUNK, tend = tb + (uint64_t)T.n_chunks * CHUNK;
+                const uint64_t x0 = tb + (uint64_t)lane * FQ_LANE_BYTES;
+                const uint64_t x1 = x0 + FQ_LANE_BYTES < tend ? x0 + FQ_LANE_BYTES : tend;
+                if (x0 < tend) fastq_lane_records<K>(arena, F0, F1, x0, x1, rs, fq_err + file);
+            }
+            __syncthreads();
+        }
         t = te;
     }
 }

@@ -252,7 +252,12 @@ int main(int argc, char **argv) {
             size_t smem = sizeof(uint32_t) << (2 * k);
 #define RUNQ(KK) case KK: if (threads == 64) emu::launch(grid, 64, smem, [&]() { count_fastq_smem_kernel<KK, 64, 1>(arena.data(), fq.data(), cb.data(), off.data(), len.data(), fwd.data(), file_row.data(), err.data()); }); \
                           else emu::launch(grid, 32, smem, [&]() { count_fastq_smem_kernel<KK, 32, 1>(arena.data(), fq.data(), cb.data(), off.data(), len.data(), fwd.data(), file_row.data(), err.data()); }); break;
-            switch (k) { RUNQ(3) RUNQ(4) RUNQ(5) RUNQ(7) default: return 2; }
+            const size_t psmem = (32768 + 16384 + 2 * 2 + 4) * sizeof(uint32_t);
+            if (k == 7) {   // 8-mer pair histogram, as kf_api.cu launches it for k = 7 (stride 1 here: every emulated CTA is one)
+                if (threads == 64) emu::launch(grid, 64, psmem, [&]() { count_fastq_pairs_kernel<64>(arena.data(), fq.data(), cb.data(), 1, off.data(), len.data(), fwd.data(), file_row.data(), err.data()); });
+                else emu::launch(grid, 32, psmem, [&]() { count_fastq_pairs_kernel<32>(arena.data(), fq.data(), cb.data(), 1, off.data(), len.data(), fwd.data(), file_row.data(), err.data()); });
+            } else
+            switch (k) { RUNQ(3) RUNQ(4) RUNQ(5) default: return 2; }
             // files out of 4-line layout: the exact front-to-back walk, one warp per file (as kf_api.cu launches it)
             emu::launch((unsigned)((n * 32 + 127) / 128), 128, 0, [&]() { fastq_multiline_kernel<unsigned long long>(arena.data(), off.data(), len.data(), formats.data(), 0u, (uint32_t)n, k, fwd.data(), file_row.data(), err.data()); });
             for (int f = 0; f < n; f++)

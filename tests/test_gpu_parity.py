@@ -661,3 +661,13 @@ def test_peer_gather_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_fastq_pair_histogram_overflow_recount(eng):
+    """k = 7 FASTQ counts 8-mer pairs in u16 halves; a CTA that issues more than 65,535 identical pairs for one file must
+    notice (low-half checksum) and recount its tiles exactly."""
+    rec = b"@r\n" + b"A" * 150 + b"\n+\n" + b"I" * 150 + b"\n"
+    odd = b"@s\n" + b"A" * 70 + b"N" + b"ACGTACGTTTGCA" + b"\n+\n" + b"I" * 84 + b"\n@t\nACGTAC\n+\nIIIIII\n"
+    data = rec * 40000 + odd + rec * 9000           # ~15 MB: several CTAs, each far beyond 65,535 identical pairs
+    rng = random.Random(77)
+    check_against_oracle(eng, [data, rand_fastq(rng), data[: len(rec) * 700]], 7)

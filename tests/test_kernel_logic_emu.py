@@ -307,3 +307,18 @@ def test_emulated_multiline_fastq(tmp_path):
         for f, (tot, counts, _) in zip(files, res):
             ref = o.canonical_counts_bytes(open(f, "rb").read(), k)
             assert np.array_equal(counts, ref), (s, k, f)
+
+
+def test_emulated_fastq_pair_histogram_overflow_recount(tmp_path):
+    """k = 7 FASTQ counts 8-mer pairs in u16 halves: more than 65,535 identical pairs between two flushes wrap a half, the
+    low-half checksum must catch it and the CTA recount its tiles exactly (reads of poly-A with an N and a short read)."""
+    rec = b"@r\n" + b"A" * 150 + b"\n+\n" + b"I" * 150 + b"\n"
+    odd = b"@s\n" + b"A" * 70 + b"N" + b"ACGTACGTTTGCA" + b"\n+\n" + b"I" * 84 + b"\n@t\nACGTAC\n+\nIIIIII\n"
+    data = rec * 1200 + odd + rec * 300
+    p = str(tmp_path / "polyA.fq")
+    open(p, "wb").write(data)
+    ref = o.canonical_counts_bytes(data, 7)
+    assert int(ref.max()) > 2 * 65535
+    for grid, thr, tile in ((1, 64, 64), (2, 32, 64)):
+        tot, counts, _ = run_emu(7, thr, grid, False, tile, [p])[0]
+        assert np.array_equal(counts, ref), (grid, thr, tile)

@@ -34,13 +34,13 @@ if len(sys.argv) >= 6 and sys.argv[2] == "--traffic-json":
     best = None
     for r in rows[2:]:
         d = dict(zip(hdr, r))
-        if "count_fasta_lines_kernel<80" in d["Kernel Name"]:
+        if "count_fasta_lines_kernel<" in d["Kernel Name"]:
             units = dict(zip(hdr, rows[1]))
             def to_bytes(key):
                 v, u = float(d[key]), units[key]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
             best = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
     out = {"genomes": G, "bases": NB, "k": K, "dram_bytes_per_launch": best,
-           "source": "ncu --set full --clock-control none, count_fasta_lines_kernel<80,512>, dram__bytes_read.sum + dram__bytes_write.sum (%s)" % os.path.basename(rep)}
+           "source": "ncu --set full --clock-control none, count_fasta_lines_kernel, dram__bytes_read.sum + dram__bytes_write.sum (%s)" % os.path.basename(rep)}
     json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json"), "w"), indent=1)
     print(out)
