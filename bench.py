@@ -502,6 +502,13 @@ def main():
                "ms_per_step": float(dt.item()) / args.steps * 1e3, "parity_ok": e2e_ok,
                "api": "kf_count_buffers (C ABI, pinned host buffers in, counts+frequencies out)",
                "host_numa_node_rank0": numa_node}
+        hp = os.path.join(ROOT, "profiles", "h2d_ceiling.json")
+        if os.path.exists(hp):
+            hc = json.load(open(hp)).get(str(world))
+            if hc:   # what the box's host-to-device copies alone reach with this many ranks copying at once
+                e2e["bound_gbs"] = hc["h2d_concurrent_total_gbs"]
+                e2e["bound"] = "concurrent pinned host-to-device copies, no kernels: " + hc["source"]
+                e2e["h2d_gbs_achieved"] = e2e["h2d_bytes_per_step"] * world / (e2e["ms_per_step"] * 1e-3) / 1e9
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -12,7 +12,7 @@ python tools/exp_sparse.py 296 12 11 > gpurun_out/sparse.jsonl 2> gpurun_out/spa
 python tools/exp_files.py 1000 > gpurun_out/files.jsonl 2> gpurun_out/files.err; echo "files rc=$?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-configs > gpurun_out/ncu.log 2>&1; echo "ncu1 rc=$?"
-ncu --set full --import-source on --clock-control none -k regex:count_fasta_lines_kernel -s 3 -c 1 -f -o gpurun_out/prof_ln_bench \
+ncu --set full --import-source on --clock-control none -k regex:count_fasta_lines_kernel -s 1 -c 1 -f -o gpurun_out/prof_ln_bench \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-configs > gpurun_out/ncu2.log 2>&1; echo "ncu2 rc=$?"
 ncu --set full --import-source on --clock-control none -k regex:count_fasta_lines_kernel -s 2 -c 1 -f -o gpurun_out/prof_vl \
     python tools/exp_widths.py 1000 0 > gpurun_out/ncu3.log 2>&1; echo "ncu3 rc=$?"
