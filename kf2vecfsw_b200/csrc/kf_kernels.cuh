@@ -926,7 +926,8 @@ __device__ __forceinline__ uint32_t digit_rev7(uint32_t x) {   // reverse the se
 // PK receives the 2-bit codes LSB-first (base j of the line at bits 2(j%16) of PK[j/16]; the '\n' is skipped).
 // GAP = bytes between the line's last base and the look-ahead bases: 1 (the '\n' of wrapped FASTA) or 0 (virtual lines cut
 // out of one long line, see vl_process_piece).
-template <int LW, int GAP = 1>
+// PACK = false: the validity test only (PK untouched) -- the line kernel packs while it counts (ln_pack_count_pairs).
+template <int LW, int GAP = 1, bool PACK = true>
 __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::NWA + 1], uint32_t (&PK)[LineGeom<LW>::NPK + 1]) {
     using G = LineGeom<LW>;
     static_assert(GAP == 0 || GAP == 1, "gap");
@@ -936,7 +937,7 @@ __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::
 #pragma unroll
     for (int i = 0; i < G::NWA; i++) {
         const uint32_t w = x[i];
-        pk[i] = (w & 0x06060606u) * MPACK;
+        pk[i] = PACK ? (w & 0x06060606u) * MPACK : 0u;
         // at bit 4 of every byte: bit4 == (bit2 & ~bit1)  [T is the only base with bit 4]  and  bit0 != bit4
         const uint32_t b = w * 4u, c = w * 8u, d = w * 16u;
         const uint32_t X = w ^ (b & ~c);
@@ -951,6 +952,7 @@ __device__ __forceinline__ uint32_t ln_decode(const uint32_t (&x)[LineGeom<LW>::
         if (m == 0xFFFFFFFFu) { acc4 |= Y; accC |= Z; }
         else if (m != 0) { acc4 |= Y & m; accC |= Z & m; }
     }
+    if (!PACK) return (acc4 & 0x10101010u) | (accC & 0xC8C8C8C8u);
     constexpr int NFULL = (LW / 4) / 4;   // groups of four full words -> one register, three byte permutes
 #pragma unroll
     for (int gq = 0; gq < NFULL; gq++) {
@@ -1005,6 +1007,58 @@ __device__ __forceinline__ void ln_count_pairs(const uint32_t (&PK)[LineGeom<LW>
 #pragma unroll
     for (int i = 0; i < G::NPAIR; i++) {
         const uint32_t par = i >= 4 ? sv[i - 4] : (PK[0] << (17 - 4 * i));   // bit 17 = stream bit 4i = v's lowest bit
+        red_shared_add_imm<BASE>(hist16, hbase, sv[i] & 0x1FFFCu, (par & 0x20000u) | one);
+    }
+}
+
+// The same, packing as it goes: register PK[g] (16 bases) is packed right before the pairs that need it, so the line's
+// ~100 packing instructions sit BETWEEN its 40 REDs instead of in front of them.  (With everything packed first the
+// REDs come every fourth instruction and the warps pile up behind the shared-memory queue: mio_throttle 3.6 % -> 14 %,
+// +1.5 % time although the instruction count fell by a fifth.)  Only for a line already found clean.
+template <int LW, int GAP, uint32_t BASE>
+__device__ __forceinline__ void ln_pack_count_pairs(const uint32_t (&x)[LineGeom<LW>::NWA + 1], uint32_t *hist16, uint32_t hbase, uint32_t one) {
+    using G = LineGeom<LW>;
+    constexpr uint32_t MPACK = (1u << 23) + (1u << 17) + (1u << 11) + (1u << 5);
+    constexpr int NFULL = (LW / 4) / 4;
+    uint32_t PK[G::NPK + 1];
+    // the registers past the full groups (line tail + look-ahead) first: they are few and their layout is irregular
+#pragma unroll
+    for (int i = NFULL; i <= G::NPK; i++) PK[i] = 0;
+#pragma unroll
+    for (int i = 4 * NFULL; i < G::NWA; i++) {
+        const uint32_t g8 = ((x[i] & 0x06060606u) * MPACK) >> 24;
+#pragma unroll
+        for (int seg = 0; seg < 2; seg++) {
+            int b0 = (seg == 0) ? 0 : LW + GAP - 4 * i;
+            int b1 = (seg == 0) ? LW - 4 * i : LW + GAP + G::LA - 4 * i;
+            b0 = b0 < 0 ? 0 : b0;
+            b1 = b1 > 4 ? 4 : b1;
+            if (b1 > b0) {
+                const int n = b1 - b0;
+                const int byte = 4 * i + b0;
+                const int pos = byte < LW ? byte : byte - GAP;
+                const uint32_t val = (g8 >> (2 * b0)) & ((1u << (2 * n)) - 1u);
+                const int sh = 2 * (pos & 15);
+                PK[pos >> 4] |= val << sh;
+                if (sh + 2 * n > 32) PK[(pos >> 4) + 1] |= val >> (32 - sh);
+            }
+        }
+    }
+    auto pack_group = [&](int gq) {
+        const uint32_t p0 = (x[4 * gq] & 0x06060606u) * MPACK, p1 = (x[4 * gq + 1] & 0x06060606u) * MPACK;
+        const uint32_t p2 = (x[4 * gq + 2] & 0x06060606u) * MPACK, p3 = (x[4 * gq + 3] & 0x06060606u) * MPACK;
+        PK[gq] = __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
+    };
+    uint32_t sv[G::NPAIR];
+    if (NFULL > 0) pack_group(0);
+    int packed = NFULL > 0 ? 1 : 0;   // full groups packed so far (compile-time after unrolling)
+#pragma unroll
+    for (int i = 0; i < G::NPAIR; i++) {
+        // pair i reads stream bits [4i - 1, 4i + 17): registers (4i - 1) >> 5 and, when it crosses, the next one
+        const int need = (4 * i + 16) >> 5;      // highest register index it may touch
+        if (need >= packed && packed < NFULL) { pack_group(packed); packed++; }
+        sv[i] = i == 0 ? (PK[0] << 1) : ln_stream32<LW>(PK, 4 * i - 1);
+        const uint32_t par = i >= 4 ? sv[i - 4] : (PK[0] << (17 - 4 * i));
         red_shared_add_imm<BASE>(hist16, hbase, sv[i] & 0x1FFFCu, (par & 0x20000u) | one);
     }
 }
@@ -1274,9 +1328,9 @@ __device__ __forceinline__ void ln_process_piece(const uint8_t *__restrict__ are
         bool dirty = false;
         if ((uint32_t)lane < f) {
             uint32_t PK[G::NPK + 1];
-            const uint32_t anyV = ln_decode<LW>(x, PK);
+            const uint32_t anyV = ln_decode<LW, 1, false>(x, PK);
             if (anyV == 0) {
-                ln_count_pairs<LW, BASE>(PK, hist16, hbase, one);
+                ln_pack_count_pairs<LW, 1, BASE>(x, hist16, hbase, one);
                 npairs += G::NPAIR;
             } else {
                 dirty = true;
@@ -1602,7 +1656,7 @@ __device__ __forceinline__ void vl_process_piece(const uint8_t *__restrict__ are
             }
             uint32_t PK[G::NPK + 1];
             const bool active = (uint32_t)lane < nact;
-            const uint32_t anyV = ln_decode<LW, 0>(x, PK);
+            const uint32_t anyV = ln_decode<LW, 0, false>(x, PK);
             const bool dirty = active && anyV != 0;
             const unsigned D = __ballot_sync(FULL, dirty);
             uint32_t f = nact;   // lanes [0, f) are virtual lines of one sequence line
@@ -1624,7 +1678,7 @@ __device__ __forceinline__ void vl_process_piece(const uint8_t *__restrict__ are
                 if (Bk) f = (uint32_t)(__ffs((int)Bk) - 1);
             }
             if ((uint32_t)lane < f && active && !dirty) {
-                ln_count_pairs<LW, BASE>(PK, hist16, hbase, one);
+                ln_pack_count_pairs<LW, 0, BASE>(x, hist16, hbase, one);
                 npairs += G::NPAIR;
             }
             // dirty lanes before the break: N runs, IUPAC codes ... -- all lanes count such a line together
