@@ -42,6 +42,7 @@ struct Ctx {
     int sm_all = 0;   // the device's SM count; sm_count = SMs the counting kernels are sized for (kf_set_sm_limit)
     uint32_t smem_base = 0;   // shared-window address of dynamic shared memory (kf_smem_base_probe_kernel)
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::vector<cudaEvent_t> ev_sub;   // kf_count_buffers: per sub-batch, region zeroed / copies landed
     cudaEvent_t ev_copy = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;   // ev_k0/ev_k1: the current call's pair of the ring below
     bool ev_valid = false;
     // the counting kernels of the last EV_RING calls, timed on the launching stream (read back after the fact, so a
@@ -739,6 +740,7 @@ int kf_shutdown(void) {
         if (g.h_stage[i]) cudaFreeHost(g.h_stage[i]);
         if (g.ev_stage[i]) cudaEventDestroy(g.ev_stage[i]);
     }
+    for (cudaEvent_t ev : g.ev_sub) cudaEventDestroy(ev);
     cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaEventDestroy(g.ev_copy); cudaEventDestroy(g.ev_done);
     for (int i = 0; i < Ctx::EV_RING; i++) { cudaEventDestroy(g.ring0[i]); cudaEventDestroy(g.ring1[i]); }
     cudaGetLastError();
@@ -819,23 +821,71 @@ int kf_count_buffers(const uint8_t *const *bufs, const size_t *lens_in, int n, i
     if ((rc = ensure(g.d_counts, g.counts_cap, (size_t)n * V * sizeof(unsigned long long))) != KF_OK) return rc;
     if ((rc = ensure(g.d_freq, g.freq_cap, (size_t)n * V * sizeof(double))) != KF_OK) return rc;
     if ((rc = ensure(g.d_totals, g.totals_cap, (size_t)n * sizeof(unsigned long long))) != KF_OK) return rc;
-    // stage: zero the arena (gaps must be NUL), then one copy per file
-    CK(cudaMemsetAsync(g.d_arena, 0, arena_bytes, g.copy_stream));
-    for (int i = 0; i < n; i++)
-        if (lens[(size_t)i]) CK(cudaMemcpyAsync(g.d_arena + offsets[(size_t)i], bufs[i], lens[(size_t)i], cudaMemcpyHostToDevice, g.copy_stream));
-    CK(cudaEventRecord(g.ev_copy, g.copy_stream));
-    CK(cudaStreamWaitEvent(g.stream, g.ev_copy, 0));
-    rc = count_device_locked(g.d_arena, arena_bytes, offsets.data(), lens.data(), formats.data(), n, k, flags, g.d_counts,
-                             g.d_freq, nullptr, g.d_totals, g.stream);
-    if (rc != KF_OK) return rc;
-    if (counts_out) CK(cudaMemcpyAsync(counts_out, g.d_counts, (size_t)n * V * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
-    if (freq_out) CK(cudaMemcpyAsync(freq_out, g.d_freq, (size_t)n * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
-    if (totals_out) CK(cudaMemcpyAsync(totals_out, g.d_totals, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+    // Pipelined over sub-batches of files (about KF_SUB_BATCH_BYTES of text each): the host-to-device copies of
+    // sub-batch j + 1 run on the copy stream while sub-batch j is counted and its rows go back -- the call takes the
+    // time of its input copies plus the LAST sub-batch's kernels and device-to-host copy, not the sum of the three.
+    // A sub-batch's region of the arena is zeroed first (gaps must be NUL) on the counting stream, ahead of the copies.
+    static const bool trace = getenv("KF_TRACE_BUFFERS") != nullptr;   // developer: where a call's time goes (stderr)
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto tr_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(); };
+    double tr_copies = 0, tr_counts = 0;
+    uint64_t sub_bytes = (uint64_t)512 << 20;
+    if (const char *e = getenv("KF_SUB_BATCH_BYTES")) { const long long v = atoll(e); if (v > 0) sub_bytes = (uint64_t)v; }
+    std::vector<int> sb(1, 0);
+    {
+        uint64_t acc = 0;
+        for (int i = 0; i < n; i++) {
+            acc += (lens[(size_t)i] + CHUNK - 1) / CHUNK * CHUNK;
+            if (acc >= sub_bytes && i + 1 < n) { sb.push_back(i + 1); acc = 0; }
+        }
+        sb.push_back(n);
+    }
+    const int nsb = (int)sb.size() - 1;
+    while ((int)g.ev_sub.size() < 2 * nsb) {
+        cudaEvent_t ev;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        g.ev_sub.push_back(ev);
+    }
+    if (g.last_stream_valid && g.last_stream != g.stream) CK(cudaStreamWaitEvent(g.stream, g.ev_done, 0));   // (an earlier call on a caller's stream may still read the arena)
+    for (int j = 0; j < nsb; j++) {
+        const uint64_t r0 = offsets[(size_t)sb[(size_t)j]];
+        const uint64_t r1 = j + 1 < nsb ? offsets[(size_t)sb[(size_t)j + 1]] : arena_bytes;
+        CK(cudaMemsetAsync(g.d_arena + r0, 0, r1 - r0, g.stream));
+        CK(cudaEventRecord(g.ev_sub[(size_t)(2 * j)], g.stream));
+    }
+    for (int j = 0; j < nsb; j++) {
+        CK(cudaStreamWaitEvent(g.copy_stream, g.ev_sub[(size_t)(2 * j)], 0));
+        for (int i = sb[(size_t)j]; i < sb[(size_t)j + 1]; i++)
+            if (lens[(size_t)i]) CK(cudaMemcpyAsync(g.d_arena + offsets[(size_t)i], bufs[i], lens[(size_t)i], cudaMemcpyHostToDevice, g.copy_stream));
+        CK(cudaEventRecord(g.ev_sub[(size_t)(2 * j + 1)], g.copy_stream));
+    }
+    tr_copies = tr_ms();
+    bool any_fq = false;
+    int launches = 0;
+    g.h_fq_err.assign((size_t)n, ~0ull);
+    for (int j = 0; j < nsb; j++) {
+        const int i0 = sb[(size_t)j], ns = sb[(size_t)j + 1] - i0;
+        CK(cudaStreamWaitEvent(g.stream, g.ev_sub[(size_t)(2 * j + 1)], 0));
+        rc = count_device_locked(g.d_arena, arena_bytes, offsets.data() + i0, lens.data() + i0, formats.data() + i0, ns, k, flags,
+                                 g.d_counts + (size_t)i0 * V, g.d_freq + (size_t)i0 * V, nullptr, g.d_totals + i0, g.stream);
+        if (rc != KF_OK) { cudaStreamSynchronize(g.copy_stream); cudaStreamSynchronize(g.stream); return rc; }
+        launches += g.last_launches;
+        if (counts_out) CK(cudaMemcpyAsync(counts_out + (size_t)i0 * V, g.d_counts + (size_t)i0 * V, (size_t)ns * V * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+        if (freq_out) CK(cudaMemcpyAsync(freq_out + (size_t)i0 * V, g.d_freq + (size_t)i0 * V, (size_t)ns * V * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+        if (totals_out) CK(cudaMemcpyAsync(totals_out + i0, g.d_totals + i0, (size_t)ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, g.stream));
+        if (g.fq_err_n > 0) {   // (the next sub-batch reuses d_fq_err: fetch this one's layout reports now, in stream order)
+            CK(cudaMemcpyAsync(g.h_fq_err.data() + i0, g.d_fq_err, (size_t)ns * sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream));
+            any_fq = true;
+        }
+    }
+    tr_counts = tr_ms();
+    if (trace) { cudaStreamSynchronize(g.copy_stream); fprintf(stderr, "kf_count_buffers: copies queued %.2f ms, counts queued %.2f ms, copies landed %.2f ms", tr_copies, tr_counts, tr_ms()); }
     CK(cudaStreamSynchronize(g.stream));
+    if (trace) fprintf(stderr, ", done %.2f ms (%d sub-batches)\n", tr_ms(), nsb);
+    g.last_launches = launches;
+    g.fq_err_n = 0;   // (d_fq_err holds the last sub-batch only: nothing for kf_last_file_status to read)
     // 4-line FASTQ layout check: a violation inside the file is an error unless only line ends follow it
-    if (g.fq_err_n > 0) {
-        g.h_fq_err.resize((size_t)n);
-        CK(cudaMemcpy(g.h_fq_err.data(), g.d_fq_err, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (any_fq) {
         for (int i = 0; i < n; i++) {
             if (formats[(size_t)i] != '@' || status_out[i] != KF_OK) continue;
             const unsigned long long e = g.h_fq_err[(size_t)i];

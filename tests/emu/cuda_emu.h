@@ -118,6 +118,12 @@ inline T __shfl_up_sync(unsigned, T v, int d) {
     T r = (T)emu::exchange((uint64_t)v, l - d < 0 ? l : l - d);
     return r;
 }
+template <typename T>
+inline T __shfl_down_sync(unsigned, T v, int d) {
+    int l = (int)(threadIdx.x & 31);
+    T r = (T)emu::exchange((uint64_t)v, l + d > 31 ? l : l + d);
+    return r;
+}
 inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

@@ -671,3 +671,29 @@ def test_fastq_pair_histogram_overflow_recount(eng):
     data = rec * 40000 + odd + rec * 9000           # ~15 MB: several CTAs, each far beyond 65,535 identical pairs
     rng = random.Random(77)
     check_against_oracle(eng, [data, rand_fastq(rng), data[: len(rec) * 700]], 7)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [7, 9])
+def test_count_buffers_sub_batch_pipeline(eng, toy_inputs, monkeypatch, k):
+    """kf_count_buffers pipelines sub-batches of files (input copies of j + 1 beside the counting and the result copies
+    of j).  A tiny sub-batch size makes every file or two its own sub-batch: results, totals and the per-file status
+    (FASTQ layout reports are fetched per sub-batch) must not depend on the cut."""
+    rng = random.Random(4242)
+    ml = b"@r\nACGTACGTAC\nACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIII\n@s\nACGTACGTAC\n+\nIIIIIIIIII\n"   # multi-line: exact slow path
+    bufs = [toy_inputs["G000830275sub"], rand_fastq(rng), b"", rand_fasta(rng), ml, b"hello\n", rand_fasta_grid(rng), rand_fastq(rng),
+            toy_inputs["G000402355sub"], b"@r\nACGT\n+\nIII\n@s\nACGTACGTACGT\n+\nIIIIIIIIIIII\n" + b"x" * 600, rand_fasta(rng), rand_fastq(rng)]
+    one = eng.count_buffers(bufs, k=k)
+    monkeypatch.setenv("KF_SUB_BATCH_BYTES", "3000")
+    cut = eng.count_buffers(bufs, k=k)
+    monkeypatch.delenv("KF_SUB_BATCH_BYTES")
+    assert np.array_equal(one[3], cut[3]), (one[3], cut[3])
+    assert one[3][2] != 0 and one[3][5] != 0 and one[3][4] == 0   # empty, not a sequence file; multi-line FASTQ is counted (exact slow path)
+    for i, b in enumerate(bufs):
+        if one[3][i] != 0:
+            continue
+        ref = o.canonical_counts_bytes(bytes(b), k)
+        assert np.array_equal(cut[0][i], ref), i
+        assert np.array_equal(one[0][i], ref), i
+        assert int(cut[2][i]) == int(ref.sum())
+        assert np.array_equal(cut[1][i], one[1][i], equal_nan=True)
