@@ -127,7 +127,8 @@ template <int MODE, typename KT> struct sink_walks_itself<SparseSink<MODE, KT>> 
 template <int MODE, typename KT, bool WALK_ALL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
 sparse_tile_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin, int k,
-                   uint32_t file_base, uint32_t *__restrict__ tile_hist, KT *__restrict__ keys, const uint64_t *__restrict__ kbase) {
+                   uint32_t file_base, uint32_t *__restrict__ tile_hist, KT *__restrict__ keys, const uint64_t *__restrict__ kbase,
+                   int bucket_shift /* bucket = code >> bucket_shift; < 0: the leading SP_BUCKET_BITS bits */) {
     __shared__ uint32_t hist[SP_BUCKETS];
     constexpr int NWARPS = THREADS / 32;
     const int warp = threadIdx.x >> 5;
@@ -135,7 +136,7 @@ sparse_tile_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ t
     sink.k = k;
     sink.e.hist = hist;
     sink.e.cursor = hist;
-    sink.e.shift = (uint32_t)(2 * k - SP_BUCKET_BITS);
+    sink.e.shift = bucket_shift >= 0 ? (uint32_t)bucket_shift : (uint32_t)(2 * k - SP_BUCKET_BITS);
     sink.e.keys = nullptr;
     const int t1 = cta_begin[blockIdx.x + 1];
     for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
@@ -161,18 +162,29 @@ sparse_tile_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ t
 // the file's key region); boff [nf][SP_BUCKETS + 1] = exclusive scan of the file's bucket totals (last = all keys).
 __global__ void __launch_bounds__(1024)
 sparse_tile_scan_kernel(uint32_t *__restrict__ tile_hist, const int *__restrict__ file_t0, uint32_t *__restrict__ boff,
-                        unsigned long long *__restrict__ totals, uint32_t file_base) {
+                        unsigned long long *__restrict__ totals, uint32_t file_base,
+                        uint32_t pad /* 0, or 7: every run starts at a multiple of 8 keys */, uint32_t *__restrict__ tile_place /* null: in place */) {
     static_assert(SP_BUCKETS == 4096, "four buckets per thread");
     __shared__ uint32_t wsum[32];
+    __shared__ unsigned long long s_true;
+    if (threadIdx.x == 0) s_true = 0ull;
+    if (tile_place == nullptr) tile_place = tile_hist;
     const uint32_t f = blockIdx.x;
     const int ta = file_t0[f], tb = file_t0[f + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4 run = make_uint4(0u, 0u, 0u, 0u);
+    unsigned long long tsum = 0;   // the true number of keys (pad or not)
     for (int t = ta; t < tb; t++) {   // per bucket: counts -> running offsets over the file's tiles
-        uint4 *p = reinterpret_cast<uint4 *>(tile_hist + (size_t)t * SP_BUCKETS) + threadIdx.x;
-        const uint4 c = *p;
-        *p = run;
-        run.x += c.x; run.y += c.y; run.z += c.z; run.w += c.w;
+        const uint4 c = reinterpret_cast<const uint4 *>(tile_hist + (size_t)t * SP_BUCKETS)[threadIdx.x];
+        reinterpret_cast<uint4 *>(tile_place + (size_t)t * SP_BUCKETS)[threadIdx.x] = run;
+        run.x += (c.x + pad) & ~pad; run.y += (c.y + pad) & ~pad; run.z += (c.z + pad) & ~pad; run.w += (c.w + pad) & ~pad;
+        tsum += (unsigned long long)c.x + c.y + c.z + c.w;
+    }
+    if (pad) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(FULL, tsum, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0 && tsum) atomicAdd(&s_true, tsum);
     }
     const uint4 v = run;   // the file's bucket totals
     const uint32_t mine = v.x + v.y + v.z + v.w;
@@ -194,10 +206,10 @@ sparse_tile_scan_kernel(uint32_t *__restrict__ tile_hist, const int *__restrict_
     bo[4 * threadIdx.x] = o4.x; bo[4 * threadIdx.x + 1] = o4.y; bo[4 * threadIdx.x + 2] = o4.z; bo[4 * threadIdx.x + 3] = o4.w;
     if (threadIdx.x == 1023) {
         bo[SP_BUCKETS] = ex + mine;
-        if (totals) totals[file_base + f] = (unsigned long long)(ex + mine);
+        if (totals) totals[file_base + f] = pad ? s_true : (unsigned long long)(ex + mine);   // (s_true: complete since the barriers above)
     }
     for (int t = ta; t < tb; t++) {   // + the bucket's start
-        uint4 *p = reinterpret_cast<uint4 *>(tile_hist + (size_t)t * SP_BUCKETS) + threadIdx.x;
+        uint4 *p = reinterpret_cast<uint4 *>(tile_place + (size_t)t * SP_BUCKETS) + threadIdx.x;
         uint4 c = *p;
         c.x += o4.x; c.y += o4.y; c.z += o4.z; c.w += o4.w;
         *p = c;
@@ -298,6 +310,336 @@ sparse_bucket_emit_kernel(const uint32_t *__restrict__ keys, const uint64_t *__r
             counts_out[o] = c;
         }
         pos += (unsigned long long)__popc(m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16 < 2k <= 24 (k = 9 .. 12): buckets of 65,536 codes, write-combined partition, histogram per (file, bucket)
+// ------------------------------------------------------------------------------------------------
+// What bounded the 4,096-bucket partition above was not its atomics but its stores: a warp's 32 codes go to 32 different
+// runs, i.e. 32 write requests of 4 bytes, and an SM hands the L2 about one request every four clocks whatever its size
+// (profiles/r02_v2_ncu_sparse.txt: 61 G stores/s, issue slots 6 % busy, DRAM writes 3.5 x the keys).  Here a code's leading
+// 2k - 16 bits number its bucket (<= 256 buckets) and only its low 16 bits are kept:
+//   sparse_wc_scatter_kernel   every WARP owns 16 two-byte slots per bucket in shared memory; a code goes to its bucket's
+//                              slots (shared-memory atomic), full groups of 8 leave as ONE 16-byte store -- 8 codes per
+//                              write request, and half the bytes.  A (tile, bucket) run starts at a multiple of 8 keys
+//                              (the scan pads); what is left in the slots at the tile's end, and whatever arrives at a full
+//                              bucket, is stored code by code from the run's END downwards: blocks and single codes meet
+//                              without a hole, the padding lies behind the run's count.
+//   sparse16_distinct_kernel   one CTA per (file, bucket): 65,536-bit map -> number of distinct codes
+//   sparse16_emit_kernel       one CTA per (file, bucket): two halves of 32,768 u32 bins (128 KB), each warp walks its
+//                              2,048 bins in order (count, scan over the warps, write): ascending (code, count) entries
+constexpr int SP16_SLOTS = 16;
+constexpr int SP16_THREADS_SCATTER = 256;   // 8 warps x 256 buckets x 16 slots x 2 bytes = 64 KB (+ fills and cursors): two CTAs per SM
+constexpr int SP16_THREADS_EMIT = 512;
+constexpr uint32_t SP16_MAX_BUCKETS = 256;
+constexpr size_t sp16_scatter_smem() {
+    return (size_t)(SP16_THREADS_SCATTER / 32) * SP16_MAX_BUCKETS * (SP16_SLOTS * sizeof(uint16_t) + sizeof(uint32_t)) + 2 * SP16_MAX_BUCKETS * sizeof(uint32_t);
+}
+
+struct SparseEmitWC {
+    uint16_t *wbuf;     // this warp's [buckets][SP16_SLOTS]
+    uint32_t *fill;     // this warp's [buckets]: codes put into the slots since the bucket was last drained (may exceed the slots)
+    uint32_t *back;     // CTA: [buckets] end of the run's unwritten part (single codes are stored below it)
+    uint16_t *keys;     // the current file's key region
+    __device__ __forceinline__ void operator()(uint64_t canon) const {
+        const uint32_t b = (uint32_t)(canon >> 16);
+        const uint32_t slot = atomicAdd(fill + b, 1u);
+        if (slot < (uint32_t)SP16_SLOTS) wbuf[b * SP16_SLOTS + slot] = (uint16_t)canon;
+        else keys[atomicSub(back + b, 1u) - 1u] = (uint16_t)canon;
+    }
+};
+struct SparseWcSink {
+    SparseEmitWC e;
+    uint32_t *front;    // CTA: [buckets] where the run's next block of 8 goes
+    uint32_t nbuckets;
+    int k;
+    __device__ __forceinline__ void window(uint32_t hi, uint32_t lo, uint32_t n) const {   // (SparseSink::window)
+        const uint32_t hs = hi ^ ((hi >> 1) & 0x55555555u), ls = lo ^ ((lo >> 1) & 0x55555555u);
+        const uint64_t w = ((uint64_t)hs << 32) | ls;
+        const uint64_t rcw = digit_reverse64(~w);
+        const uint64_t mask = (1ull << (2 * k)) - 1ull;
+        const int s0 = 64 - 2 * k;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (j < 15 || n == 16) {
+                const uint64_t F = (w >> (s0 - 2 * j)) & mask;
+                const uint64_t R = (rcw >> (2 * j)) & mask;
+                e(F < R ? F : R);
+            }
+        }
+    }
+    template <class Src>
+    __device__ __forceinline__ void walk(const Src src, uint64_t p0, uint64_t p1, bool in_hdr, bool at_ls) const {
+        fasta_walk_lane_canon(src, p0, p1, in_hdr, at_ls, k, e);
+    }
+    // All lanes, converged (fasta_process_range calls record() for every lane of every chunk before the chunk's k-mers are
+    // counted; the kernel calls it once more after the range): buckets that hold 8 codes or more give their first 8 (or 16)
+    // away as 16-byte stores, the rest moves to the front of the slots.  Lane l looks after the buckets l, l + 32, ...
+    __device__ __forceinline__ void drain(bool all) const {
+        KF_SYNCWARP();
+        const int lane = threadIdx.x & 31;
+        for (uint32_t b = (uint32_t)lane; b < nbuckets; b += 32) {
+            uint32_t n = e.fill[b];
+            if (n > (uint32_t)SP16_SLOTS) n = SP16_SLOTS;
+            if (n < 8u && !(all && n > 0u)) continue;
+            uint4 *slots = reinterpret_cast<uint4 *>(e.wbuf + b * SP16_SLOTS);
+            uint32_t done = 0;
+            while (n - done >= 8u) {
+                const uint32_t at = atomicAdd(front + b, 8u);
+                *reinterpret_cast<uint4 *>(e.keys + at) = slots[done >> 3];
+                done += 8u;
+            }
+            uint32_t rest = n - done;   // < 8
+            if (all) {
+                for (uint32_t i = 0; i < rest; i++) e.keys[atomicSub(e.back + b, 1u) - 1u] = e.wbuf[b * SP16_SLOTS + done + i];
+                rest = 0;
+            } else if (done == 8u && rest) {
+                slots[0] = slots[1];
+            }
+            e.fill[b] = rest;
+        }
+        KF_SYNCWARP();
+    }
+    __device__ __forceinline__ void record(size_t, bool, uint32_t, uint32_t, uint32_t) const { drain(false); }
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+template <> struct sink_takes_window<SparseWcSink> { static constexpr bool value = true; };
+template <> struct sink_walks_itself<SparseWcSink> { static constexpr bool value = true; };
+template <> struct sink_records_lanes<SparseWcSink> { static constexpr bool value = true; };
+
+// tile_cnt / tile_place [tiles][SP_BUCKETS]: a (tile, bucket) run's number of codes and its place in the file's key region
+// (multiple of 8); keys16: the batch's key workspace, file f at kbase[f] (multiple of 8).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
+sparse_wc_scatter_kernel(const uint8_t *__restrict__ arena, const Tile *__restrict__ tiles, const int *__restrict__ cta_begin, int k,
+                         uint32_t file_base, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_place,
+                         uint16_t *__restrict__ keys16, const uint64_t *__restrict__ kbase) {
+    constexpr int NWARPS = THREADS / 32;
+    KF_DYN_SMEM(uint32_t, wc_smem);
+    const uint32_t NBK = 1u << (2 * k - 16);
+    uint32_t *front = wc_smem, *back = front + SP16_MAX_BUCKETS;
+    uint32_t *fill_all = back + SP16_MAX_BUCKETS;
+    uint16_t *wbuf_all = reinterpret_cast<uint16_t *>(fill_all + NWARPS * SP16_MAX_BUCKETS);
+    const int warp = threadIdx.x >> 5;
+    SparseWcSink sink;
+    sink.k = k;
+    sink.nbuckets = NBK;
+    sink.front = front;
+    sink.e.back = back;
+    sink.e.fill = fill_all + warp * SP16_MAX_BUCKETS;
+    sink.e.wbuf = wbuf_all + (size_t)warp * SP16_MAX_BUCKETS * SP16_SLOTS;
+    sink.e.keys = nullptr;
+    for (uint32_t i = threadIdx.x; i < NWARPS * SP16_MAX_BUCKETS; i += THREADS) fill_all[i] = 0;
+    const int t1 = cta_begin[blockIdx.x + 1];
+    for (int t = cta_begin[blockIdx.x]; t < t1; ++t) {
+        const Tile T = tiles[t];
+        for (uint32_t b = threadIdx.x; b < NBK; b += THREADS) {
+            const uint32_t pl = tile_place[(size_t)t * SP_BUCKETS + b];
+            front[b] = pl;
+            back[b] = pl + tile_cnt[(size_t)t * SP_BUCKETS + b];
+        }
+        __syncthreads();
+        sink.e.keys = keys16 + kbase[T.file - file_base];
+        const uint32_t cpw = (T.n_chunks + NWARPS - 1) / NWARPS;
+        const uint32_t c0 = T.first_chunk + (uint32_t)warp * cpw;
+        const uint32_t cend = T.first_chunk + T.n_chunks;
+        const uint32_t c1 = (c0 + cpw < cend) ? c0 + cpw : cend;
+        if (c0 < c1) fasta_process_range<12, false, 3>(GlobalSrc{arena}, c0, c1, T.file_chunk0, sink);
+        sink.drain(true);
+        __syncthreads();
+    }
+}
+
+// keys of (file f, bucket b): the runs (tile, b) of the file's tiles
+__global__ void __launch_bounds__(256)
+sparse16_distinct_kernel(const uint16_t *__restrict__ keys16, const uint64_t *__restrict__ kbase, const int *__restrict__ file_t0,
+                         const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_place, uint32_t nbuckets,
+                         uint32_t *__restrict__ nd /* [nf][SP_BUCKETS], zeroed */) {
+    __shared__ uint32_t bitmap[2048];
+    __shared__ uint32_t s_n[2];   // distinct codes below / from 32,768 (the emit kernel takes the two halves in separate CTAs)
+    const uint32_t f = blockIdx.x / nbuckets, b = blockIdx.x - f * nbuckets;
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) bitmap[i] = 0;
+    if (threadIdx.x < 2) s_n[threadIdx.x] = 0;
+    __syncthreads();
+    const uint16_t *fk = keys16 + kbase[f];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int t = file_t0[f] + warp; t < file_t0[f + 1]; t += nwarps) {   // a warp per run, eight keys per 16-byte load
+        const uint32_t n = tile_cnt[(size_t)t * SP_BUCKETS + b];
+        const uint16_t *gk = fk + tile_place[(size_t)t * SP_BUCKETS + b];
+        const uint32_t n8 = n & ~7u;
+        for (uint32_t i = 8u * (uint32_t)lane; i < n8; i += 256u) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(gk + i);
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t v0 = w4[j] & 0xFFFFu, v1 = w4[j] >> 16;
+                atomicOr(bitmap + (v0 >> 5), 1u << (v0 & 31u));
+                atomicOr(bitmap + (v1 >> 5), 1u << (v1 & 31u));
+            }
+        }
+        if (n8 + (uint32_t)lane < n) {
+            const uint32_t v = gk[n8 + lane];
+            atomicOr(bitmap + (v >> 5), 1u << (v & 31u));
+        }
+    }
+    __syncthreads();
+    uint32_t c0 = 0, c1 = 0;
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) { c0 += (uint32_t)__popc(bitmap[i]); c1 += (uint32_t)__popc(bitmap[1024 + i]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c0 += __shfl_xor_sync(FULL, c0, o); c1 += __shfl_xor_sync(FULL, c1, o); }
+    if ((threadIdx.x & 31) == 0) { if (c0) atomicAdd(&s_n[0], c0); if (c1) atomicAdd(&s_n[1], c1); }
+    __syncthreads();
+    if (threadIdx.x < 2) nd[(size_t)f * SP_BUCKETS + 2 * b + threadIdx.x] = s_n[threadIdx.x];
+}
+
+// One CTA per (file, bucket, half of the bucket's code range): 32,768 codes in 16,384 words of two u16 counters (code c of
+// the half: word c >> 1, half word c & 1) = 64 KB, three CTAs per SM.  One pass over the bucket's keys (a warp per
+// (tile, bucket) run, eight keys per 16-byte load; the other half's keys are skipped).  A counter that reaches 65,536
+// carries or wraps: the sum of all counters then differs from the number of keys counted and the half is done again
+// exactly, with u32 bins in two quarters (poly-A stretches; tests force it).  Then every warp walks its words in order,
+// 128 per round (four words = eight codes per lane): count the non-zero counters, scan over the warps, write ascending
+// (code, count) entries.  ooff / nd are indexed by 2 * bucket + half.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 3)
+sparse16_emit_kernel(const uint16_t *__restrict__ keys16, const uint64_t *__restrict__ kbase, const int *__restrict__ file_t0,
+                     const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ tile_place, uint32_t nbuckets,
+                     const uint32_t *__restrict__ ooff /* [nf][SP_BUCKETS] */, const unsigned long long *__restrict__ out_base /* [nf] */,
+                     unsigned long long *__restrict__ codes_out, uint32_t *__restrict__ counts_out) {
+    constexpr int NWARPS = THREADS / 32;
+    constexpr uint32_t NWORDS = 16384;
+    constexpr uint32_t PER_WARP = NWORDS / NWARPS;   // words a warp walks
+    static_assert(PER_WARP % 128 == 0, "whole rounds of 128 words");
+    KF_DYN_SMEM(uint32_t, bins);                                  // NWORDS u32
+    __shared__ uint32_t s_w[3 * NWARPS];                          // per warp: non-zero counters | sum of all counters | keys counted
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t item = blockIdx.x >> 1, half = blockIdx.x & 1u;
+    const uint32_t f = item / nbuckets, b = item - f * nbuckets;
+    const uint16_t *fk = keys16 + kbase[f];
+    const int ta = file_t0[f], tb = file_t0[f + 1];
+    const unsigned long long pos = out_base[f] + (unsigned long long)ooff[(size_t)f * SP_BUCKETS + 2 * b + half];
+    uint32_t total = 0;
+    for (int t = ta; t < tb; t++) total += tile_cnt[(size_t)t * SP_BUCKETS + b];
+    if (total == 0) return;   // (the whole CTA)
+    uint4 *b4 = reinterpret_cast<uint4 *>(bins);
+    for (uint32_t i = threadIdx.x; i < NWORDS / 4; i += THREADS) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    uint32_t nkeys = 0;   // keys of my half this thread has counted
+    auto count = [&](uint32_t v) {
+        if ((v >> 15) == half) { atomicAdd(bins + ((v & 0x7FFFu) >> 1), 1u << ((v & 1u) << 4)); nkeys++; }
+    };
+    for (int t = ta + warp; t < tb; t += NWARPS) {   // a warp per run; the run starts at a multiple of 8 keys
+        const uint32_t n = tile_cnt[(size_t)t * SP_BUCKETS + b];
+        const uint16_t *gk = fk + tile_place[(size_t)t * SP_BUCKETS + b];
+        const uint32_t n8 = n & ~7u;
+        for (uint32_t i = 8u * (uint32_t)lane; i < n8; i += 256u) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(gk + i);
+            count(q.x & 0xFFFFu); count(q.x >> 16); count(q.y & 0xFFFFu); count(q.y >> 16);
+            count(q.z & 0xFFFFu); count(q.z >> 16); count(q.w & 0xFFFFu); count(q.w >> 16);
+        }
+        if (n8 + (uint32_t)lane < n) count((uint32_t)gk[n8 + lane]);
+    }
+    __syncthreads();
+    const uint4 *wb = reinterpret_cast<const uint4 *>(bins + (size_t)warp * PER_WARP);
+    uint32_t nz = 0, sum = 0;
+    for (uint32_t r = 0; r < PER_WARP / 128; r++) {
+        const uint4 v = wb[r * 32 + lane];
+        const uint32_t c4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            nz += ((c4[j] & 0xFFFFu) != 0u) + ((c4[j] >> 16) != 0u);
+            sum += (c4[j] & 0xFFFFu) + (c4[j] >> 16);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { nz += __shfl_xor_sync(FULL, nz, o); sum += __shfl_xor_sync(FULL, sum, o); nkeys += __shfl_xor_sync(FULL, nkeys, o); }
+    if (lane == 0) { s_w[warp] = nz; s_w[NWARPS + warp] = sum; s_w[2 * NWARPS + warp] = nkeys; }
+    __syncthreads();
+    uint32_t before = 0, all_sum = 0, all_keys = 0;
+#pragma unroll
+    for (int w = 0; w < NWARPS; w++) {
+        if (w < warp) before += s_w[w];
+        all_sum += s_w[NWARPS + w];
+        all_keys += s_w[2 * NWARPS + w];
+    }
+    const unsigned long long code0 = ((unsigned long long)b << 16) | ((unsigned long long)half << 15);
+    if (all_sum == all_keys) {
+        if (nz == 0u) return;   // (uniform over the warp; no barrier follows)
+        unsigned long long wp = pos + before;
+        const unsigned long long hi = code0 | (unsigned long long)(2u * warp * PER_WARP);
+        for (uint32_t r = 0; r < PER_WARP / 128; r++) {
+            const uint4 v = wb[r * 32 + lane];
+            const uint32_t c[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) mine += c[j] != 0u;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+            unsigned long long o = wp + (incl - mine);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (c[j]) {
+                    codes_out[o] = hi | (unsigned long long)(r * 256 + lane * 8 + j);
+                    counts_out[o] = c[j];
+                    o++;
+                }
+            }
+            wp += __shfl_sync(FULL, incl, 31);
+        }
+        return;
+    }
+    // ---- a 16-bit counter carried or wrapped: the half again with u32 bins, 16,384 codes at a time ----
+    __syncthreads();
+    unsigned long long qpos = pos;
+    for (uint32_t quarter = 0; quarter < 2; quarter++) {
+        for (uint32_t i = threadIdx.x; i < NWORDS / 4; i += THREADS) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        for (int t = ta; t < tb; t++) {
+            const uint32_t n = tile_cnt[(size_t)t * SP_BUCKETS + b];
+            const uint16_t *gk = fk + tile_place[(size_t)t * SP_BUCKETS + b];
+            for (uint32_t i = threadIdx.x; i < n; i += THREADS) {
+                const uint32_t v = gk[i];
+                if ((v >> 14) == 2u * half + quarter) atomicAdd(bins + (v & 0x3FFFu), 1u);
+            }
+        }
+        __syncthreads();
+        uint32_t qnz = 0;
+        for (uint32_t r = 0; r < PER_WARP / 128; r++) {
+            const uint4 v = wb[r * 32 + lane];
+            qnz += (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qnz += __shfl_xor_sync(FULL, qnz, o);
+        if (lane == 0) s_w[warp] = qnz;
+        __syncthreads();
+        uint32_t qbefore = 0, qall = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; w++) { const uint32_t c = s_w[w]; if (w < warp) qbefore += c; qall += c; }
+        unsigned long long wp = qpos + qbefore;
+        const unsigned long long hi = code0 | ((unsigned long long)quarter << 14) | (unsigned long long)(warp * PER_WARP);
+        if (qnz) {
+            for (uint32_t r = 0; r < PER_WARP / 128; r++) {
+                const uint4 v = wb[r * 32 + lane];
+                const uint32_t c4[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t mine = (v.x != 0u) + (v.y != 0u) + (v.z != 0u) + (v.w != 0u);
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+                unsigned long long o = wp + (incl - mine);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (c4[j]) {
+                        codes_out[o] = hi | (unsigned long long)(r * 128 + lane * 4 + j);
+                        counts_out[o] = c4[j];
+                        o++;
+                    }
+                }
+                wp += __shfl_sync(FULL, incl, 31);
+            }
+        }
+        qpos += qall;
+        __syncthreads();
     }
 }
 

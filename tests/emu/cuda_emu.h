@@ -111,6 +111,7 @@ inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atomicOr(uint32_t *p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline uint32_t atomicSub(uint32_t *p, uint32_t v) { return __atomic_fetch_sub(p, v, __ATOMIC_RELAXED); }
 #define __shared__ static
 template <typename T>
 inline T __shfl_up_sync(unsigned, T v, int d) {

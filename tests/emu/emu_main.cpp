@@ -105,12 +105,19 @@ int main(int argc, char **argv) {
     if (mode == 3) {
         // sparse sort-and-run-length path, the launch sequence of kf_sparse_host.inc:sparse_run_batch (one sub-batch)
         const int thr = threads == 512 ? 64 : threads;
-        std::vector<uint64_t> kbase(n + 1, 0);
-        for (int f = 0; f < n; f++) kbase[f + 1] = kbase[f] + ((len[f] && arena[off[f]] == '>') ? len[f] : 0);
         std::vector<int> file_t0(n + 1, 0);
         { size_t t = 0; for (int f = 0; f < n; f++) { file_t0[f] = (int)t; while (t < tiles.size() && tiles[t].file == (uint32_t)f) t++; } file_t0[n] = (int)t; }
         const int R = 2 * k - SP_BUCKET_BITS;
         const bool hist_path = R <= SP_HIST_MAX_R && k <= 16;
+        const bool path16 = hist_path && 2 * k > 16 && 2 * k <= 24 && !getenv("KF_SPARSE_NO16");   // (kf_sparse_host.inc)
+        const uint32_t nbk16 = path16 ? 1u << (2 * k - 16) : 0u;
+        std::vector<uint64_t> kbase(n + 1, 0);
+        for (int f = 0; f < n; f++) {
+            kbase[f + 1] = kbase[f] + ((len[f] && arena[off[f]] == '>') ? len[f] : 0);
+            if (path16) kbase[f + 1] = (kbase[f + 1] + 8ull * nbk16 * (uint64_t)(file_t0[f + 1] - file_t0[f]) + 7ull) & ~7ull;
+        }
+        std::vector<uint32_t> tile_place((tiles.size() + 1) * SP_BUCKETS, 0xBEEFu);
+        const int bshift = path16 ? 16 : -1;
         uint32_t S = 1;
         while (S < SP_BUCKETS / 8 && (uint64_t)n * S < 16) S <<= 1;
         const uint32_t n_items = hist_path ? (uint32_t)n * SP_BUCKETS : (uint32_t)n * S;
@@ -122,20 +129,32 @@ int main(int argc, char **argv) {
             auto tile_pass = [&](auto modec) {
                 constexpr int M = decltype(modec)::value;
                 emu::launch(grid, thr, 0, [&]() {
-                    if (k > 16) { if (thr == 32) sparse_tile_kernel<M, KT, true, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data());
-                                  else sparse_tile_kernel<M, KT, true, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data()); }
-                    else { if (thr == 32) sparse_tile_kernel<M, KT, false, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data());
-                           else sparse_tile_kernel<M, KT, false, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data()); }
+                    if (k > 16) { if (thr == 32) sparse_tile_kernel<M, KT, true, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data(), bshift);
+                                  else sparse_tile_kernel<M, KT, true, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data(), bshift); }
+                    else { if (thr == 32) sparse_tile_kernel<M, KT, false, 32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data(), bshift);
+                           else sparse_tile_kernel<M, KT, false, 64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), keys.data(), kbase.data(), bshift); }
                 });
             };
             tile_pass(std::integral_constant<int, 0>());
-            emu::launch(n, 1024, 0, [&]() { sparse_tile_scan_kernel(tile_hist.data(), file_t0.data(), boff.data(), totals.data(), 0u); });
-            tile_pass(std::integral_constant<int, 1>());
+            emu::launch(n, 1024, 0, [&]() { sparse_tile_scan_kernel(tile_hist.data(), file_t0.data(), boff.data(), totals.data(), 0u, path16 ? 7u : 0u, path16 ? tile_place.data() : (uint32_t *)nullptr); });
+            std::vector<uint16_t> keys16(path16 ? kbase[n] + 64 : 0, (uint16_t)0x5A5A);
+            if (path16) emu::launch(grid, thr, sp16_scatter_smem(), [&]() {
+                if (thr == 32) sparse_wc_scatter_kernel<32>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), tile_place.data(), keys16.data(), kbase.data());
+                else sparse_wc_scatter_kernel<64>(arena.data(), tiles.data(), cta_begin.data(), k, 0u, tile_hist.data(), tile_place.data(), keys16.data(), kbase.data()); });
+            else tile_pass(std::integral_constant<int, 1>());
             std::vector<unsigned long long> codes;
             std::vector<uint32_t> cnts;
             std::vector<unsigned long long> row_off(n + 1, 0ull);
             if constexpr (sizeof(KT) == 4) {
-                if (hist_path) {
+                if (path16) {
+                    emu::launch(n * nbk16, 64, 0, [&]() { sparse16_distinct_kernel(keys16.data(), kbase.data(), file_t0.data(), tile_hist.data(), tile_place.data(), nbk16, nd.data()); });
+                    emu::launch(n, 1024, 0, [&]() { sparse_scan_distinct_kernel(nd.data(), ooff32.data(), nd_file.data()); });
+                    unsigned long long run = 0;
+                    for (int f = 0; f < n; f++) { out_base[f] = run; run += nd_file[f]; row_off[f + 1] = run; }
+                    codes.assign(run + 1, 0ull); cnts.assign(run + 1, 0u);
+                    emu::launch(2 * n * nbk16, 64, 16384 * 4, [&]() {
+                        sparse16_emit_kernel<64>(keys16.data(), kbase.data(), file_t0.data(), tile_hist.data(), tile_place.data(), nbk16, ooff32.data(), out_base.data(), codes.data(), cnts.data()); });
+                } else if (hist_path) {
                     emu::launch(n_items / SP_HIST_WARPS, 32 * SP_HIST_WARPS, 0, [&]() { sparse_bucket_distinct_kernel((const uint32_t *)keys.data(), kbase.data(), boff.data(), R, nd.data()); });
                     emu::launch(n, 1024, 0, [&]() { sparse_scan_distinct_kernel(nd.data(), ooff32.data(), nd_file.data()); });
                     unsigned long long run = 0;

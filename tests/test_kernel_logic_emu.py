@@ -229,6 +229,35 @@ def run_emu_sparse(k, threads, grid, tile_chunks, files):
     return res
 
 
+def test_emulated_sparse_16bit_buckets_fuzz(tmp_path, monkeypatch):
+    """k = 9 .. 12 on the sparse path: buckets of 65,536 codes, 16-bit keys, write-combined partition (per-warp slots,
+    blocks of 8 from a run's front, single codes from its end), 65,536-bit map and two halves of 32,768 bins per
+    (file, bucket).  A poly-A stretch overfills one bucket's slots within a chunk (single-code stores), counts above
+    65,535 need the u32 bins."""
+    for s, k in zip(range(950, 956), (12, 9, 11, 10, 12, 9)):
+        rng = random.Random(s)
+        files = []
+        for i in range(rng.randint(1, 2)):
+            p = str(tmp_path / ("w%d_%d.fa" % (s, i)))
+            data = rand_fasta(rng) if rng.random() < 0.5 else rand_fasta_grid(rng)
+            if s >= 954:
+                seq = "A" * 70001 + "ACGTTGCAAGGCTTAACCGGTTAA" * 40 + "T" * 300
+                data += (">poly\n" + "\n".join(seq[j:j + 80] for j in range(0, len(seq), 80)) + "\n").encode()
+            open(p, "wb").write(data)
+            files.append(p)
+        grid, thr, tile = rng.randint(1, 3), rng.choice([32, 64]), rng.choice([1, 3, 64])
+        res = run_emu_sparse(k, thr, grid, tile, files)
+        for f, (tot, codes, counts) in zip(files, res):
+            rc, rn, rt = o.sparse_counts_bytes(open(f, "rb").read(), k)
+            assert tot == rt, (s, k, f)
+            assert np.array_equal(codes, rc) and np.array_equal(counts, rn), (s, k, grid, thr, tile, f)
+    # the 4,096-bucket path stays behind KF_SPARSE_NO16 (and serves k = 6 .. 8)
+    monkeypatch.setenv("KF_SPARSE_NO16", "1")
+    res = run_emu_sparse(12, 32, 2, 3, files[:1])
+    rc, rn, rt = o.sparse_counts_bytes(open(files[0], "rb").read(), 12)
+    assert res[0][0] == rt and np.array_equal(res[0][1], rc) and np.array_equal(res[0][2], rn)
+
+
 def test_emulated_sparse_sort_rle_fuzz(tmp_path):
     """The sparse (sort-and-run-length) path for large k: two extraction passes (bucket histogram, bucket scatter),
     per-bucket bitonic sort, run-length emit -- against the NumPy oracle's observed canonical k-mers, k = 6 .. 31
