@@ -302,29 +302,34 @@ def other_configs(engine, dev, threads, steps=5):
               kern_ms, arena.file_bytes + GL * V * 12, "count_fasta_part_kernel<%d> (partitioned shared-memory histogram) + tiled fold" % k,
               4 * 5e6, dt, "4 of the genomes, oracle/kf_oracle.c", ok)
         del counts
-    # k = 12: sparse (observed canonical k-mers, sorted) -- the sort-and-run-length path
-    GS = 64
-    arena_s = engine.DeviceArena(fa[:GS], device=dev)
-    ms = []
-    for _ in range(3):
-        torch.cuda.synchronize(dev)
+    # k = 11, 12: sparse (observed canonical k-mers, sorted) -- the sort-and-run-length path on the same 296 genomes; parity
+    # of two genomes' entries against the C oracle (fetched from a small arena of their own)
+    arena_s = engine.DeviceArena(fa[:2], device=dev)
+    for k in (11, 12):
+        ms = []
+        for _ in range(3):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            _, _, row_off, _, _ = engine.sparse_count_device(arena, k, fetch=False)
+            torch.cuda.synchronize(dev)
+            ms.append((time.perf_counter() - t0) * 1e3)
+        entries = int(row_off[-1])
+        engine.sparse_release()
+        codes, cnts, row_off2, totals, _ = engine.sparse_count_device(arena_s, k)
         t0 = time.perf_counter()
-        _, _, row_off, _, _ = engine.sparse_count_device(arena_s, 12, fetch=False)
-        torch.cuda.synchronize(dev)
-        ms.append((time.perf_counter() - t0) * 1e3)
-    codes, cnts, row_off, totals, _ = engine.sparse_count_device(arena_s, 12)
-    t0 = time.perf_counter()
-    rc, rn, rt = c_oracle.count_sparse(fa[0].tobytes(), 12)
-    dt = time.perf_counter() - t0
-    a, e = int(row_off[0]), int(row_off[1])
-    ok = rt == int(totals[0]) and np.array_equal(codes[a:e], rc) and np.array_equal(cnts[a:e].astype(np.uint64), rn)
-    entries = int(row_off[-1])
-    engine.sparse_release()
-    step_ms = min(ms[1:])
-    entry("large_k12_sparse", "BASELINE.json configs[4]: %d synthetic genomes x 5 Mbp, k=12, sparse (code, count) output sorted by code" % GS,
-          GS * 5e6, step_ms, step_ms, arena_s.file_bytes + entries * 12, "sparse_extract / sparse_sort / sparse_emit (whole call, host-timed: it "
-          "synchronises to size the output)", 5e6, dt, "1 genome, 1 thread (sort + run lengths), oracle/kf_oracle.c", ok, entries=entries)
-    out["large_k12_sparse"]["cpu_baseline"]["cores"] = 1
+        rc, rn, rt = c_oracle.count_sparse(fa[0].tobytes(), k)
+        dt = time.perf_counter() - t0
+        a, e = int(row_off2[0]), int(row_off2[1])
+        ok = rt == int(totals[0]) and np.array_equal(codes[a:e], rc) and np.array_equal(cnts[a:e].astype(np.uint64), rn) and \
+            int(row_off[1] - row_off[0]) == e - a
+        engine.sparse_release()
+        step_ms = min(ms[1:])
+        name = "large_k%d_sparse" % k
+        entry(name, "BASELINE.json configs[4]: %d synthetic genomes x 5 Mbp, k=%d, sparse (code, count) output sorted by code" % (GL, k),
+              GL * 5e6, step_ms, step_ms, arena.file_bytes + entries * 12, "sparse_tile / sparse_wc_scatter / sparse16_distinct / sparse16_emit "
+              "(whole call, host-timed: it synchronises once per sub-batch to size the output)", 5e6, dt,
+              "1 genome, 1 thread (sort + run lengths), oracle/kf_oracle.c", ok, entries=entries)
+        out[name]["cpu_baseline"]["cores"] = 1
     del arena, arena_s, fa
     return out
 

@@ -523,7 +523,7 @@ def check_sparse(eng, bufs, k, **kw):
     return codes, counts, row_off
 
 
-@pytest.mark.parametrize("k", [6, 7, 11, 12, 15, 16, 17, 21, 31])
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 17, 21, 31])
 def test_sparse_counts_vs_c_oracle(eng, toy_inputs, k):
     """kf_sparse_count: observed canonical k-mers, ascending by code, against the C oracle (sort + run lengths of the
     rolling canonical mers): toy genomes, fuzz files (N runs, lower case, IUPAC, CRLF, blank lines, ragged widths),
@@ -561,7 +561,7 @@ def test_sparse_synthetic_genomes_k21_and_skewed_buckets(eng):
     bufs = [kfsynth.synth_fasta(7, i, 5_000_000) for i in range(3)]
     seq = "A" * 400000 + "ACGTTGCA" * 30000 + "N" * 7 + "AAAAAAAAAAAAC" * 20000
     bufs.append(np.frombuffer((">low\n" + "\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + "\n").encode(), dtype=np.uint8))
-    for k in (12, 21):
+    for k in (12, 10, 21):   # (k = 10, 12: the poly-A run overflows the packed 16-bit counters of its bucket -> exact u32 redo)
         check_sparse(eng, bufs, k)
     eng.sparse_release()
 
