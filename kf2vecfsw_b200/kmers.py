@@ -42,11 +42,13 @@ def kmer_matrix_sparse(codes: np.ndarray, counts: np.ndarray, k: int) -> np.ndar
     return mat
 
 
-_BATCH_BYTES = 1 << 30   # files are counted in batches of about this many input bytes (one sparse call each)
+_BATCH_BYTES = 1 << 30   # files are counted in batches of about this many input bytes (one call each)
+_DENSE_MAX_K = 10        # up to here the dense canonical row is the faster way to the observed k-mers (k = 7, the default:
+                         # 2.7 Tbases/s against 0.03 on the sparse path; k = 10: 0.14 against 0.13; a row is 4 MB at k = 10)
 
 
 def kmer_matrices(paths, k: int):
-    """Yields (path, matrix | None, status) per file.  k >= 6 goes through the sparse sort-and-run-length path
+    """Yields (path, matrix | None, status) per file.  k >= 11 goes through the sparse sort-and-run-length path
     (``kf_sparse_count``: any k up to 31, the reference's -k range, main.py:81-82), smaller k through the dense rows."""
     paths = list(paths)
     i = 0
@@ -56,7 +58,7 @@ def kmer_matrices(paths, k: int):
             nbytes += os.path.getsize(paths[j])
             j += 1
         bufs = [np.fromfile(p, dtype=np.uint8) for p in paths[i:j]]
-        if k >= engine.KF_SPARSE_MIN_K:
+        if k > _DENSE_MAX_K:
             codes, counts, row_off, _, status = engine.sparse_count(bufs, k)
             for t, p in enumerate(paths[i:j]):
                 a, b = int(row_off[t]), int(row_off[t + 1])
