@@ -500,6 +500,10 @@ sparse16_distinct_kernel(const uint16_t *__restrict__ keys16, const uint64_t *__
 // exactly, with u32 bins in two quarters (poly-A stretches; tests force it).  Then every warp walks its words in order,
 // 128 per round (four words = eight codes per lane): count the non-zero counters, scan over the warps, write ascending
 // (code, count) entries.  ooff / nd are indexed by 2 * bucket + half.
+__device__ __forceinline__ uint32_t sp16_nonzero_halves(uint32_t w) {   // how many of the two u16 halves of w are non-zero
+    return (uint32_t)__popc((((w & 0x7FFF7FFFu) + 0x7FFF7FFFu) | w) & 0x80008000u);
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 3)
 sparse16_emit_kernel(const uint16_t *__restrict__ keys16, const uint64_t *__restrict__ kbase, const int *__restrict__ file_t0,
@@ -547,7 +551,7 @@ sparse16_emit_kernel(const uint16_t *__restrict__ keys16, const uint64_t *__rest
         const uint32_t c4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            nz += ((c4[j] & 0xFFFFu) != 0u) + ((c4[j] >> 16) != 0u);
+            nz += sp16_nonzero_halves(c4[j]);
             sum += (c4[j] & 0xFFFFu) + (c4[j] >> 16);
         }
     }
@@ -565,23 +569,26 @@ sparse16_emit_kernel(const uint16_t *__restrict__ keys16, const uint64_t *__rest
     const unsigned long long code0 = ((unsigned long long)b << 16) | ((unsigned long long)half << 15);
     if (all_sum == all_keys) {
         if (nz == 0u) return;   // (uniform over the warp; no barrier follows)
-        unsigned long long wp = pos + before;
+        // (32-bit offsets from the half bucket's first entry: a half holds at most 32,768 entries)
+        unsigned long long *const co = codes_out + pos;
+        uint32_t *const no = counts_out + pos;
+        uint32_t wp = before;
         const unsigned long long hi = code0 | (unsigned long long)(2u * warp * PER_WARP);
         for (uint32_t r = 0; r < PER_WARP / 128; r++) {
             const uint4 v = wb[r * 32 + lane];
-            const uint32_t c[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
-            uint32_t mine = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) mine += c[j] != 0u;
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t mine = sp16_nonzero_halves(v.x) + sp16_nonzero_halves(v.y) + sp16_nonzero_halves(v.z) + sp16_nonzero_halves(v.w);
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-            unsigned long long o = wp + (incl - mine);
+            uint32_t o = wp + (incl - mine);
+            const uint32_t cbase = r * 256 + (uint32_t)lane * 8;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                if (c[j]) {
-                    codes_out[o] = hi | (unsigned long long)(r * 256 + lane * 8 + j);
-                    counts_out[o] = c[j];
+                const uint32_t c = (j & 1) ? w4[j >> 1] >> 16 : w4[j >> 1] & 0xFFFFu;
+                if (c) {
+                    co[o] = hi | (unsigned long long)(cbase + j);
+                    no[o] = c;
                     o++;
                 }
             }
