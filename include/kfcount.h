@@ -163,6 +163,11 @@ int kf_sparse_count_device(const uint8_t *d_arena, size_t arena_bytes, const uin
  * entries back to back in file order, row_off_out [n + 1] where each file's begin (any may be NULL). */
 int64_t kf_sparse_total_entries(void);
 int kf_sparse_fetch(uint64_t *codes_out, uint32_t *counts_out, uint64_t *row_off_out);
+/* The FSW fork's feature matrix of one file of the last result (kf2vec/main.py:147-169, get_kmers): out_host
+ * [n_distinct][k + 1] float32, row = the k-mer's k bases as codes A0 T1 C2 G3 (main.py:118) followed by count / divisor in
+ * fp32 -- the reference divides the float32 counts by their float32 sum (main.py:165-169), which the caller passes.  Rows in
+ * ascending code order (the reference: Jellyfish's hash order).  Expanded on the device, one copy to the host. */
+int kf_sparse_kmer_matrix(int file, float divisor, float *out_host);
 /* Device view of the last result: it is held as one chunk per internal sub-batch of files [file0, file1), whose entries
  * are the global entries [first_entry, first_entry + n_entries). */
 int kf_sparse_chunk_count(void);

@@ -810,4 +810,29 @@ sparse_emit_kernel(const KT *__restrict__ keys, const uint64_t *__restrict__ kba
     if (pending && threadIdx.x == 0) { codes_out[cur] = pend_key; counts_out[cur] = r1 - pend_start; }
 }
 
+// The FSW fork's k-mer feature matrix (kf2vec/main.py:147-169): one row per observed canonical k-mer -- its k bases as
+// float codes A0 T1 C2 G3 (main.py:118), then count / divisor in fp32 (the reference divides the float32 counts by their
+// float32 sum: the caller passes that sum).  One thread per matrix element: coalesced stores.
+__global__ void __launch_bounds__(256)
+sparse_kmer_matrix_kernel(const unsigned long long *__restrict__ codes, const uint32_t *__restrict__ counts, unsigned long long n, int k,
+                          float divisor, float *__restrict__ out) {
+    const unsigned long long total = n * (unsigned long long)(k + 1);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long row = i / (unsigned long long)(k + 1);
+        const int col = (int)(i - row * (unsigned long long)(k + 1));
+        float v;
+        if (col < k) {
+            const uint32_t d = (uint32_t)(codes[row] >> (2 * (k - 1 - col))) & 3u;   // vocabulary digit A0 C1 G2 T3
+            v = (float)((0x1320u >> (4 * d)) & 0xFu);                                // -> A0 T1 C2 G3: 0, 2, 3, 1
+        } else {
+#ifdef KF_EMU
+            v = (float)counts[row] / divisor;
+#else
+            v = __fdiv_rn((float)counts[row], divisor);
+#endif
+        }
+        out[i] = v;
+    }
+}
+
 }  // namespace kf

@@ -90,6 +90,7 @@ def _load():
                                          ctypes.c_void_p]
     L.kf_sparse_total_entries.restype = ctypes.c_int64
     L.kf_sparse_fetch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.kf_sparse_kmer_matrix.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
     L.kf_sparse_chunk.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_void_p]
     L.kf_set_sm_limit.argtypes = [ctypes.c_int]
@@ -250,6 +251,25 @@ def _sparse_fetch(n: int):
     row_off = np.zeros(n + 1, dtype=np.uint64)
     _check(L.kf_sparse_fetch(codes.ctypes.data, counts.ctypes.data, row_off.ctypes.data), "kf_sparse_fetch")
     return codes, counts, row_off
+
+
+def sparse_fetch_counts(n: int):
+    """Counts (u32 [E]) and row offsets (u64 [n + 1]) of the last sparse result; the codes stay on the device."""
+    L = _load()
+    total = int(L.kf_sparse_total_entries())
+    counts = np.empty(total, dtype=np.uint32)
+    row_off = np.zeros(n + 1, dtype=np.uint64)
+    _check(L.kf_sparse_fetch(None, counts.ctypes.data, row_off.ctypes.data), "kf_sparse_fetch")
+    return counts, row_off
+
+
+def sparse_kmer_matrix(file: int, k: int, n_rows: int, divisor) -> np.ndarray:
+    """The FSW feature matrix of file `file` of the last sparse result, expanded on the device (kf_sparse_kmer_matrix):
+    [n_rows, k + 1] float32 = k base codes A0 T1 C2 G3 + count / divisor (fp32)."""
+    mat = np.empty((n_rows, k + 1), dtype=np.float32)
+    if n_rows:
+        _check(_load().kf_sparse_kmer_matrix(int(file), ctypes.c_float(float(divisor)), mat.ctypes.data), "kf_sparse_kmer_matrix")
+    return mat
 
 
 def sparse_count(bufs: Sequence, k: int, fetch: bool = True):

@@ -59,10 +59,14 @@ def kmer_matrices(paths, k: int):
             j += 1
         bufs = [np.fromfile(p, dtype=np.uint8) for p in paths[i:j]]
         if k > _DENSE_MAX_K:
-            codes, counts, row_off, _, status = engine.sparse_count(bufs, k)
+            # the entries stay on the device; a file's matrix is expanded there (kf_sparse_kmer_matrix) and copied out once.
+            # The divisor is the reference's float32 sum of the float32 counts (main.py:165-169), taken with NumPy.
+            _, _, _, _, status = engine.sparse_count(bufs, k, fetch=False)
+            counts, row_off = engine.sparse_fetch_counts(len(bufs))
             for t, p in enumerate(paths[i:j]):
                 a, b = int(row_off[t]), int(row_off[t + 1])
-                yield p, (kmer_matrix_sparse(codes[a:b], counts[a:b], k) if b > a else None), int(status[t])
+                mat = engine.sparse_kmer_matrix(t, k, b - a, np.sum(counts[a:b].astype(np.float32))) if b > a else None
+                yield p, mat, int(status[t])
             engine.sparse_release()
         else:
             cnt, _, _, status = engine.count_buffers(bufs, k=k, want_freq=False)
