@@ -6,7 +6,9 @@
 // (A0 C1 G2 T3, first base most significant -- the vocabulary order of the dense path), which is what Jellyfish dumps
 // (in hash order).
 //
-// Pipeline over one batch of files (MSD radix partition by the code's leading 12 bits, then per bucket):
+// k = 9 .. 12 take the 16-bit-bucket pipeline further down (sparse_wc_scatter_kernel, sparse16_*): buckets of 65,536 codes,
+// 16-bit keys, write-combined partition -- 3 to 5 times the rate of what follows.  Everything else (k = 6 .. 8, k >= 13):
+// pipeline over one batch of files (MSD radix partition by the code's leading 12 bits, then per bucket):
 //   1. sparse_tile_kernel<0>      text -> canonical codes -> per-(tile, bucket) counts (shared-memory histogram per tile)
 //   2. sparse_tile_scan_kernel    per file: where every (tile, bucket) run goes inside the file's key region
 //   3. sparse_tile_kernel<1>      the same parse again (the tile comes from L2); every code is stored at its place
