@@ -768,7 +768,6 @@ sparse_emit_kernel(const KT *__restrict__ keys, const uint64_t *__restrict__ kba
     __shared__ uint32_t s_idx[THREADS];
     __shared__ unsigned long long s_key[THREADS];
     __shared__ uint32_t wsum[THREADS / 32];
-    __shared__ uint32_t s_h;
     const uint32_t item = blockIdx.x, f = item / S, seg = item - f * S;
     const uint32_t per = SP_BUCKETS / S;
     const uint32_t *bo = boff + (size_t)f * (SP_BUCKETS + 1);
