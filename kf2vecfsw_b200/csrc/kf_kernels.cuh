@@ -2171,10 +2171,12 @@ struct FqPairSink {
         const uint32_t pm = ok & (ok >> 1) & 0x5555u;          // even j: 7-mers j and j + 1 both count
         npairs += (uint32_t)__popc(pm);
         if (pm) {
+            // no branch per pair: a pair that does not count adds 0 (its address is a valid bin all the same)
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 const uint32_t off8 = kmer_off_at<8>(hi, lo, j);   // 4 * v
-                red_shared_add_if(hist16, hbase, (off8 >> 1) & 0x1FFFCu, ((off8 & 4u) << 14) | 1u, pm, 1u << j);
+                const uint32_t vm = 0u - ((pm >> j) & 1u);
+                red_shared_add(hist16, hbase, (off8 >> 1) & 0x1FFFCu, (((off8 & 4u) << 14) | 1u) & vm);
             }
         }
         uint32_t sm = ok & ~(pm | (pm << 1));                  // counted 7-mers outside a pair
@@ -2286,7 +2288,8 @@ __device__ __forceinline__ void fastq_lane_records(const uint8_t *__restrict__ a
             if (V0 | V1 | V2 | V3) {
                 inv = movemask4(nonzero_bytes(V0)) | (movemask4(nonzero_bytes(V1)) << 4) | (movemask4(nonzero_bytes(V2)) << 8) |
                       (movemask4(nonzero_bytes(V3)) << 12);
-                nlm = newline_mask16(w);
+                // a '\n' has bit 6 clear; a piece of letters only (bases and N: the usual reason to be here) holds none
+                if (~(w.x & w.y & w.z & w.w) & 0x40404040u) nlm = newline_mask16(w);
             }
             if (a + 16 > F1) { const uint32_t v = (uint32_t)(F1 - a); inv |= 0xFFFFu & ~((1u << v) - 1u); nlm |= 1u << v; }   // file end = line end
             nlm &= ~lead;
