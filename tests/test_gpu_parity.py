@@ -697,3 +697,30 @@ def test_count_buffers_sub_batch_pipeline(eng, toy_inputs, monkeypatch, k):
         assert np.array_equal(one[0][i], ref), i
         assert int(cut[2][i]) == int(ref.sum())
         assert np.array_equal(cut[1][i], one[1][i], equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [9, 12])
+def test_sparse_bucket_paths_agree_and_device_kmer_matrix(eng, toy_inputs, monkeypatch, k):
+    """k = 9 .. 12 have two independent device paths: buckets of 65,536 codes with 16-bit keys (write-combined partition, packed
+    counters) and the 4,096-bucket path behind KF_SPARSE_NO16 -- same entries.  kf_sparse_kmer_matrix (the FSW rows expanded
+    on the device) equals the NumPy expansion of the fetched entries bit for bit (main.py:147-169)."""
+    from kf2vecfsw_b200.kmers import kmer_matrix_sparse
+    rng = random.Random(77 + k)
+    bufs = [toy_inputs["G000830275sub"], rand_fasta(rng), toy_inputs["G000402355sub"], rand_fasta_grid(rng), kfsynth.synth_fasta(3, 1, 1_200_000).tobytes()]
+    a = eng.sparse_count(bufs, k)
+    mats = []
+    for i in range(len(bufs)):
+        lo, hi = int(a[2][i]), int(a[2][i + 1])
+        mats.append(eng.sparse_kmer_matrix(i, k, hi - lo, np.sum(a[1][lo:hi].astype(np.float32))))
+    monkeypatch.setenv("KF_SPARSE_NO16", "1")
+    b = eng.sparse_count(bufs, k)
+    monkeypatch.delenv("KF_SPARSE_NO16")
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    for i in range(len(bufs)):
+        lo, hi = int(a[2][i]), int(a[2][i + 1])
+        ref = kmer_matrix_sparse(a[0][lo:hi], a[1][lo:hi], k)
+        assert mats[i].dtype == np.float32 and mats[i].shape == ref.shape
+        assert np.array_equal(mats[i], ref), i
+    eng.sparse_release()
