@@ -286,7 +286,7 @@ def other_configs(engine, dev, threads, steps=5):
     dt, ref = cpu(fq[:2], 7)
     ok = np.array_equal(ref, counts[:2].cpu().numpy().astype(np.uint64)) and bool((engine.last_file_status(arena) == 0).all())
     entry("fastq_k7", "BASELINE.json configs[3]: %d FASTQ samples x %d reads x 150 bp (30x of 5 Mbp, N-containing), k=7" % (n_samples, n_reads),
-          n_samples * n_reads * 150, step_ms, kern_ms, arena.file_bytes + n_samples * V * 12, "count_fastq_smem_kernel<7>",
+          n_samples * n_reads * 150, step_ms, kern_ms, arena.file_bytes + n_samples * V * 12, "count_fastq_pairs_kernel (8-mer pair histogram; every lane chases its own records)",
           2 * n_reads * 150, dt, "2 of the samples, oracle/kf_oracle.c", ok, bytes_per_base=arena.file_bytes / (n_samples * n_reads * 150))
     del arena, counts, fq
     # ---- configs[4]: large-k sweep on 5 Mbp genomes ----
